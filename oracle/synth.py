@@ -1,0 +1,194 @@
+"""TEST INFRASTRUCTURE ONLY -- seeded synthetic checkpoints, tokenizer and audio.
+
+There is no network, so neither the trained WhisperSeg checkpoints nor the Whisper tokenizer
+files exist here.  This module builds, deterministically from a seed:
+
+  * an offline `WhisperTokenizer` with the *real* multilingual Whisper id layout for every id
+    the path touches (reference model.py:111-113: `<|i|>` tokens are appended after the 50364
+    base vocabulary, so `<|0|>` == 50364; digits '0'..'9' are GPT-2 byte tokens 15..24);
+  * a random-init `WhisperForConditionalGeneration` of a named architecture with
+    `max_source_positions = total_spec_columns/2` (reference model.py:79-84) and the config
+    contract the segmenter reads (model.py:590-595);
+  * a weight-shaping recipe so greedy decoding is content dependent
+    and terminates with EOS -- with HF's default init the decoder ignores the audio and every
+    downstream parity check would be vacuous;
+  * synthetic "vocal-like" audio.
+
+Both the reference arm (HF torch) and the CUDA path load the SAME checkpoint directory written
+by `save_checkpoint`, the way `WhisperSegmenter(model_path)` does (reference model.py:626-644).
+"""
+import json
+import os
+
+import numpy as np
+
+ARCHS = {
+    #         d_model layers heads ffn
+    "tiny":  (384, 4, 6, 1536),
+    "base":  (512, 6, 8, 2048),
+    "small": (768, 12, 12, 3072),
+    "large": (1280, 32, 20, 5120),
+}
+VOCAB_SIZE = 51865
+TOTAL_SPEC_COLUMNS = 1000
+ID_EOT = 50257
+ID_SOT = 50258
+ID_EN = 50259
+ID_NOTIMESTAMPS = 50363
+ID_TS0 = 50364            # "<|0|>"
+ID_DIGIT0 = 15            # "0" in the GPT-2 byte alphabet
+SPECIES = ["<|zebra_finch|>", "<|bengalese_finch|>", "<|mouse|>", "<|marmoset|>", "<|human|>",
+           "<|unknown|>", "<|animal|>"]
+
+
+def bytes_to_unicode():
+    """GPT-2 byte<->unicode alphabet (published algorithm, openai/gpt-2 encoder.py)."""
+    bs = list(range(ord("!"), ord("~") + 1)) + list(range(ord("\xa1"), ord("\xac") + 1)) + \
+        list(range(ord("\xae"), ord("\xff") + 1))
+    cs = bs[:]
+    n = 0
+    for b in range(256):
+        if b not in bs:
+            bs.append(b)
+            cs.append(256 + n)
+            n += 1
+    return dict(zip(bs, [chr(c) for c in cs]))
+
+
+def build_tokenizer():
+    from transformers import WhisperTokenizer
+    alphabet = list(bytes_to_unicode().values())
+    vocab = {ch: i for i, ch in enumerate(alphabet)}
+    i = 256
+    while len(vocab) < ID_EOT:
+        vocab["~f%d" % i] = len(vocab)
+        i += 1
+    tok = WhisperTokenizer(vocab=vocab, merges=[], pad_token="<|endoftext|>")
+    assert tok.convert_tokens_to_ids("<|endoftext|>") == ID_EOT
+    specials = ["<|startoftranscript|>", "<|en|>"] + ["<|lang%d|>" % k for k in range(1, 99)] + \
+        ["<|translate|>", "<|transcribe|>", "<|startoflm|>", "<|startofprev|>", "<|nocaptions|>",
+         "<|notimestamps|>"]
+    tok.add_tokens(specials, special_tokens=True)
+    # reference model.py:112-113
+    tok.add_tokens(["<|%d|>" % i for i in range(TOTAL_SPEC_COLUMNS + 1)], special_tokens=True)
+    tok.add_tokens(SPECIES, special_tokens=True)
+    assert tok.convert_tokens_to_ids(["<|startoftranscript|>", "<|en|>", "<|notimestamps|>", "<|0|>"]) == \
+        [ID_SOT, ID_EN, ID_NOTIMESTAMPS, ID_TS0]
+    return tok
+
+
+def allowed_token_ids():
+    """Ids the shaped model may emit: timestamps <|0|>..<|1000|>, digits, EOS."""
+    return sorted(list(range(ID_TS0, ID_TS0 + TOTAL_SPEC_COLUMNS + 1)) +
+                  list(range(ID_DIGIT0, ID_DIGIT0 + 10)) + [ID_EOT])
+
+
+def make_hf_model(arch="tiny", seed=0, shaped=True, cluster_codebook=None,
+                  default_segmentation_config=None, **shape_kw):
+    """Random-init HF Whisper of `arch` with the WhisperSeg config contract."""
+    import torch
+    from transformers import WhisperConfig, WhisperForConditionalGeneration
+    d, L, H, F = ARCHS[arch]
+    cfg = WhisperConfig(vocab_size=VOCAB_SIZE, num_mel_bins=80, d_model=d,
+                        encoder_layers=L, decoder_layers=L,
+                        encoder_attention_heads=H, decoder_attention_heads=H,
+                        encoder_ffn_dim=F, decoder_ffn_dim=F,
+                        max_source_positions=TOTAL_SPEC_COLUMNS // 2, max_target_positions=448,
+                        pad_token_id=ID_EOT, bos_token_id=ID_EOT, eos_token_id=ID_EOT,
+                        decoder_start_token_id=ID_SOT, dropout=0.0, attention_dropout=0.0,
+                        activation_dropout=0.0)
+    cfg.total_spec_columns = TOTAL_SPEC_COLUMNS
+    cfg.cluster_codebook = cluster_codebook if cluster_codebook is not None else {"vocal": 0, "b": 1}
+    cfg.species_codebook = {s[2:-2]: s for s in SPECIES}
+    if default_segmentation_config is not None:
+        cfg.default_segmentation_config = default_segmentation_config
+    torch.manual_seed(seed)
+    model = WhisperForConditionalGeneration(cfg)
+    model.eval()
+    if shaped:
+        shape_weights_(model, seed, **shape_kw)
+        allowed = set(allowed_token_ids())
+        sup = [i for i in range(VOCAB_SIZE) if i not in allowed]
+        model.generation_config.suppress_tokens = sup
+        model.generation_config.begin_suppress_tokens = None
+        model.config.suppress_tokens = sup
+        model.config.begin_suppress_tokens = None
+    return model
+
+
+def shape_weights_(model, seed, n_digits=2, eos_scale=2.0, qk_cross=3.0, qk_self=2.0, emb_std=0.05,
+                   digit_scale=2.5):
+    """SURVEY.md section 7.2-1 recipe (constants tuned so rows end with EOS at varied lengths)."""
+    import torch
+    g = torch.Generator().manual_seed(1000 + seed)
+    sd = model.state_dict()
+    with torch.no_grad():
+        for name, p in sd.items():
+            if "embed_positions" in name and "encoder" in name:
+                continue                                    # keep the sinusoid table
+            if "layer_norm" in name:
+                continue                                    # identity LN
+            if name.endswith("embed_tokens.weight") or name == "proj_out.weight":
+                continue
+            if name.endswith("decoder.embed_positions.weight"):
+                p.copy_(torch.randn(p.shape, generator=g))
+                continue
+            if p.dim() >= 2:
+                fan_in = p[0].numel()
+                p.copy_(torch.randn(p.shape, generator=g) / fan_in ** 0.5)
+                if name.endswith("q_proj.weight") or name.endswith("k_proj.weight"):
+                    p.mul_(qk_cross if "encoder_attn" in name else qk_self)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+        emb = model.model.decoder.embed_tokens.weight
+        emb.copy_(torch.randn(emb.shape, generator=g) * emb_std)
+        emb[ID_DIGIT0:ID_DIGIT0 + n_digits] *= digit_scale
+        emb[ID_EOT] *= eos_scale
+    model.tie_weights()
+
+
+def save_checkpoint(model, path, tokenizer=None):
+    os.makedirs(path, exist_ok=True)
+    model.save_pretrained(path, safe_serialization=True)
+    (tokenizer or build_tokenizer()).save_pretrained(path)
+    return path
+
+
+def synth_audio(seconds, sr, seed, band=(500.0, 8000.0), burst=(0.03, 0.25), gap=(0.02, 0.4)):
+    """Mono float32 in [-1,1]: harmonic chirp bursts over pink-ish noise at -30 dB."""
+    rng = np.random.default_rng(seed)
+    n = int(round(seconds * sr))
+    # pink-ish noise by 1/sqrt(f) shaping of white noise, chunked to bound memory
+    out = np.empty(n, dtype=np.float32)
+    chunk = 1 << 20
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        w = rng.standard_normal(m)
+        spec = np.fft.rfft(w)
+        f = np.arange(spec.shape[0], dtype=np.float64)
+        f[0] = 1.0
+        spec /= np.sqrt(f)
+        x = np.fft.irfft(spec, n=m)
+        x *= 0.0316 / (np.abs(x).max() + 1e-12)
+        out[s:s + m] = x.astype(np.float32)
+    t = 0.0
+    hi = min(band[1], 0.45 * sr)
+    while t < seconds:
+        t += rng.uniform(*gap)
+        dur = rng.uniform(*burst)
+        a, b = int(t * sr), min(n, int((t + dur) * sr))
+        if b <= a:
+            break
+        tt = np.arange(b - a, dtype=np.float64) / sr
+        f0 = rng.uniform(band[0], hi / 4)
+        f1 = f0 * rng.uniform(0.7, 1.4)
+        phase = 2 * np.pi * (f0 * tt + 0.5 * (f1 - f0) / max(dur, 1e-6) * tt * tt)
+        sig = np.zeros_like(tt)
+        for h in range(1, int(rng.integers(3, 6)) + 1):
+            if f0 * h < hi:
+                sig += np.sin(h * phase) / h
+        env = np.hanning(b - a)
+        out[a:b] += (0.5 * sig * env / (np.abs(sig).max() + 1e-12)).astype(np.float32)
+        t += dur
+    np.clip(out, -1.0, 1.0, out=out)
+    return out

@@ -1,0 +1,254 @@
+"""Token -> segment post-processing (host side, float64, bit-exact with the reference).
+
+This is integer/index/float64 work that the reference does in Python after generation; it must
+give *identical* results, so every float operation below is done in the reference's order
+(`int * sts * 2`, then `+ offset_time`, comparisons on un-rounded values, `np.round(., 3)` last,
++-n_fft/2/sr after rounding).  Citations are to /root/reference/model.py.
+
+Differences in *how* (not *what*):
+  * parsing works on decoded text with the same regex (model.py:120) -- the text is produced by
+    `tokens.TokenTable.decode`;
+  * multi-trial consolidation by clustering does not build the reference's O(n^2) Python-callable
+    distance matrix (model.py:305); neighbours are found with a sliding window over the onset-
+    sorted segments (a pair within `eps` must have |onset difference| <= 2*eps) and DBSCAN's
+    label assignment is replayed in sklearn's visiting order, which yields the same clusters;
+  * frame voting computes the per-frame mode with a counting pass instead of scipy.stats.mode.
+"""
+import re
+from math import ceil
+
+import numpy as np
+
+RATIO_DECODING_TIME_STEP_TO_SPEC_TIME_STEP = 2         # reference utils.py:5
+_SEGMENT_RE = re.compile(r"<\|([0-9]+)\|>(\d+?)<\|([0-9]+)\|>")
+
+
+def segments_from_text(text, spec_time_step, inverse_cluster_codebook):
+    """model.py:191-207 -> list of [onset, offset, cluster_name] (window-relative seconds)."""
+    found = []
+    for on_s, cid_s, off_s in _SEGMENT_RE.findall(text):
+        on = int(on_s) * spec_time_step * RATIO_DECODING_TIME_STEP_TO_SPEC_TIME_STEP
+        off = int(off_s) * spec_time_step * RATIO_DECODING_TIME_STEP_TO_SPEC_TIME_STEP
+        name = inverse_cluster_codebook.get(int(cid_s))
+        if name is None or off - on <= 0:
+            continue
+        found.append([on, off, name])
+    return found
+
+
+def _stitch_trial(per_window):
+    """Concatenate one trial's windows, fusing a segment cut by a window boundary (model.py:235-248)."""
+    acc = []
+    for segs in per_window:
+        if acc and segs and acc[-1][1] == segs[0][0] and acc[-1][2] == segs[0][2]:
+            acc[-1][1] = segs[0][1]
+            segs = segs[1:]
+        acc.extend(segs)
+    return acc
+
+
+def _dbscan_labels(onsets, offsets, eps, min_samples):
+    """DBSCAN on the metric (|d_onset| + |d_offset|)/2 (model.py:285-288, 305-309).
+
+    Same labels as sklearn's DBSCAN(metric="precomputed"): core test counts the point itself,
+    clusters are grown from unlabeled core points in index order with a LIFO frontier."""
+    n = len(onsets)
+    order = np.argsort(onsets, kind="stable")
+    so = onsets[order]
+    neigh = [None] * n
+    lo = 0
+    for r in range(n):
+        i = order[r]
+        while so[r] - so[lo] > 2 * eps + 1e-9:
+            lo += 1
+        hi = r
+        while hi + 1 < n and so[hi + 1] - so[r] <= 2 * eps + 1e-9:
+            hi += 1
+        cand = order[lo:hi + 1]
+        d = (np.abs(onsets[cand] - onsets[i]) + np.abs(offsets[cand] - offsets[i])) / 2
+        nb = cand[d <= eps]
+        nb.sort()
+        neigh[i] = nb
+    core = np.fromiter((len(nb) >= min_samples for nb in neigh), dtype=bool, count=n)
+    labels = np.full(n, -1, dtype=np.int64)
+    current = 0
+    for seed in range(n):
+        if labels[seed] != -1 or not core[seed]:
+            continue
+        stack, i = [], seed
+        while True:
+            if labels[i] == -1:
+                labels[i] = current
+                if core[i]:
+                    for v in neigh[i]:
+                        if labels[v] == -1:
+                            stack.append(v)
+            if not stack:
+                break
+            i = stack.pop()
+        current += 1
+    return labels
+
+
+def consolidate_trials_by_clustering(trials, eps, min_samples):
+    """model.py:291-337."""
+    onsets = np.array([t for tr in trials for t in tr["onset"]], dtype=np.float64)
+    offsets = np.array([t for tr in trials for t in tr["offset"]], dtype=np.float64)
+    names = [c for tr in trials for c in tr["cluster"]]
+    if len(onsets) == 0:
+        return {"onset": [], "offset": [], "cluster": []}
+    labels = _dbscan_labels(onsets, offsets, eps, min_samples)
+    merged = []
+    for label in range(int(labels.max()) + 1 if len(labels) else 0):
+        members = np.nonzero(labels == label)[0]
+        if len(members) == 0:
+            continue
+        tally = {}
+        for i in members:
+            tally[names[i]] = tally.get(names[i], 0) + 1
+        best = max(tally.values())
+        name = next(k for k, v in tally.items() if v == best)          # first-seen wins ties
+        merged.append((np.mean([onsets[i] for i in members]), np.mean([offsets[i] for i in members]), name))
+    merged.sort(key=lambda s: s[0])
+    return {"onset": [s[0] for s in merged], "offset": [s[1] for s in merged], "cluster": [s[2] for s in merged]}
+
+
+def consolidate_trials_by_voting(trials, time_per_frame, cluster_codebook):
+    """model.py:339-394."""
+    stamps = [t for tr in trials for t in list(tr["onset"]) + list(tr["offset"])]
+    if len(stamps) == 0 or len(stamps) % 2 != 0:
+        return {"onset": [], "offset": [], "cluster": []}
+    t_min, t_max = np.min(stamps), np.max(stamps)
+    n_frames = int(np.round((t_max - t_min) / time_per_frame))
+    grid = np.full((len(trials), n_frames), -1, dtype=np.int64)
+    for r, tr in enumerate(trials):
+        for on, off, name in zip(tr["onset"], tr["offset"], tr["cluster"]):
+            a = int(np.round((on - t_min) / time_per_frame))
+            b = int(np.round((off - t_min) / time_per_frame))
+            grid[r, a:b] = cluster_codebook[name]
+    # per-frame mode, smallest value on ties (scipy.stats.mode semantics)
+    values = np.unique(grid)
+    counts = np.stack([(grid == v).sum(axis=0) for v in values], axis=0) if n_frames else np.zeros((len(values), 0))
+    voted = values[np.argmax(counts, axis=0)] if n_frames else np.zeros(0, dtype=np.int64)
+    edges = np.nonzero(np.diff(np.concatenate([[-1], voted, [-1]])) != 0)[0]
+    inverse = {v: k for k, v in cluster_codebook.items()}
+    ons, offs, names = [], [], []
+    for a, b in zip(edges[:-1], edges[1:]):
+        cid = int(np.round(np.mean(voted[a:b].astype(np.float64))))
+        if cid == -1:
+            continue
+        ons.append(a * time_per_frame + t_min)
+        offs.append(b * time_per_frame + t_min)
+        names.append(inverse[cid])
+    return {"onset": ons, "offset": offs, "cluster": names}
+
+
+def parse_generation(texts, windows, min_segment_length, audio_duration, spec_time_step, num_trials, eps,
+                     time_per_frame_for_voting, consolidation_method, cluster_codebook, precision_bits=3):
+    """model.py:210-281.  `windows[i]` = (trial_id, offset_time, ...) in generation order."""
+    inverse = {v: k for k, v in cluster_codebook.items()}
+    by_trial = {}
+    for text, win in zip(texts, windows):
+        trial_id, offset_time = win[0], win[1]
+        segs = segments_from_text(text, spec_time_step, inverse)
+        for s in segs:
+            s[0] += offset_time
+            s[1] += offset_time
+        by_trial.setdefault(trial_id, []).append(segs)
+    trials = []
+    for per_window in by_trial.values():
+        segs = _stitch_trial(per_window)
+        for s in segs:
+            s[0] = max(0, s[0])
+            s[1] = min(s[1], audio_duration)
+        segs.sort(key=lambda s: s[0])
+        segs = [s for s in segs if s[1] - s[0] >= min_segment_length]
+        trials.append({"onset": [s[0] for s in segs], "offset": [s[1] for s in segs], "cluster": [s[2] for s in segs]})
+    if num_trials == 1:
+        final = trials[0]
+    elif consolidation_method == "clustering":
+        final = consolidate_trials_by_clustering(trials, eps, max(2, int(ceil(num_trials * 0.5))))
+    else:
+        final = consolidate_trials_by_voting(trials, time_per_frame_for_voting, cluster_codebook)
+    final["onset"] = [float(np.round(t, precision_bits)) for t in final["onset"]]
+    final["offset"] = [float(np.round(t, precision_bits)) for t in final["offset"]]
+    return final
+
+
+def correct_fft_blur_and_dedupe(prediction, sr, n_fft):
+    """model.py:439-468: shrink each segment by n_fft/2/sr per side, then drop exact duplicates."""
+    delta = n_fft / 2 / sr
+    rows = []
+    for on, off, name in zip(prediction["onset"], prediction["offset"], prediction["cluster"]):
+        a, b = on + delta, off - delta
+        if a > b:
+            a = b = (on + off) / 2
+        rows.append((a, b, name))
+    rows.sort(key=lambda r: r[0])
+    out = {"onset": [], "offset": [], "cluster": []}
+    for a, b, name in rows:
+        if out["onset"] and a == out["onset"][-1] and b == out["offset"][-1] and name == out["cluster"][-1]:
+            continue
+        out["onset"].append(a)
+        out["offset"].append(b)
+        out["cluster"].append(name)
+    return out
+
+
+# ----------------------------------------------------------------------- scoring (model.py:474-569)
+def compute_syllable_score(prediction_on_offset_list, label_on_offset_list, tolerance):
+    n_pred, n_label, tp = len(prediction_on_offset_list), len(label_on_offset_list), 0
+    for on, off, name in prediction_on_offset_list:
+        for j, (lon, loff, lname) in enumerate(label_on_offset_list):
+            if np.abs(on - lon) <= tolerance and np.abs(off - loff) <= tolerance and name == lname:
+                tp += 1
+                label_on_offset_list.pop(j)
+                break
+    return tp, n_pred, n_label
+
+
+def segment_score(prediction, label, target_cluster=None, tolerance=None, default_spec_time_step=0.0025):
+    if tolerance is None:
+        tolerance = default_spec_time_step * 4
+    def rows(d):
+        return [[d["onset"][i], d["offset"][i], str(d["cluster"][i])] for i in range(len(d["onset"]))
+                if target_cluster is None or str(target_cluster) == str(d["cluster"][i])]
+    pred, lab = rows(prediction), rows(label)
+    if target_cluster is not None and len(lab) == 0:
+        print("Warning: the specified target cluster '%s' does not exist in the ground-truth labels." % str(target_cluster))
+    tp, n_pred, n_label = compute_syllable_score(pred, lab, tolerance)
+    precision = tp / max(n_pred, 1e-12)
+    recall = tp / max(n_label, 1e-12)
+    f1 = 2 / (1 / max(precision, 1e-12) + 1 / max(recall, 1e-12))
+    return tp, n_pred, n_label, precision, recall, f1
+
+
+def frame_score(prediction, label, target_cluster=None, time_per_frame_for_scoring=None, default_spec_time_step=0.0025):
+    if time_per_frame_for_scoring is None:
+        time_per_frame_for_scoring = min(0.001, default_spec_time_step)
+    prediction["cluster"] = list(map(str, prediction["cluster"]))
+    label["cluster"] = list(map(str, label["cluster"]))
+    ids = {}
+    for name in list(prediction["cluster"]) + list(label["cluster"]):
+        ids.setdefault(name, len(ids))
+    stamps = list(prediction["onset"]) + list(prediction["offset"]) + list(label["onset"]) + list(label["offset"])
+    max_time = np.max(stamps) if len(stamps) else 1.0
+    n_frames = int(np.round(max_time / time_per_frame_for_scoring)) + 1
+
+    def rasterise(d):
+        row = np.ones(n_frames) * -1
+        for on, off, name in zip(d["onset"], d["offset"], d["cluster"]):
+            row[int(np.round(on / time_per_frame_for_scoring)):int(np.round(off / time_per_frame_for_scoring))] = ids[name]
+        return row
+    fp, fl = rasterise(prediction), rasterise(label)
+    if target_cluster is None:
+        tp = np.logical_and(fl != -1, fp == fl).sum()
+        p_pred, p_label = (fp != -1).sum(), (fl != -1).sum()
+    else:
+        tid = ids[target_cluster]
+        tp = np.logical_and(fl == tid, fp == fl).sum()
+        p_pred, p_label = (fp == tid).sum(), (fl == tid).sum()
+    precision = tp / max(p_pred, 1e-12)
+    recall = tp / max(p_label, 1e-12)
+    f1 = 2 / (1 / max(precision, 1e-12) + 1 / max(recall, 1e-12))
+    return tp, p_pred, p_label, precision, recall, f1
