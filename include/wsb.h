@@ -1,0 +1,103 @@
+/* libwsb -- C ABI of the B200-native WhisperSeg segmentation hot path.
+ *
+ * The reference (nianlonggu/WhisperSeg) is pure Python and has NO plugin / operator / FFI layer: its
+ * hot path sits behind the Python methods of `model.py`.  This header is therefore the FFI a
+ * maintainer would bind *from that Python file* (ctypes).  Every entry point
+ * names the reference interface it replaces.  Conventions: plain pointers and sizes, no torch
+ * types; device pointers are raw CUDA device addresses; `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream); every function returns 0 on success and a non-zero
+ * status otherwise, with a human-readable message available from wsb_last_error().
+ * There is no CPU fallback: every compute entry point requires an sm_100 device.
+ */
+#ifndef WSB_H_
+#define WSB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WSB_ABI_VERSION 1
+
+/* ---- library ------------------------------------------------------------------------------ */
+int wsb_abi_version(void);
+const char* wsb_last_error(void);
+/* number of CUDA kernels launched by this library since the last call with reset != 0 */
+long long wsb_launch_count(int reset);
+
+/* ---- K1: log-mel front-end ------------------------------------------------------------------
+ * Replaces SegmenterBase.get_sliced_audios_features's per-window feature extraction
+ * (reference model.py:146-165 -> HF WhisperFeatureExtractor, called at model.py:152) and the
+ * WhisperSegFeatureExtractor configuration (reference audio_utils.py:45-76).                   */
+typedef struct wsb_logmel_plan wsb_logmel_plan;
+
+/* mel_filters: host float32 [n_fft/2+1][80] (the slaney bank for [min_frequency, sr//2]);
+ * n_cols = total_spec_columns (1000).  clip_len = int(n_cols * spec_time_step * sr).           */
+int wsb_logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float* mel_filters,
+                           int n_freq, wsb_logmel_plan** plan);
+void wsb_logmel_plan_destroy(wsb_logmel_plan* plan);
+/* audio_dev: device float32 samples (16-byte aligned).  windows_dev: device int64 [n_windows][3] =
+ * {start, lo, hi}: window w covers audio[start .. start+clip_len) and a sample index a is read
+ * only if lo <= a < hi (zero otherwise: trial left-padding, tail zero-padding, file boundaries).
+ * features_dev: device float32 [n_windows][80][n_cols].                                         */
+int wsb_logmel_run(const wsb_logmel_plan* plan, const float* audio_dev, const int64_t* windows_dev,
+                   int n_windows, float* features_dev, void* stream);
+
+/* ---- model ------------------------------------------------------------------------------------
+ * Replaces WhisperForConditionalGeneration as used by WhisperSegmenter.__init__ /
+ * generate_segment_text_core (reference model.py:626-676) and ctranslate2.models.Whisper as used
+ * by WhisperSegmenterFast (model.py:679-746).                                                   */
+typedef struct wsb_model wsb_model;
+
+typedef struct wsb_model_config {
+    int d_model;            /* 384 / 512 / 768 / 1280 ...; head_dim is 64 */
+    int n_heads;
+    int n_layers;           /* encoder_layers == decoder_layers */
+    int ffn_dim;
+    int vocab_size;         /* 51865 */
+    int n_mels;             /* 80 */
+    int n_cols;             /* total_spec_columns: 1000 -> 500 encoder positions */
+    int max_target_positions; /* 448 */
+    int max_batch;          /* windows processed per encode/generate call */
+} wsb_model_config;
+
+/* names[i] / tensors_dev[i]: prepared device tensors (see whisperseg_b200/weights.py for the list,
+ * dtypes and layouts).  The model keeps the pointers; the caller keeps the memory alive.        */
+int wsb_model_create(const wsb_model_config* cfg, const char* const* names, const void* const* tensors_dev,
+                     int n_tensors, wsb_model** model);
+void wsb_model_destroy(wsb_model* model);
+size_t wsb_model_workspace_bytes(const wsb_model* model);
+
+/* Encoder (conv stem + n_layers pre-LN blocks + final LN); replaces HF WhisperEncoder.forward
+ * reached from model.generate (reference model.py:655).  features_dev: float32 [batch][80][n_cols].
+ * hidden_f32_dev: optional (may be NULL) float32 [batch][n_cols/2][d_model] copy of the output;
+ * the bf16 output stays inside the model for wsb_generate.                                       */
+int wsb_encode(wsb_model* model, const float* features_dev, int batch, float* hidden_f32_dev, void* stream);
+
+/* Greedy generation over the windows of the last wsb_encode call; replaces model.generate(...,
+ * num_beams=1) at reference model.py:655-666 / 723-727.  prompt: host int32[prompt_len]
+ * ([<|startoftranscript|>, <|en|>, <|notimestamps|>]); max_length counts the prompt tokens.
+ * tokens_dev: device int32 [batch][max_length - prompt_len], finished rows padded with pad_id.
+ * forced_dev: NULL, or device int32 [batch][max_length] decoder inputs for teacher forcing (the
+ * per-position arg-max is still what is written to tokens_dev).  n_steps (host, may be NULL)
+ * receives the number of generated positions actually computed.  flags: bit0 = use CUDA graph. */
+int wsb_generate(wsb_model* model, int batch, const int32_t* prompt, int prompt_len, int eos_id, int pad_id,
+                 int max_length, const int32_t* forced_dev, int32_t* tokens_dev, int* n_steps, int flags,
+                 void* stream);
+
+/* ---- individual kernels, exported for parity tests and profiling ------------------------------ */
+/* C = act(A W^T + bias) (+ resid): A bf16 [M][K], W bf16 [N][K], fp32 accumulate.
+ * out_f32 != 0: C float32 [M][N] (+ optional float32 residual [M][N]); else C bf16 [M][N].      */
+int wsb_gemm_bf16(const void* a_dev, const void* w_dev, int M, int N, int K, const float* bias_dev, int gelu,
+                  const float* resid_dev, void* c_dev, int out_f32, int block_n, void* stream);
+int wsb_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_dev, void* out_bf16_dev,
+                  float* out_f32_dev, int rows, int d, void* stream);
+/* qkv bf16 [batch*T][3*n_heads*64] (q pre-scaled) -> out bf16 [batch*T][n_heads*64] */
+int wsb_encoder_attention(const void* qkv_dev, void* out_dev, int batch, int T, int n_heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSB_H_ */

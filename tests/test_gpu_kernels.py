@@ -1,0 +1,97 @@
+"""Kernel-level parity through the C ABI: tcgen05 GEMM (all tile widths, every fused epilogue),
+LayerNorm, encoder attention -- against plain torch fp32 on the same bf16-rounded inputs."""
+import ctypes
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from whisperseg_b200 import _lib
+    return _lib.load()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 256, 64, 256), (128, 128, 64, 128), (256, 512, 128, 256), (1000, 1280, 1280, 256), (1000, 1280, 1280, 128),
+    (777, 384, 1536, 128), (300, 1152, 384, 64), (5, 1536, 384, 32), (240, 5120, 1280, 0), (2500, 3840, 1280, 0),
+    (130, 200, 64, 64), (64, 51880, 384, 0),
+])
+def test_gemm_plain(lib, M, N, K, bn):
+    import torch
+    from whisperseg_b200 import _lib
+    torch.manual_seed(M * 7 + N)
+    dev = "cuda"
+    a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    ref = a.float() @ w.float().t() + bias
+    out32 = torch.full((M, N), float("nan"), device=dev)
+    ldn = N
+    if N % 4 == 0:
+        _lib.check(lib.wsb_gemm_bf16(_p(a), _p(w), M, N, K, _p(bias), 0, _p(None), _p(out32), 1, bn, None), "gemm f32")
+        torch.cuda.synchronize()
+        err = (out32 - ref).abs().max().item()
+        assert err < 2e-3 * max(1.0, ref.abs().max().item()), "f32 out: max err %g" % err
+    if N % 8 == 0:
+        out16 = torch.zeros((M, ldn), device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.wsb_gemm_bf16(_p(a), _p(w), M, N, K, _p(bias), 1, _p(None), _p(out16), 0, bn, None), "gemm bf16")
+        torch.cuda.synchronize()
+        refg = torch.nn.functional.gelu(ref)
+        err = (out16.float() - refg).abs().max().item()
+        assert err < 1e-2 * max(1.0, refg.abs().max().item()), "bf16+gelu out: max err %g" % err
+
+
+def test_gemm_residual_inplace(lib):
+    import torch
+    from whisperseg_b200 import _lib
+    torch.manual_seed(3)
+    M, N, K = 900, 1280, 5120
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    x = torch.randn(M, N, device="cuda")
+    ref = x + a.float() @ w.float().t() + bias
+    _lib.check(lib.wsb_gemm_bf16(_p(a), _p(w), M, N, K, _p(bias), 0, _p(x), _p(x), 1, 0, None), "gemm resid")
+    torch.cuda.synchronize()
+    assert (x - ref).abs().max().item() < 3e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("rows,d", [(1000, 1280), (37, 384), (500, 512), (3, 768)])
+def test_layernorm(lib, rows, d):
+    import torch
+    from whisperseg_b200 import _lib
+    torch.manual_seed(rows)
+    x = torch.randn(rows, d, device="cuda") * 3 + 1
+    g = torch.randn(d, device="cuda")
+    b = torch.randn(d, device="cuda")
+    o16 = torch.empty(rows, d, device="cuda", dtype=torch.bfloat16)
+    o32 = torch.empty(rows, d, device="cuda")
+    _lib.check(lib.wsb_layernorm(_p(x), _p(g), _p(b), _p(o16), _p(o32), rows, d, None), "layernorm")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (d,), g, b, 1e-5)
+    assert (o32 - ref).abs().max().item() < 1e-4
+    assert (o16.float() - ref).abs().max().item() < 4e-2
+
+
+@pytest.mark.parametrize("B,T,H", [(1, 500, 6), (3, 500, 20), (2, 128, 8), (2, 300, 6)])
+def test_encoder_attention(lib, B, T, H):
+    import torch
+    from whisperseg_b200 import _lib
+    torch.manual_seed(B * 100 + T)
+    d = H * 64
+    qkv = torch.randn(B * T, 3 * d, device="cuda")
+    qkv[:, :d] *= 0.35                      # q already carries the 1/8 scaling (and then some spread)
+    qkv = qkv.to(torch.bfloat16)
+    out = torch.zeros(B * T, d, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.wsb_encoder_attention(_p(qkv), _p(out), B, T, H, None), "attention")
+    torch.cuda.synchronize()
+    q, k, v = [t.float().view(B, T, H, 64).transpose(1, 2) for t in qkv.split(d, dim=1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2), -1) @ v).transpose(1, 2).reshape(B * T, d)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2, "attention max err %g" % err

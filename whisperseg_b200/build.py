@@ -1,0 +1,65 @@
+"""Build libwsb.so (all CUDA kernels + the C ABI) for sm_100a, in-tree.
+
+    python -m whisperseg_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The .so lands next to this file (git-ignored, but it travels to
+the GPU box with the gpurun snapshot).
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libwsb.so")
+SOURCES = ["logmel.cu", "gemm.cu", "elementwise.cu", "attention.cu", "decode.cu", "engine.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _digest():
+    h = hashlib.sha256()
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for name in sorted(os.listdir(root)):
+            if name.endswith((".cu", ".cuh", ".h")):
+                h.update(name.encode())
+                h.update(open(os.path.join(root, name), "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    stamp = LIB + ".sha256"
+    digest = _digest()
+    if not force and os.path.isfile(LIB) and os.path.isfile(stamp) and open(stamp).read().strip() == digest:
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
+    for src in SOURCES:
+        obj = os.path.join(HERE, "_build", src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append("==== %s\n%s" % (src, out))
+        if p.returncode != 0:
+            failed = True
+    open(os.path.join(HERE, "_build", "nvcc.log"), "w").write("\n".join(log))
+    if failed or verbose:
+        sys.stderr.write("\n".join(log))
+    if failed:
+        raise RuntimeError("nvcc failed; see whisperseg_b200/_build/nvcc.log")
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    subprocess.check_call(cmd)
+    open(stamp, "w").write(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

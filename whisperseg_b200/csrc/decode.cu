@@ -1,0 +1,302 @@
+// K5 -- kernels of the batched-over-windows greedy decode step that are not GEMMs:
+//   * single-query attention over a head-major K/V block (self-attention over the growing cache with
+//     fused cache append, and cross-attention over the 500 encoder frames)  -- HBM-bound streaming;
+//   * the arg-max / logits-processor tail: combine the per-tile partial arg-max of the tied output
+//     projection, apply finished-row masking, record the token, update the finished flags.
+//
+// Replaces, per generated token, HF WhisperDecoderLayer self/cross attention with its KV cache
+// (modeling_whisper.py:417-506, 241-357) and the greedy branch of generate() with the
+// SuppressTokens / SuppressTokensAtBegin processors (generation_whisper.py:1774-1812) -- the
+// suppression masks are additive -inf vectors fused into the projection GEMM's epilogue.
+#include "common.cuh"
+#include "wsb_internal.h"
+#include "decode.h"
+
+namespace wsb {
+
+constexpr int kDaThreads = 128;
+constexpr int kDaMaxKeys = 512;
+
+// q: bf16 [B][q_ld] (+ head*64), already scaled.  K/V blocks: bf16 [n_keys][64] contiguous per (b, head).
+// mode 0 (cross): K at kv + ((b*kv_heads_total + k_slot)*T)*64, n_keys = T, fixed.
+// mode 1 (self) : cache [B][H][Tmax][64] for K and V; the new k,v (from the packed qkv row) are
+//                 appended at position *step_ptr + pos_offset before attending over [0, pos].
+struct DaParams {
+    const __nv_bfloat16* q;
+    long long q_ld;
+    const __nv_bfloat16* k_base;
+    const __nv_bfloat16* v_base;
+    __nv_bfloat16* k_cache;       // self mode only (same memory as k_base)
+    __nv_bfloat16* v_cache;
+    const __nv_bfloat16* new_k;   // self mode: pointer to k part of the packed row (b stride q_ld)
+    const __nv_bfloat16* new_v;
+    long long bh_stride;          // elements between consecutive (b,h) blocks
+    long long b_stride;           // elements between consecutive b
+    int n_keys_fixed;             // cross: T
+    const int* step_ptr;          // self: current step (device)
+    int pos_offset;               // self: position = pos_offset + *step_ptr
+    const unsigned char* finished;
+    __nv_bfloat16* out;           // [B][d]
+    int d;
+    int self_mode;
+};
+
+__global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaParams p) {
+    const int h = blockIdx.x, b = blockIdx.y;
+    if (p.finished && p.finished[b]) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __shared__ float s_q[64];
+    __shared__ float s_p[kDaMaxKeys];
+    __shared__ float s_red[kDaThreads / 32];
+    __shared__ float s_out[kDaThreads / 32][64];
+
+    const long long blk = static_cast<long long>(b) * p.b_stride + static_cast<long long>(h) * p.bh_stride;
+    const __nv_bfloat16* K = p.k_base + blk;
+    const __nv_bfloat16* V = p.v_base + blk;
+    int n_keys;
+    if (p.self_mode) {
+        const int pos = p.pos_offset + *p.step_ptr;
+        n_keys = pos + 1;
+        if (tid < 64) {
+            const __nv_bfloat16 kv = p.new_k[static_cast<long long>(b) * p.q_ld + h * 64 + tid];
+            p.k_cache[blk + static_cast<long long>(pos) * 64 + tid] = kv;
+        } else {
+            const int e = tid - 64;
+            const __nv_bfloat16 vv = p.new_v[static_cast<long long>(b) * p.q_ld + h * 64 + e];
+            p.v_cache[blk + static_cast<long long>(pos) * 64 + e] = vv;
+        }
+    } else {
+        n_keys = p.n_keys_fixed;
+    }
+    if (tid < 64) s_q[tid] = __bfloat162float(p.q[static_cast<long long>(b) * p.q_ld + h * 64 + tid]);
+    __syncthreads();                                   // also orders the cache append before the reads below
+
+    // scores: a warp covers 4 keys per iteration; lane = (key % 4) * 8 + 16-byte chunk
+    const int sub = lane >> 3, ch = lane & 7;
+    float qv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qv[i] = s_q[ch * 8 + i];
+    float lmax = -INFINITY;
+    for (int j0 = warp * 4; j0 < n_keys; j0 += (kDaThreads / 32) * 4) {
+        const int j = j0 + sub;
+        float dot = 0.0f;
+        if (j < n_keys) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(K + static_cast<long long>(j) * 64 + ch * 8);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(h2[i]);
+                dot = fmaf(f.x, qv[2 * i], dot);
+                dot = fmaf(f.y, qv[2 * i + 1], dot);
+            }
+        }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        if (j < n_keys) {
+            if (ch == 0) s_p[j] = dot;
+            lmax = fmaxf(lmax, dot);
+        }
+    }
+    lmax = warp_max(lmax);
+    if (lane == 0) s_red[warp] = lmax;
+    __syncthreads();
+    float gmax = s_red[0];
+#pragma unroll
+    for (int i = 1; i < kDaThreads / 32; ++i) gmax = fmaxf(gmax, s_red[i]);
+    __syncthreads();
+    float lsum = 0.0f;
+    for (int j = tid; j < n_keys; j += kDaThreads) {
+        const float e = __expf(s_p[j] - gmax);
+        s_p[j] = e;
+        lsum += e;
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0) s_red[warp] = lsum;
+    __syncthreads();
+    float gsum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kDaThreads / 32; ++i) gsum += s_red[i];
+
+    // out = sum_j p_j V_j : same 4-keys-per-warp streaming pattern, 8 dims per lane
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    for (int j0 = warp * 4; j0 < n_keys; j0 += (kDaThreads / 32) * 4) {
+        const int j = j0 + sub;
+        if (j < n_keys) {
+            const float pj = s_p[j];
+            const uint4 raw = *reinterpret_cast<const uint4*>(V + static_cast<long long>(j) * 64 + ch * 8);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(h2[i]);
+                acc[2 * i] = fmaf(pj, f.x, acc[2 * i]);
+                acc[2 * i + 1] = fmaf(pj, f.y, acc[2 * i + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    }
+    if (sub == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_out[warp][ch * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float o = 0.0f;
+#pragma unroll
+        for (int wi = 0; wi < kDaThreads / 32; ++wi) o += s_out[wi][tid];
+        p.out[static_cast<long long>(b) * p.d + h * 64 + tid] = __float2bfloat16(o / gsum);
+    }
+}
+
+int decode_self_attention(const __nv_bfloat16* qkv, int d, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int t_max,
+                          const int* step_ptr, int pos_offset, const unsigned char* finished, __nv_bfloat16* out,
+                          int B, int n_heads, cudaStream_t stream) {
+    WSB_REQUIRE(t_max <= kDaMaxKeys, "self-attention cache longer than 512 positions");
+    if (B <= 0) return 0;
+    DaParams p;
+    p.q = qkv;
+    p.q_ld = 3LL * d;
+    p.k_base = k_cache;
+    p.v_base = v_cache;
+    p.k_cache = k_cache;
+    p.v_cache = v_cache;
+    p.new_k = qkv + d;
+    p.new_v = qkv + 2 * d;
+    p.bh_stride = static_cast<long long>(t_max) * 64;
+    p.b_stride = static_cast<long long>(n_heads) * t_max * 64;
+    p.n_keys_fixed = 0;
+    p.step_ptr = step_ptr;
+    p.pos_offset = pos_offset;
+    p.finished = finished;
+    p.out = out;
+    p.d = d;
+    p.self_mode = 1;
+    decode_attention_kernel<<<dim3(n_heads, B), kDaThreads, 0, stream>>>(p);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int decode_cross_attention(const __nv_bfloat16* q, int d, const __nv_bfloat16* cross_kv, int layer, int n_layers,
+                           int T, const unsigned char* finished, __nv_bfloat16* out, int B, int n_heads,
+                           cudaStream_t stream) {
+    WSB_REQUIRE(T <= kDaMaxKeys, "cross-attention over more than 512 encoder positions");
+    if (B <= 0) return 0;
+    // cross_kv layout (written by the head-major GEMM epilogue): [b][layer][k|v][head][T][64]
+    DaParams p;
+    p.q = q;
+    p.q_ld = d;
+    const long long per_head = static_cast<long long>(T) * 64;
+    p.k_base = cross_kv + (static_cast<long long>(layer) * 2 + 0) * n_heads * per_head;
+    p.v_base = cross_kv + (static_cast<long long>(layer) * 2 + 1) * n_heads * per_head;
+    p.k_cache = nullptr;
+    p.v_cache = nullptr;
+    p.new_k = nullptr;
+    p.new_v = nullptr;
+    p.bh_stride = per_head;
+    p.b_stride = static_cast<long long>(n_layers) * 2 * n_heads * per_head;
+    p.n_keys_fixed = T;
+    p.step_ptr = nullptr;
+    p.pos_offset = 0;
+    p.finished = finished;
+    p.out = out;
+    p.d = d;
+    p.self_mode = 0;
+    decode_attention_kernel<<<dim3(n_heads, B), kDaThreads, 0, stream>>>(p);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- arg-max tail
+// one warp per row: reduce the per-tile partials (lowest index wins ties, like torch.argmax), then
+// finished rows emit pad, the token is recorded and fed back, EOS marks the row finished.
+// `*step_ptr` is the decoder position of the token just consumed; the token produced here lands in
+// tokens_out[row][pos - out_offset].  With `forced` (teacher forcing, parity tests) the next input is
+// forced[row][pos + 1] instead of the arg-max and rows never finish.
+__global__ void argmax_finalize_kernel(const float* __restrict__ val, const int* __restrict__ idx, int n_tiles,
+                                       int* __restrict__ tokens_out, int max_new, int out_offset,
+                                       int* __restrict__ next_token, const int* __restrict__ forced, int forced_ld,
+                                       unsigned char* __restrict__ finished, const int* __restrict__ step_ptr,
+                                       int* __restrict__ n_active, int eos_id, int pad_id, int B) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int pos = *step_ptr;
+    if (warp < B) {
+        float best = -INFINITY;
+        int best_i = 0x7fffffff;
+        for (int t = lane; t < n_tiles; t += 32) {
+            const float v = val[static_cast<long long>(warp) * n_tiles + t];
+            const int i = idx[static_cast<long long>(warp) * n_tiles + t];
+            if (v > best || (v == best && i < best_i)) {
+                best = v;
+                best_i = i;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (ov > best || (ov == best && oi < best_i)) {
+                best = ov;
+                best_i = oi;
+            }
+        }
+        if (lane == 0) {
+            const int slot = pos - out_offset;
+            if (forced) {
+                if (slot >= 0 && slot < max_new) tokens_out[static_cast<long long>(warp) * max_new + slot] = best_i;
+                next_token[warp] = (pos + 1 < forced_ld) ? forced[static_cast<long long>(warp) * forced_ld + pos + 1] : pad_id;
+            } else {
+                const bool was_finished = finished[warp] != 0;
+                const int tok = was_finished ? pad_id : best_i;
+                if (slot >= 0 && slot < max_new) tokens_out[static_cast<long long>(warp) * max_new + slot] = tok;
+                next_token[warp] = tok;
+                if (!was_finished && tok == eos_id) {
+                    finished[warp] = 1;
+                    atomicSub(n_active, 1);
+                }
+            }
+        }
+    }
+}
+__global__ void step_increment_kernel(int* step_ptr) { *step_ptr += 1; }
+
+int argmax_finalize(const float* val, const int* idx, int n_tiles, int* tokens_out, int max_new, int out_offset,
+                    int* next_token, const int* forced, int forced_ld, unsigned char* finished, int* step_ptr,
+                    int* n_active, int eos_id, int pad_id, int B, cudaStream_t stream) {
+    if (B <= 0) return 0;
+    argmax_finalize_kernel<<<ceil_div(B * 32, 256), 256, 0, stream>>>(val, idx, n_tiles, tokens_out, max_new, out_offset,
+                                                                       next_token, forced, forced_ld, finished, step_ptr,
+                                                                       n_active, eos_id, pad_id, B);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    step_increment_kernel<<<1, 1, 0, stream>>>(step_ptr);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    count_launch(2);
+    return 0;
+}
+
+// prompt positions before the last one: no logits, just feed the next prompt token
+__global__ void prefill_advance_kernel(int* __restrict__ next_token, const int* __restrict__ forced, int forced_ld,
+                                       const int* __restrict__ prompt, int* __restrict__ step_ptr, int B) {
+    const int pos = *step_ptr;
+    for (int b = threadIdx.x; b < B; b += blockDim.x)
+        next_token[b] = forced ? forced[static_cast<long long>(b) * forced_ld + pos + 1] : prompt[pos + 1];
+    __syncthreads();
+    if (threadIdx.x == 0) *step_ptr = pos + 1;
+}
+
+int prefill_advance(int* next_token, const int* forced, int forced_ld, const int* prompt_dev, int* step_ptr, int B,
+                    cudaStream_t stream) {
+    prefill_advance_kernel<<<1, 256, 0, stream>>>(next_token, forced, forced_ld, prompt_dev, step_ptr, B);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace wsb

@@ -1,0 +1,187 @@
+// Bandwidth-bound helper kernels: LayerNorm (fp32 residual stream -> bf16 GEMM operand), the conv1
+// stem (80 -> d, k=3, pad=1, GELU) and decoder token/position embedding.
+//
+//   LayerNorm  : HF WhisperEncoderLayer / WhisperDecoderLayer nn.LayerNorm(eps=1e-5)
+//                (modeling_whisper.py:361-414, 417-506)
+//   conv1+GELU : HF WhisperEncoder.forward, modeling_whisper.py:619-620
+//   embedding  : HF WhisperDecoder.forward, modeling_whisper.py:742-760 (embed_tokens + embed_positions)
+#include "common.cuh"
+#include "wsb_internal.h"
+
+namespace wsb {
+
+// ------------------------------------------------------------------------------ LayerNorm
+// one warp per row; the row lives in registers between the statistics and the normalisation
+constexpr int kLnMaxVec = 12;   // float4 per lane -> d <= 1536
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_bf16,
+                                                        float* __restrict__ out_f32, int rows, int d) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nvec = d >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
+    float4 v[kLnMaxVec];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nvec) {
+            v[i] = xr[j];
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(sum) / d;
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nvec) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+            sq += (a * a + b * b) + (c * c + e * e);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / d + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nvec) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + j);
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + j);
+            const float o0 = (v[i].x - mean) * rstd * g.x + bt.x;
+            const float o1 = (v[i].y - mean) * rstd * g.y + bt.y;
+            const float o2 = (v[i].z - mean) * rstd * g.z + bt.z;
+            const float o3 = (v[i].w - mean) * rstd * g.w + bt.w;
+            if (out_bf16) {
+                uint2 pk;
+                pk.x = pack_bf16x2(o0, o1);
+                pk.y = pack_bf16x2(o2, o3);
+                reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(row) * d)[j] = pk;
+            }
+            if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * d)[j] = make_float4(o0, o1, o2, o3);
+        }
+    }
+}
+
+int layernorm_f32_to_bf16(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out_bf16,
+                          float* out_f32, int rows, int d, cudaStream_t stream) {
+    WSB_REQUIRE(d % 4 == 0 && d <= kLnMaxVec * 128, "LayerNorm width must be a multiple of 4 and <= 1536");
+    if (rows <= 0) return 0;
+    const int rows_per_block = 8;
+    layernorm_kernel<<<ceil_div(rows, rows_per_block), rows_per_block * 32, 0, stream>>>(x, gamma, beta, out_bf16,
+                                                                                         out_f32, rows, d);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ conv1 + GELU
+// out[b][1 + t][co] = gelu(bias[co] + sum_{ci,k} w[co][ci][k] * x[b][ci][t + k - 1]),  t in [0, n_cols)
+// x: f32 [B][80][n_cols] (K1's output layout); wt: f32 [80*3][d] (pre-transposed, co contiguous);
+// out: bf16, row 0 of every batch is the zero row conv2's left padding reads (written here).
+constexpr int kC1Threads = 256;
+constexpr int kC1TileT = 128;
+constexpr int kC1TileC = 64;
+constexpr int kC1In = 80;
+
+__global__ void __launch_bounds__(kC1Threads) conv1_kernel(const float* __restrict__ x, const float* __restrict__ wt,
+                                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                           int n_cols, int d, long long out_batch_stride) {
+    extern __shared__ __align__(16) float c1_smem[];
+    float* s_x = c1_smem;                               // [80][kC1TileT + 4]  (t0-1 .. t0+128)
+    float* s_w = c1_smem + kC1In * (kC1TileT + 4);      // [240][64]
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * kC1TileT;
+    const int co0 = blockIdx.y * kC1TileC;
+    const int tid = threadIdx.x;
+    const float* xb = x + static_cast<size_t>(b) * kC1In * n_cols;
+    for (int i = tid; i < kC1In * (kC1TileT + 2); i += kC1Threads) {
+        const int ci = i / (kC1TileT + 2), j = i - ci * (kC1TileT + 2);
+        const int t = t0 - 1 + j;
+        s_x[ci * (kC1TileT + 4) + j] = (t >= 0 && t < n_cols) ? __ldg(xb + static_cast<size_t>(ci) * n_cols + t) : 0.0f;
+    }
+    for (int i = tid; i < kC1In * 3 * (kC1TileC / 4); i += kC1Threads) {
+        const int kk = i / (kC1TileC / 4), c4 = i - kk * (kC1TileC / 4);
+        reinterpret_cast<float4*>(s_w)[kk * (kC1TileC / 4) + c4] =
+            __ldg(reinterpret_cast<const float4*>(wt + static_cast<size_t>(kk) * d + co0) + c4);
+    }
+    __syncthreads();
+    const int cx = tid & 15, ty = tid >> 4;             // 16 x 16 threads: 4 channels x 8 time steps each
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+    for (int ci = 0; ci < kC1In; ++ci) {
+        float xv[10];
+        const float* xs = s_x + ci * (kC1TileT + 4) + ty * 8;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) xv[i] = xs[i];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float4 w4 = reinterpret_cast<const float4*>(s_w)[(ci * 3 + k) * (kC1TileC / 4) + cx];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                acc[i][0] = fmaf(w4.x, xv[i + k], acc[i][0]);
+                acc[i][1] = fmaf(w4.y, xv[i + k], acc[i][1]);
+                acc[i][2] = fmaf(w4.z, xv[i + k], acc[i][2]);
+                acc[i][3] = fmaf(w4.w, xv[i + k], acc[i][3]);
+            }
+        }
+    }
+    const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + co0) + cx);
+    __nv_bfloat16* ob = out + static_cast<size_t>(b) * out_batch_stride;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int t = t0 + ty * 8 + i;
+        if (t < n_cols) {
+            uint2 pk;
+            pk.x = pack_bf16x2(gelu_erf(acc[i][0] + bs.x), gelu_erf(acc[i][1] + bs.y));
+            pk.y = pack_bf16x2(gelu_erf(acc[i][2] + bs.z), gelu_erf(acc[i][3] + bs.w));
+            *reinterpret_cast<uint2*>(ob + static_cast<size_t>(1 + t) * d + co0 + cx * 4) = pk;
+        }
+    }
+    if (blockIdx.x == 0 && ty == 0)                     // zero row in front of every batch
+        *reinterpret_cast<uint2*>(ob + co0 + cx * 4) = make_uint2(0u, 0u);
+}
+
+int conv1_gelu(const float* feats, const float* wt, const float* b, __nv_bfloat16* out, int B, int n_cols, int d,
+               int64_t out_batch_stride, cudaStream_t stream) {
+    WSB_REQUIRE(d % kC1TileC == 0, "d_model must be a multiple of 64");
+    if (B <= 0) return 0;
+    static bool attr_set = false;
+    const size_t smem = sizeof(float) * (kC1In * (kC1TileT + 4) + kC1In * 3 * kC1TileC);
+    if (!attr_set) {
+        WSB_CHECK_CUDA(cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_set = true;
+    }
+    dim3 grid(ceil_div(n_cols, kC1TileT), d / kC1TileC, B);
+    conv1_kernel<<<grid, kC1Threads, smem, stream>>>(feats, wt, b, out, n_cols, d, out_batch_stride);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ decoder embedding
+__global__ void embed_kernel(const int* __restrict__ tokens, const int* __restrict__ step_ptr, int pos_offset,
+                             const __nv_bfloat16* __restrict__ emb, const float* __restrict__ pos_emb,
+                             float* __restrict__ x, int d) {
+    const int b = blockIdx.x;
+    const int tok = tokens[b];
+    const int pos = pos_offset + (step_ptr ? *step_ptr : 0);
+    const __nv_bfloat16* e = emb + static_cast<size_t>(tok) * d;
+    const float* pe = pos_emb + static_cast<size_t>(pos) * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) x[static_cast<size_t>(b) * d + i] = __bfloat162float(e[i]) + pe[i];
+}
+
+int embed_tokens_step(const int* tokens, const int* step_ptr, int pos_offset, const __nv_bfloat16* emb,
+                      const float* pos_emb, float* x, int B, int d, cudaStream_t stream) {
+    if (B <= 0) return 0;
+    embed_kernel<<<B, 256, 0, stream>>>(tokens, step_ptr, pos_offset, emb, pos_emb, x, d);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace wsb

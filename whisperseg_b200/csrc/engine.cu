@@ -1,0 +1,476 @@
+// Engine: owns the per-model workspace and sequences the kernels of the hot path.
+//   wsb_encode   -- conv stem + encoder layers           (HF WhisperEncoder.forward, modeling_whisper.py:593-647)
+//   wsb_generate -- cross-K/V projection + greedy KV-cache decode loop, optionally replayed from a
+//                   CUDA graph                            (HF generate, reference model.py:655-666)
+// plus the extern "C" surface declared in include/wsb.h.
+#include "common.cuh"
+#include "wsb_internal.h"
+#include "decode.h"
+#include "../../include/wsb.h"
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace wsb {
+
+static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* get_last_error() { return g_last_error.c_str(); }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct EncLayer {
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    const __nv_bfloat16 *qkv_w, *o_w, *fc1_w, *fc2_w;
+    const float *qkv_b, *o_b, *fc1_b, *fc2_b;
+};
+struct DecLayer {
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+    const __nv_bfloat16 *sqkv_w, *so_w, *cq_w, *co_w, *fc1_w, *fc2_w;
+    const float *sqkv_b, *so_b, *cq_b, *co_b, *fc1_b, *fc2_b;
+};
+
+struct Model {
+    wsb_model_config cfg;
+    int T;                                // encoder positions = n_cols / 2
+    // encoder weights
+    const float *conv1_wt, *conv1_b, *conv2_b, *enc_pos, *enc_ln_g, *enc_ln_b;
+    const __nv_bfloat16* conv2_w;
+    std::vector<EncLayer> enc;
+    // decoder weights
+    const __nv_bfloat16 *dec_emb, *crosskv_w;
+    const float *dec_pos, *crosskv_b, *dec_ln_g, *dec_ln_b, *suppress, *begin_suppress;
+    std::vector<DecLayer> dec;
+    // workspace
+    char* ws = nullptr;
+    size_t ws_bytes = 0;
+    __nv_bfloat16 *h1p, *xn, *qkv, *att, *ff, *enc_out, *cross_kv, *k_cache, *v_cache, *dxn, *dqkv, *datt, *dq, *dff;
+    float *x, *dx, *am_val;
+    int *am_idx, *tokens, *next_token, *step, *n_active, *prompt_dev;
+    unsigned char* finished;
+    int am_tiles = 0, logits_bn = 0;
+    int last_batch = 0;
+    // CUDA graph of one steady-state decode step, keyed by batch
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_batch = -1;
+    int* pinned_active = nullptr;
+};
+
+template <typename T>
+static T* carve(char*& p, size_t count) {
+    T* r = reinterpret_cast<T*>(p);
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    p += bytes;
+    return r;
+}
+
+static int model_layout(Model* m, bool assign) {
+    const wsb_model_config& c = m->cfg;
+    const size_t B = c.max_batch, d = c.d_model, F = c.ffn_dim, L = c.n_layers, H = c.n_heads, T = m->T;
+    const size_t rows = B * T;
+    char* p = assign ? m->ws : nullptr;
+    char* p0 = p;
+    m->h1p = carve<__nv_bfloat16>(p, B * (c.n_cols + 1) * d);
+    m->x = carve<float>(p, rows * d);
+    m->xn = carve<__nv_bfloat16>(p, rows * d);
+    m->qkv = carve<__nv_bfloat16>(p, rows * 3 * d);
+    m->att = carve<__nv_bfloat16>(p, rows * d);
+    m->ff = carve<__nv_bfloat16>(p, rows * F);
+    m->enc_out = carve<__nv_bfloat16>(p, rows * d);
+    m->cross_kv = carve<__nv_bfloat16>(p, B * L * 2 * H * T * 64);
+    m->k_cache = carve<__nv_bfloat16>(p, L * B * H * c.max_target_positions * 64);
+    m->v_cache = carve<__nv_bfloat16>(p, L * B * H * c.max_target_positions * 64);
+    m->dx = carve<float>(p, B * d);
+    m->dxn = carve<__nv_bfloat16>(p, B * d);
+    m->dqkv = carve<__nv_bfloat16>(p, B * 3 * d);
+    m->datt = carve<__nv_bfloat16>(p, B * d);
+    m->dq = carve<__nv_bfloat16>(p, B * d);
+    m->dff = carve<__nv_bfloat16>(p, B * F);
+    m->am_val = carve<float>(p, B * m->am_tiles);
+    m->am_idx = carve<int>(p, B * m->am_tiles);
+    m->tokens = carve<int>(p, B * c.max_target_positions);
+    m->next_token = carve<int>(p, B);
+    m->step = carve<int>(p, 4);
+    m->n_active = carve<int>(p, 4);
+    m->prompt_dev = carve<int>(p, 16);
+    m->finished = carve<unsigned char>(p, B);
+    m->ws_bytes = static_cast<size_t>(p - p0);
+    return 0;
+}
+
+static int lookup(const std::unordered_map<std::string, const void*>& tab, const std::string& name, const void** out) {
+    auto it = tab.find(name);
+    if (it == tab.end() || it->second == nullptr) {
+        set_last_error("wsb_model_create: missing tensor '" + name + "'");
+        return 5;
+    }
+    *out = it->second;
+    return 0;
+}
+#define WSB_GET(field, name)                                                       \
+    do {                                                                           \
+        const void* _p = nullptr;                                                  \
+        int _rc = lookup(tab, name, &_p);                                          \
+        if (_rc) return _rc;                                                       \
+        field = reinterpret_cast<decltype(field)>(_p);                             \
+    } while (0)
+
+static int model_create(const wsb_model_config* cfg, const char* const* names, const void* const* ptrs, int n,
+                        Model** out) {
+    WSB_REQUIRE(cfg->d_model == cfg->n_heads * 64, "head_dim must be 64");
+    WSB_REQUIRE(cfg->d_model % 64 == 0 && cfg->ffn_dim % 64 == 0, "d_model / ffn_dim must be multiples of 64");
+    WSB_REQUIRE(cfg->n_cols % 2 == 0 && cfg->n_cols / 2 <= 512, "n_cols/2 encoder positions must be <= 512");
+    WSB_REQUIRE(cfg->n_mels == 80, "80 mel bins");
+    WSB_REQUIRE(cfg->max_batch >= 1, "max_batch >= 1");
+    WSB_REQUIRE(cfg->max_target_positions <= 512, "max_target_positions <= 512");
+    int dev = 0, major = 0;
+    WSB_CHECK_CUDA(cudaGetDevice(&dev));
+    WSB_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    WSB_REQUIRE(major == 10, "libwsb needs an sm_100 (Blackwell B200) device; there is no fallback path");
+    std::unordered_map<std::string, const void*> tab;
+    for (int i = 0; i < n; ++i) tab[names[i]] = ptrs[i];
+    Model* m = new Model();
+    m->cfg = *cfg;
+    m->T = cfg->n_cols / 2;
+    WSB_GET(m->conv1_wt, "enc.conv1.wt");
+    WSB_GET(m->conv1_b, "enc.conv1.b");
+    WSB_GET(m->conv2_w, "enc.conv2.w");
+    WSB_GET(m->conv2_b, "enc.conv2.b");
+    WSB_GET(m->enc_pos, "enc.pos");
+    WSB_GET(m->enc_ln_g, "enc.ln.g");
+    WSB_GET(m->enc_ln_b, "enc.ln.b");
+    m->enc.resize(cfg->n_layers);
+    for (int l = 0; l < cfg->n_layers; ++l) {
+        const std::string p = "enc." + std::to_string(l) + ".";
+        EncLayer& e = m->enc[l];
+        WSB_GET(e.ln1_g, p + "ln1.g"); WSB_GET(e.ln1_b, p + "ln1.b");
+        WSB_GET(e.qkv_w, p + "qkv.w"); WSB_GET(e.qkv_b, p + "qkv.b");
+        WSB_GET(e.o_w, p + "o.w"); WSB_GET(e.o_b, p + "o.b");
+        WSB_GET(e.ln2_g, p + "ln2.g"); WSB_GET(e.ln2_b, p + "ln2.b");
+        WSB_GET(e.fc1_w, p + "fc1.w"); WSB_GET(e.fc1_b, p + "fc1.b");
+        WSB_GET(e.fc2_w, p + "fc2.w"); WSB_GET(e.fc2_b, p + "fc2.b");
+    }
+    WSB_GET(m->dec_emb, "dec.emb");
+    WSB_GET(m->dec_pos, "dec.pos");
+    WSB_GET(m->crosskv_w, "dec.crosskv.w");
+    WSB_GET(m->crosskv_b, "dec.crosskv.b");
+    WSB_GET(m->dec_ln_g, "dec.ln.g");
+    WSB_GET(m->dec_ln_b, "dec.ln.b");
+    WSB_GET(m->suppress, "dec.suppress");
+    WSB_GET(m->begin_suppress, "dec.begin_suppress");
+    m->dec.resize(cfg->n_layers);
+    for (int l = 0; l < cfg->n_layers; ++l) {
+        const std::string p = "dec." + std::to_string(l) + ".";
+        DecLayer& e = m->dec[l];
+        WSB_GET(e.ln1_g, p + "ln1.g"); WSB_GET(e.ln1_b, p + "ln1.b");
+        WSB_GET(e.sqkv_w, p + "sqkv.w"); WSB_GET(e.sqkv_b, p + "sqkv.b");
+        WSB_GET(e.so_w, p + "so.w"); WSB_GET(e.so_b, p + "so.b");
+        WSB_GET(e.ln2_g, p + "ln2.g"); WSB_GET(e.ln2_b, p + "ln2.b");
+        WSB_GET(e.cq_w, p + "cq.w"); WSB_GET(e.cq_b, p + "cq.b");
+        WSB_GET(e.co_w, p + "co.w"); WSB_GET(e.co_b, p + "co.b");
+        WSB_GET(e.ln3_g, p + "ln3.g"); WSB_GET(e.ln3_b, p + "ln3.b");
+        WSB_GET(e.fc1_w, p + "fc1.w"); WSB_GET(e.fc1_b, p + "fc1.b");
+        WSB_GET(e.fc2_w, p + "fc2.w"); WSB_GET(e.fc2_b, p + "fc2.b");
+    }
+    m->logits_bn = gemm_pick_block_n(cfg->max_batch, cfg->vocab_size);
+    m->am_tiles = gemm_n_tiles(cfg->vocab_size, m->logits_bn);
+    model_layout(m, false);
+    WSB_CHECK_CUDA(cudaMalloc(&m->ws, m->ws_bytes));
+    model_layout(m, true);
+    WSB_CHECK_CUDA(cudaMallocHost(&m->pinned_active, sizeof(int) * 4));
+    *out = m;
+    return 0;
+}
+
+static void model_destroy(Model* m) {
+    if (!m) return;
+    if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+    cudaFree(m->ws);
+    cudaFreeHost(m->pinned_active);
+    delete m;
+}
+
+#define WSB_RUN(expr)        \
+    do {                     \
+        int _rc = (expr);    \
+        if (_rc) return _rc; \
+    } while (0)
+
+static int linear(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, int M, int N, int K, int act,
+                  const float* resid, void* out, int out_mode, cudaStream_t s, int block_n = 0) {
+    GemmArgs g;
+    g.A = A;
+    g.lda = K;
+    g.W = W;
+    g.M = M;
+    g.N = N;
+    g.K = K;
+    g.bias = bias;
+    g.act = act;
+    g.resid = resid;
+    g.ldr = N;
+    g.out = out;
+    g.ldc = N;
+    g.out_mode = out_mode;
+    g.block_n = block_n;
+    return gemm_bf16(g, s);
+}
+
+static int encode(Model* m, const float* feats, int B, float* hidden_f32, cudaStream_t s) {
+    const wsb_model_config& c = m->cfg;
+    WSB_REQUIRE(B >= 1 && B <= c.max_batch, "batch exceeds the model's max_batch");
+    const int d = c.d_model, T = m->T, rows = B * T;
+    const long long h1_stride = static_cast<long long>(c.n_cols + 1) * d;
+    WSB_RUN(conv1_gelu(feats, m->conv1_wt, m->conv1_b, m->h1p, B, c.n_cols, d, h1_stride, s));
+    {   // conv2 (k=3, stride 2, pad 1) as an im2col-free GEMM: row t' of batch b is the contiguous span
+        // h1p[b][2t' .. 2t'+2][:] (3d elements), i.e. a strided, overlapping view of h1p.
+        GemmArgs g;
+        g.A = m->h1p;
+        g.lda = 2LL * d;
+        g.a_rows_per_batch = T;
+        g.a_batch_stride = h1_stride;
+        g.W = m->conv2_w;
+        g.M = rows;
+        g.N = d;
+        g.K = 3 * d;
+        g.bias = m->conv2_b;
+        g.act = GEMM_ACT_GELU;
+        g.rowvec = m->enc_pos;
+        g.rows_per_batch = T;
+        g.out = m->x;
+        g.ldc = d;
+        g.out_mode = GEMM_OUT_F32;
+        WSB_RUN(gemm_bf16(g, s));
+    }
+    for (int l = 0; l < c.n_layers; ++l) {
+        const EncLayer& e = m->enc[l];
+        WSB_RUN(layernorm_f32_to_bf16(m->x, e.ln1_g, e.ln1_b, m->xn, nullptr, rows, d, s));
+        WSB_RUN(linear(m->xn, e.qkv_w, e.qkv_b, rows, 3 * d, d, GEMM_ACT_NONE, nullptr, m->qkv, GEMM_OUT_BF16, s));
+        WSB_RUN(encoder_attention(m->qkv, m->att, B, T, c.n_heads, s));
+        WSB_RUN(linear(m->att, e.o_w, e.o_b, rows, d, d, GEMM_ACT_NONE, m->x, m->x, GEMM_OUT_F32, s));
+        WSB_RUN(layernorm_f32_to_bf16(m->x, e.ln2_g, e.ln2_b, m->xn, nullptr, rows, d, s));
+        WSB_RUN(linear(m->xn, e.fc1_w, e.fc1_b, rows, c.ffn_dim, d, GEMM_ACT_GELU, nullptr, m->ff, GEMM_OUT_BF16, s));
+        WSB_RUN(linear(m->ff, e.fc2_w, e.fc2_b, rows, d, c.ffn_dim, GEMM_ACT_NONE, m->x, m->x, GEMM_OUT_F32, s));
+    }
+    WSB_RUN(layernorm_f32_to_bf16(m->x, m->enc_ln_g, m->enc_ln_b, m->enc_out, hidden_f32, rows, d, s));
+    m->last_batch = B;
+    return 0;
+}
+
+// one decoder position for all rows.  with_logits: project + arg-max + finalize; else prefill advance.
+static int decode_step(Model* m, int B, bool with_logits, bool first_generated, int prompt_len, int max_new,
+                       const int* forced, int forced_ld, int eos_id, int pad_id, cudaStream_t s) {
+    const wsb_model_config& c = m->cfg;
+    const int d = c.d_model, F = c.ffn_dim, L = c.n_layers, H = c.n_heads, T = m->T, tmax = c.max_target_positions;
+    const unsigned char* fin = forced ? nullptr : m->finished;
+    WSB_RUN(embed_tokens_step(m->next_token, m->step, 0, m->dec_emb, m->dec_pos, m->dx, B, d, s));
+    const long long cache_l = static_cast<long long>(B) * H * tmax * 64;
+    for (int l = 0; l < L; ++l) {
+        const DecLayer& e = m->dec[l];
+        WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln1_g, e.ln1_b, m->dxn, nullptr, B, d, s));
+        WSB_RUN(linear(m->dxn, e.sqkv_w, e.sqkv_b, B, 3 * d, d, GEMM_ACT_NONE, nullptr, m->dqkv, GEMM_OUT_BF16, s));
+        WSB_RUN(decode_self_attention(m->dqkv, d, m->k_cache + l * cache_l, m->v_cache + l * cache_l, tmax, m->step, 0,
+                                      fin, m->datt, B, H, s));
+        WSB_RUN(linear(m->datt, e.so_w, e.so_b, B, d, d, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s));
+        WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln2_g, e.ln2_b, m->dxn, nullptr, B, d, s));
+        WSB_RUN(linear(m->dxn, e.cq_w, e.cq_b, B, d, d, GEMM_ACT_NONE, nullptr, m->dq, GEMM_OUT_BF16, s));
+        WSB_RUN(decode_cross_attention(m->dq, d, m->cross_kv, l, L, T, fin, m->datt, B, H, s));
+        WSB_RUN(linear(m->datt, e.co_w, e.co_b, B, d, d, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s));
+        WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln3_g, e.ln3_b, m->dxn, nullptr, B, d, s));
+        WSB_RUN(linear(m->dxn, e.fc1_w, e.fc1_b, B, F, d, GEMM_ACT_GELU, nullptr, m->dff, GEMM_OUT_BF16, s));
+        WSB_RUN(linear(m->dff, e.fc2_w, e.fc2_b, B, d, F, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s));
+    }
+    if (!with_logits) return prefill_advance(m->next_token, forced, forced_ld, m->prompt_dev, m->step, B, s);
+    WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec_ln_g, m->dec_ln_b, m->dxn, nullptr, B, d, s));
+    GemmArgs g;
+    g.A = m->dxn;
+    g.lda = d;
+    g.W = m->dec_emb;
+    g.M = B;
+    g.N = c.vocab_size;
+    g.K = d;
+    g.bias = m->suppress;
+    g.bias2 = first_generated ? m->begin_suppress : nullptr;
+    g.out_mode = GEMM_OUT_ARGMAX;
+    g.argmax_val = m->am_val;
+    g.argmax_idx = m->am_idx;
+    g.block_n = m->logits_bn;
+    WSB_RUN(gemm_bf16(g, s));
+    return argmax_finalize(m->am_val, m->am_idx, m->am_tiles, m->tokens, max_new, prompt_len - 1, m->next_token, forced,
+                           forced_ld, m->finished, m->step, m->n_active, eos_id, pad_id, B, s);
+}
+
+static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_id, int pad_id, int max_length,
+                    const int* forced, int* tokens_out, int* n_steps, int flags, cudaStream_t s) {
+    const wsb_model_config& c = m->cfg;
+    WSB_REQUIRE(B >= 1 && B <= c.max_batch && B == m->last_batch, "wsb_generate must follow wsb_encode with the same batch");
+    WSB_REQUIRE(prompt_len >= 1 && prompt_len <= 16, "prompt length in [1,16]");
+    WSB_REQUIRE(max_length > prompt_len && max_length <= c.max_target_positions, "max_length in (prompt_len, max_target_positions]");
+    const int d = c.d_model, L = c.n_layers, T = m->T, rows = B * T;
+    const int max_new = max_length - prompt_len;
+    // cross-attention K/V of every decoder layer in one GEMM, scattered head-major:
+    // cross_kv[b][layer][k|v][head][t][64]   (HF modeling_whisper.py:326-336, computed once and cached)
+    {
+        GemmArgs g;
+        g.A = m->enc_out;
+        g.lda = d;
+        g.W = m->crosskv_w;
+        g.M = rows;
+        g.N = 2 * L * d;
+        g.K = d;
+        g.bias = m->crosskv_b;
+        g.out = m->cross_kv;
+        g.out_mode = GEMM_OUT_HEADMAJOR;
+        g.rows_per_batch = T;
+        WSB_RUN(gemm_bf16(g, s));
+    }
+    // decode state
+    std::vector<int> init_tok(B, prompt[0]);
+    WSB_CHECK_CUDA(cudaMemcpyAsync(m->prompt_dev, prompt, sizeof(int) * prompt_len, cudaMemcpyHostToDevice, s));
+    if (forced) {
+        WSB_CHECK_CUDA(cudaMemcpy2DAsync(m->next_token, sizeof(int), forced, sizeof(int) * max_length, sizeof(int), B,
+                                         cudaMemcpyDeviceToDevice, s));
+    } else {
+        WSB_CHECK_CUDA(cudaMemcpyAsync(m->next_token, init_tok.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    }
+    WSB_CHECK_CUDA(cudaMemsetAsync(m->step, 0, sizeof(int) * 4, s));
+    WSB_CHECK_CUDA(cudaMemsetAsync(m->finished, 0, B, s));
+    WSB_CHECK_CUDA(cudaMemcpyAsync(m->n_active, &B, sizeof(int), cudaMemcpyHostToDevice, s));
+    WSB_CHECK_CUDA(cudaStreamSynchronize(s));              // init_tok / B are stack/host temporaries
+    {   // pad everything: rows that never get written (early stop) must read as pad
+        std::vector<int> pad(static_cast<size_t>(B) * max_new, pad_id);
+        WSB_CHECK_CUDA(cudaMemcpyAsync(m->tokens, pad.data(), sizeof(int) * pad.size(), cudaMemcpyHostToDevice, s));
+        WSB_CHECK_CUDA(cudaStreamSynchronize(s));
+    }
+    for (int pos = 0; pos + 1 < prompt_len; ++pos)
+        WSB_RUN(decode_step(m, B, false, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
+    // first generated token (begin-suppress mask active)
+    WSB_RUN(decode_step(m, B, true, true, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
+    int steps_done = 1;
+    const bool use_graph = (flags & 1) != 0 && max_new > 2;
+    if (use_graph && (m->graph_exec == nullptr || m->graph_batch != B * 2 + (forced ? 1 : 0))) {
+        if (m->graph_exec) {
+            cudaGraphExecDestroy(m->graph_exec);
+            m->graph_exec = nullptr;
+        }
+        cudaGraph_t graph = nullptr;
+        WSB_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = decode_step(m, B, true, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s);
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc) return rc;
+        WSB_CHECK_CUDA(ce);
+        WSB_CHECK_CUDA(cudaGraphInstantiate(&m->graph_exec, graph, 0));
+        cudaGraphDestroy(graph);
+        m->graph_batch = B * 2 + (forced ? 1 : 0);
+    }
+    const int check_every = 8;
+    while (steps_done < max_new) {
+        if (use_graph) {
+            WSB_CHECK_CUDA(cudaGraphLaunch(m->graph_exec, s));
+            count_launch(0);
+        } else {
+            WSB_RUN(decode_step(m, B, true, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
+        }
+        ++steps_done;
+        if (!forced && (steps_done % check_every) == 0 && steps_done < max_new) {
+            WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active, m->n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+            WSB_CHECK_CUDA(cudaStreamSynchronize(s));
+            if (m->pinned_active[0] <= 0) break;
+        }
+    }
+    WSB_CHECK_CUDA(cudaMemcpyAsync(tokens_out, m->tokens, sizeof(int) * static_cast<size_t>(B) * max_new,
+                                   cudaMemcpyDeviceToDevice, s));
+    if (n_steps) *n_steps = steps_done;
+    return 0;
+}
+
+}  // namespace wsb
+
+// =============================================================================================== C ABI
+using namespace wsb;
+
+struct wsb_logmel_plan {
+    LogmelPlan* impl;
+};
+struct wsb_model {
+    Model* impl;
+};
+
+extern "C" {
+
+int wsb_abi_version(void) { return WSB_ABI_VERSION; }
+const char* wsb_last_error(void) { return get_last_error(); }
+long long wsb_launch_count(int reset) {
+    long long v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return v;
+}
+
+int wsb_logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float* mel_filters, int n_freq,
+                           wsb_logmel_plan** plan) {
+    WSB_REQUIRE(plan != nullptr && mel_filters != nullptr, "null argument");
+    LogmelPlan* impl = nullptr;
+    int rc = logmel_plan_create(n_fft, hop, clip_len, n_cols, mel_filters, n_freq, &impl);
+    if (rc) return rc;
+    *plan = new wsb_logmel_plan{impl};
+    return 0;
+}
+void wsb_logmel_plan_destroy(wsb_logmel_plan* plan) {
+    if (!plan) return;
+    logmel_plan_destroy(plan->impl);
+    delete plan;
+}
+int wsb_logmel_run(const wsb_logmel_plan* plan, const float* audio_dev, const int64_t* windows_dev, int n_windows,
+                   float* features_dev, void* stream) {
+    WSB_REQUIRE(plan != nullptr, "null plan");
+    return logmel_run(plan->impl, audio_dev, reinterpret_cast<const long long*>(windows_dev), n_windows, features_dev,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int wsb_model_create(const wsb_model_config* cfg, const char* const* names, const void* const* tensors_dev,
+                     int n_tensors, wsb_model** model) {
+    WSB_REQUIRE(cfg && names && tensors_dev && model, "null argument");
+    Model* impl = nullptr;
+    int rc = model_create(cfg, names, tensors_dev, n_tensors, &impl);
+    if (rc) return rc;
+    *model = new wsb_model{impl};
+    return 0;
+}
+void wsb_model_destroy(wsb_model* model) {
+    if (!model) return;
+    model_destroy(model->impl);
+    delete model;
+}
+size_t wsb_model_workspace_bytes(const wsb_model* model) { return model ? model->impl->ws_bytes : 0; }
+
+int wsb_encode(wsb_model* model, const float* features_dev, int batch, float* hidden_f32_dev, void* stream) {
+    WSB_REQUIRE(model != nullptr, "null model");
+    return encode(model->impl, features_dev, batch, hidden_f32_dev, static_cast<cudaStream_t>(stream));
+}
+int wsb_generate(wsb_model* model, int batch, const int32_t* prompt, int prompt_len, int eos_id, int pad_id,
+                 int max_length, const int32_t* forced_dev, int32_t* tokens_dev, int* n_steps, int flags, void* stream) {
+    WSB_REQUIRE(model != nullptr && prompt != nullptr && tokens_dev != nullptr, "null argument");
+    return generate(model->impl, batch, prompt, prompt_len, eos_id, pad_id, max_length, forced_dev, tokens_dev, n_steps,
+                    flags, static_cast<cudaStream_t>(stream));
+}
+
+int wsb_gemm_bf16(const void* a_dev, const void* w_dev, int M, int N, int K, const float* bias_dev, int gelu,
+                  const float* resid_dev, void* c_dev, int out_f32, int block_n, void* stream) {
+    return linear(static_cast<const __nv_bfloat16*>(a_dev), static_cast<const __nv_bfloat16*>(w_dev), bias_dev, M, N, K,
+                  gelu ? GEMM_ACT_GELU : GEMM_ACT_NONE, resid_dev, c_dev, out_f32 ? GEMM_OUT_F32 : GEMM_OUT_BF16,
+                  static_cast<cudaStream_t>(stream), block_n);
+}
+int wsb_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_dev, void* out_bf16_dev,
+                  float* out_f32_dev, int rows, int d, void* stream) {
+    return layernorm_f32_to_bf16(x_dev, gamma_dev, beta_dev, static_cast<__nv_bfloat16*>(out_bf16_dev), out_f32_dev, rows,
+                                 d, static_cast<cudaStream_t>(stream));
+}
+int wsb_encoder_attention(const void* qkv_dev, void* out_dev, int batch, int T, int n_heads, void* stream) {
+    return encoder_attention(static_cast<const __nv_bfloat16*>(qkv_dev), static_cast<__nv_bfloat16*>(out_dev), batch, T,
+                             n_heads, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

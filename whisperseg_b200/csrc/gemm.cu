@@ -1,0 +1,425 @@
+// K3 -- persistent, warp-specialised bf16 GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+//   C[M,N] = epilogue( A[M,K] * W[N,K]^T )        A, W bf16 (K contiguous), fp32 accumulation
+//
+// Replaces every nn.Linear / conv2 the reference reaches through HF WhisperEncoder/Decoder
+// (modeling_whisper.py:279-282, 376-377, 619-625) -- cuBLAS/cuDNN library calls there.
+//
+// Structure (one CTA per SM, 256 threads, tiles 128 x BN x 64):
+//   warp 0   TMA producer: cp.async.bulk.tensor loads of the A and W tiles into a STAGES-deep ring
+//            of 128B-swizzled shared-memory buffers, completion signalled on `full` mbarriers;
+//   warp 1   MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
+//            accumulating in TMEM; tcgen05.commit releases the stage (`empty`) and, after the last
+//            k-block, publishes the accumulator (`tmem_full`);
+//   warp 2   TMEM allocator (2 accumulator buffers of BN columns, so the epilogue of tile i overlaps
+//            the main loop of tile i+1);
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused bias / GELU /
+//            positional row-vector / fp32 residual / arg-max -> global.
+// Tiles are visited n-fastest so the A tile is read from HBM once and re-used out of L2 by the other
+// n-tiles, while W (<= a few MB) stays L2 resident.
+#include "common.cuh"
+#include "wsb_internal.h"
+
+namespace wsb {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 256;
+constexpr int kABytes = kBM * kBK * 2;
+
+struct GemmDev {
+    int M, N, K;
+    int a_rows_per_batch;          // 0 = flat
+    const float* bias;
+    const float* bias2;
+    int act;
+    const float* resid;
+    long long ldr;
+    const float* rowvec;
+    int out_mode;
+    void* out;
+    long long ldc;
+    int rows_per_batch;
+    float* argmax_val;
+    int* argmax_idx;
+    int m_tiles, n_tiles;
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+    static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int S = Cfg::kStages;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tmem_full = bars + 2 * S;
+    uint64_t* tmem_empty = bars + 2 * S + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int k_blocks = p.K / kBK;
+    const int tiles_per_batch = p.a_rows_per_batch > 0 ? (p.a_rows_per_batch + kBM - 1) / kBM : 0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+                int a_row, a_batch;
+                if (tiles_per_batch > 0) {
+                    a_batch = mt / tiles_per_batch;
+                    a_row = (mt - a_batch * tiles_per_batch) * kBM;
+                } else {
+                    a_batch = 0;
+                    a_row = mt * kBM;
+                }
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* sa = smem + stage * Cfg::kStageBytes;
+                    mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+                    tma_load_3d(sa, &tmA, &full[stage], kb * kBK, a_row, a_batch);
+                    tma_load_2d(sa + kABytes, &tmB, &full[stage], kb * kBK, nt * BN);
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+                const int as = local & 1;
+                const uint32_t aphase = (local >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint64_t da = umma_desc_k_sw128(sa);
+                    const uint64_t db = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k)
+                        umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty[stage]);
+                    if (kb == k_blocks - 1) umma_commit(&tmem_full[as]);
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        const int row_in_tile = q * 32 + lane;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+            const int as = local & 1;
+            const uint32_t aphase = (local >> 1) & 1;
+            long long grow;
+            int brow;                                  // row index within its batch (for rowvec / head-major)
+            bool valid;
+            if (tiles_per_batch > 0) {
+                const int b = mt / tiles_per_batch;
+                brow = (mt - b * tiles_per_batch) * kBM + row_in_tile;
+                valid = brow < p.a_rows_per_batch;
+                grow = static_cast<long long>(b) * p.a_rows_per_batch + brow;
+            } else {
+                grow = static_cast<long long>(mt) * kBM + row_in_tile;
+                valid = grow < p.M;
+                brow = p.rows_per_batch > 0 ? static_cast<int>(grow % p.rows_per_batch) : 0;
+            }
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            float best = -INFINITY;
+            int best_idx = nt * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
+                tmem_ld_wait();
+                const int n0 = nt * BN + c * 32;
+                if (!valid || n0 >= p.N) continue;
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                const bool full_chunk = (n0 + 32 <= p.N);
+                if (p.bias) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (full_chunk || n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
+                }
+                if (p.bias2) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (full_chunk || n0 + i < p.N) v[i] += __ldg(p.bias2 + n0 + i);
+                }
+                if (p.act == GEMM_ACT_GELU) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                }
+                if (p.rowvec) {
+                    const float* rv = p.rowvec + static_cast<long long>(brow) * p.N + n0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(rv + i));
+                        v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+                    }
+                }
+                if (p.resid) {
+                    const float* rs = p.resid + grow * p.ldr + n0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(rs + i);
+                        v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+                    }
+                }
+                if (p.out_mode == GEMM_OUT_F32) {
+                    float* o = reinterpret_cast<float*>(p.out) + grow * p.ldc + n0;
+                    if (full_chunk) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+                        for (int i = 0; i < 32 && n0 + i < p.N; ++i) o[i] = v[i];
+                    }
+                } else if (p.out_mode == GEMM_OUT_BF16 || p.out_mode == GEMM_OUT_HEADMAJOR) {
+                    __nv_bfloat16* o;
+                    if (p.out_mode == GEMM_OUT_BF16) {
+                        o = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + n0;
+                    } else {
+                        const long long b = grow / p.rows_per_batch;
+                        const long long t = grow - b * p.rows_per_batch;
+                        o = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                            ((b * (p.N >> 6) + (n0 >> 6)) * p.rows_per_batch + t) * 64 + (n0 & 63);
+                    }
+                    if (full_chunk) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            uint4 pk;
+                            pk.x = pack_bf16x2(v[i], v[i + 1]);
+                            pk.y = pack_bf16x2(v[i + 2], v[i + 3]);
+                            pk.z = pack_bf16x2(v[i + 4], v[i + 5]);
+                            pk.w = pack_bf16x2(v[i + 6], v[i + 7]);
+                            *reinterpret_cast<uint4*>(o + i) = pk;
+                        }
+                    } else {
+                        for (int i = 0; i < 32 && n0 + i < p.N; ++i) o[i] = __float2bfloat16(v[i]);
+                    }
+                } else {   // GEMM_OUT_ARGMAX
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if ((full_chunk || n0 + i < p.N) && v[i] > best) {
+                            best = v[i];
+                            best_idx = n0 + i;
+                        }
+                }
+            }
+            if (p.out_mode == GEMM_OUT_ARGMAX && valid) {
+                p.argmax_val[grow * p.n_tiles + nt] = best;
+                p.argmax_idx[grow * p.n_tiles + nt] = best_idx;
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn fn = get_encode_fn();
+    WSB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    WSB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) {
+        gstr[i] = strides_bytes[i];
+        WSB_REQUIRE((gstr[i] & 15) == 0, "TMA strides must be multiples of 16 bytes");
+    }
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                    gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+        return 4;
+    }
+    return 0;
+}
+
+int gemm_pick_block_n(int M, int N) {
+    // big GEMMs: widest tile (least operand traffic per flop); skinny (decode) GEMMs: enough tiles to
+    // keep most SMs streaming weights.  Tiles that would be mostly padding along N are avoided.
+    const int m_tiles = ceil_div(M, kBM);
+    int best = 32, best_tiles = -1;
+    for (int bn : {256, 128, 64, 32}) {
+        const int nt = ceil_div(N, bn);
+        if (static_cast<double>(nt) * bn > 1.15 * N && bn != 32) continue;
+        const int tiles = m_tiles * nt;
+        if (tiles >= 120) return bn;
+        if (tiles > best_tiles) {
+            best_tiles = tiles;
+            best = bn;
+        }
+    }
+    return best;
+}
+int gemm_n_tiles(int N, int block_n) { return ceil_div(N, block_n); }
+
+template <int BN>
+static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    static int num_sms = 0;
+    if (!attr_set) {
+        WSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        int dev = 0;
+        WSB_CHECK_CUDA(cudaGetDevice(&dev));
+        WSB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_set = true;
+    }
+    CUtensorMap tmA, tmB;
+    {
+        uint64_t dims[3], strides[2];
+        uint32_t box[3] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(kBM), 1};
+        dims[0] = static_cast<uint64_t>(a.K);
+        if (a.a_rows_per_batch > 0) {
+            dims[1] = static_cast<uint64_t>(a.a_rows_per_batch);
+            dims[2] = static_cast<uint64_t>(a.M / a.a_rows_per_batch);
+            strides[1] = static_cast<uint64_t>(a.a_batch_stride) * 2;
+        } else {
+            dims[1] = static_cast<uint64_t>(a.M);
+            dims[2] = 1;
+            strides[1] = static_cast<uint64_t>(a.M) * static_cast<uint64_t>(a.lda) * 2;
+        }
+        strides[0] = static_cast<uint64_t>(a.lda) * 2;
+        int rc = make_tmap_bf16(&tmA, a.A, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(a.K), static_cast<uint64_t>(a.N)};
+        uint64_t strides[1] = {static_cast<uint64_t>(a.K) * 2};
+        uint32_t box[2] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(BN)};
+        int rc = make_tmap_bf16(&tmB, a.W, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    GemmDev p;
+    p.M = a.M;
+    p.N = a.N;
+    p.K = a.K;
+    p.a_rows_per_batch = a.a_rows_per_batch;
+    p.bias = a.bias;
+    p.bias2 = a.bias2;
+    p.act = a.act;
+    p.resid = a.resid;
+    p.ldr = a.ldr;
+    p.rowvec = a.rowvec;
+    p.out_mode = a.out_mode;
+    p.out = a.out;
+    p.ldc = a.ldc;
+    p.rows_per_batch = a.rows_per_batch;
+    p.argmax_val = a.argmax_val;
+    p.argmax_idx = a.argmax_idx;
+    if (a.a_rows_per_batch > 0)
+        p.m_tiles = (a.M / a.a_rows_per_batch) * ceil_div(a.a_rows_per_batch, kBM);
+    else
+        p.m_tiles = ceil_div(a.M, kBM);
+    p.n_tiles = ceil_div(a.N, BN);
+    const int total = p.m_tiles * p.n_tiles;
+    const int grid = std::min(total, num_sms);
+    gemm_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
+    WSB_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "empty GEMM");
+    WSB_REQUIRE(a.K % kBK == 0, "K must be a multiple of 64");
+    WSB_REQUIRE(a.lda % 8 == 0, "lda must be a multiple of 8 elements (16 bytes)");
+    WSB_REQUIRE(a.a_rows_per_batch == 0 || a.M % a.a_rows_per_batch == 0, "M must be batches * rows_per_batch");
+    if (a.out_mode == GEMM_OUT_HEADMAJOR)
+        WSB_REQUIRE(a.N % 64 == 0 && a.rows_per_batch > 0 && a.M % a.rows_per_batch == 0, "head-major output shape");
+    if (a.resid || a.rowvec) WSB_REQUIRE(a.N % 32 == 0, "residual / row-vector epilogues need N % 32 == 0");
+    if (a.out_mode == GEMM_OUT_F32) WSB_REQUIRE(a.ldc % 4 == 0, "ldc must be a multiple of 4 for fp32 output");
+    if (a.out_mode == GEMM_OUT_BF16) WSB_REQUIRE(a.ldc % 8 == 0, "ldc must be a multiple of 8 for bf16 output");
+    int bn = a.block_n ? a.block_n : gemm_pick_block_n(a.M, a.N);
+    switch (bn) {
+        case 256: return launch_gemm<256>(a, stream);
+        case 128: return launch_gemm<128>(a, stream);
+        case 64: return launch_gemm<64>(a, stream);
+        case 32: return launch_gemm<32>(a, stream);
+        default: set_last_error("unsupported block_n"); return 2;
+    }
+}
+
+}  // namespace wsb

@@ -1,0 +1,70 @@
+// Internal C++ interfaces between the translation units of libwsb.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace wsb {
+
+// ------------------------------------------------------------------ K1 log-mel (logmel.cu)
+struct LogmelPlan;
+int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float* mel_filters_host, int n_freq,
+                       LogmelPlan** out);
+void logmel_plan_destroy(LogmelPlan* pl);
+int logmel_run(const LogmelPlan* pl, const float* audio_dev, const long long* win_dev, int n_win, float* out_dev,
+               cudaStream_t stream);
+size_t logmel_plan_smem(const LogmelPlan* pl);
+int logmel_plan_cluster(const LogmelPlan* pl);
+
+// ------------------------------------------------------------------ K3 GEMM (gemm.cu)
+// C[M,N] = A[M,K] (bf16, K contiguous) * W[N,K]^T (bf16, K contiguous), fp32 accumulation in TMEM.
+enum GemmOut : int {
+    GEMM_OUT_BF16 = 0,        // out bf16 [M, ldc]
+    GEMM_OUT_F32 = 1,         // out f32  [M, ldc]
+    GEMM_OUT_HEADMAJOR = 2,   // out bf16 [M/rows_per_batch][N/64][rows_per_batch][64]
+    GEMM_OUT_ARGMAX = 3,      // out: per (row, n-tile) partial {max, argmax} -- never materialises [M,N]
+};
+enum GemmAct : int { GEMM_ACT_NONE = 0, GEMM_ACT_GELU = 1 };
+
+struct GemmArgs {
+    const __nv_bfloat16* A = nullptr;   // activations
+    int64_t lda = 0;                    // elements between consecutive rows of A
+    int a_rows_per_batch = 0;           // 0: flat [M, K]; else A is [batches][a_rows_per_batch] rows with
+    int64_t a_batch_stride = 0;         //    a_batch_stride elements between batches (M = batches * rows)
+    const __nv_bfloat16* W = nullptr;   // [N, K] row-major (ldw = K)
+    int M = 0, N = 0, K = 0;
+    const float* bias = nullptr;        // [N] or null
+    const float* bias2 = nullptr;       // [N] or null (second additive vector, e.g. begin-suppress mask)
+    int act = GEMM_ACT_NONE;
+    const float* resid = nullptr;       // f32 [M, ldr] added after activation (may alias out)
+    int64_t ldr = 0;
+    const float* rowvec = nullptr;      // f32 [rows_per_batch, N] added per (row % rows_per_batch) (pos-emb)
+    int out_mode = GEMM_OUT_BF16;
+    void* out = nullptr;
+    int64_t ldc = 0;
+    int rows_per_batch = 0;             // for HEADMAJOR / rowvec
+    float* argmax_val = nullptr;        // [M, n_tiles]
+    int* argmax_idx = nullptr;          // [M, n_tiles]
+    int block_n = 0;                    // 0 = choose
+};
+int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
+int gemm_n_tiles(int N, int block_n);
+int gemm_pick_block_n(int M, int N);
+
+// ------------------------------------------------------------------ small kernels (elementwise.cu)
+int layernorm_f32_to_bf16(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out_bf16,
+                          float* out_f32, int rows, int d, cudaStream_t stream);
+int conv1_gelu(const float* feats, const float* w /*[d][80][3]*/, const float* b, __nv_bfloat16* out, int B,
+               int n_cols, int d, int64_t out_batch_stride, cudaStream_t stream);
+int embed_tokens(const int* tokens, const int* positions, const __nv_bfloat16* emb, const float* pos_emb, float* x,
+                 int B, int d, cudaStream_t stream);
+
+// ------------------------------------------------------------------ K4 encoder attention (attention.cu)
+int encoder_attention(const __nv_bfloat16* qkv /*[B*T, 3d]*/, __nv_bfloat16* out /*[B*T, d]*/, int B, int T,
+                      int n_heads, cudaStream_t stream);
+
+// ------------------------------------------------------------------ K5 decode kernels (decode.cu)
+struct DecodeAttnArgs;
+
+}  // namespace wsb

@@ -1,0 +1,143 @@
+"""Thin Python driver over the C ABI: owns device tensors (torch is used for memory and streams
+only) and calls libwsb for every piece of arithmetic."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .frontend import N_MELS, FrontendPlan
+from .weights import load_checkpoint, prepare_tensors
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class LogmelRunner:
+    """K1 plans are cached per (sr, spec_time_step, min_frequency) -- the reference rebuilds its
+    feature extractor on every segment() call (model.py:128)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.lib = _lib.load()
+        self._plans = {}
+
+    def plan_for(self, fp: FrontendPlan):
+        key = (fp.sr, fp.hop, fp.n_fft, fp.clip_len, fp.total_spec_columns, float(fp.min_frequency), float(fp.max_frequency))
+        h = self._plans.get(key)
+        if h is None:
+            with torch.cuda.device(self.device):
+                filt = np.ascontiguousarray(fp.mel_filters.astype(np.float32))
+                handle = ctypes.c_void_p()
+                _lib.check(self.lib.wsb_logmel_plan_create(fp.n_fft, fp.hop, fp.clip_len, fp.total_spec_columns,
+                                                           filt.ctypes.data_as(ctypes.c_void_p), filt.shape[0],
+                                                           ctypes.byref(handle)), "wsb_logmel_plan_create")
+            h = handle
+            self._plans[key] = h
+        return h
+
+    def run(self, fp: FrontendPlan, audio_dev, win_desc_dev, n_windows, stream):
+        """audio_dev f32 [N] device; win_desc_dev int64 [n_windows,3] device -> f32 [n_windows,80,n_cols]."""
+        out = torch.empty((n_windows, N_MELS, fp.total_spec_columns), dtype=torch.float32, device=self.device)
+        if n_windows:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.wsb_logmel_run(self.plan_for(fp), _ptr(audio_dev), _ptr(win_desc_dev), n_windows,
+                                                   _ptr(out), ctypes.c_void_p(stream.cuda_stream)), "wsb_logmel_run")
+        return out
+
+    def __del__(self):
+        try:
+            for h in self._plans.values():
+                self.lib.wsb_logmel_plan_destroy(h)
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class Engine:
+    """One model replica on one GPU."""
+
+    def __init__(self, model_path, device="cuda:0", max_batch=64, state=None):
+        if not torch.cuda.is_available():
+            raise _lib.WsbError("whisperseg_b200 needs a CUDA (sm_100) device; there is no CPU path")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        cfg, sd, gen = state if state is not None else load_checkpoint(model_path)
+        self.hf_config = cfg
+        self.max_batch = int(max_batch)
+        with torch.cuda.device(self.device):
+            self.tensors = prepare_tensors(cfg, sd, gen, self.device)
+            self.stream = torch.cuda.Stream(self.device)
+            mc = _lib.ModelConfig(cfg["d_model"], cfg["encoder_attention_heads"], cfg["encoder_layers"],
+                                  cfg["encoder_ffn_dim"], cfg["vocab_size"], cfg["num_mel_bins"],
+                                  2 * cfg["max_source_positions"], cfg["max_target_positions"], self.max_batch)
+            names = list(self.tensors.keys())
+            c_names = (ctypes.c_char_p * len(names))(*[n.encode() for n in names])
+            c_ptrs = (ctypes.c_void_p * len(names))(*[self.tensors[n].data_ptr() for n in names])
+            handle = ctypes.c_void_p()
+            torch.cuda.synchronize(self.device)
+            _lib.check(self.lib.wsb_model_create(ctypes.byref(mc), c_names, c_ptrs, len(names), ctypes.byref(handle)),
+                       "wsb_model_create")
+        self.handle = handle
+        self.d_model = cfg["d_model"]
+        self.n_cols = 2 * cfg["max_source_positions"]
+        self.T = cfg["max_source_positions"]
+        self.logmel = LogmelRunner(self.device)
+
+    def workspace_bytes(self):
+        return int(self.lib.wsb_model_workspace_bytes(self.handle))
+
+    def _enter(self):
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+
+    def _exit(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def encode(self, feats, want_hidden=False):
+        B = feats.shape[0]
+        assert feats.dtype == torch.float32 and feats.is_contiguous() and feats.device == self.device
+        hidden = torch.empty((B, self.T, self.d_model), dtype=torch.float32, device=self.device) if want_hidden else None
+        with torch.cuda.device(self.device):
+            self._enter()
+            _lib.check(self.lib.wsb_encode(self.handle, _ptr(feats), B, _ptr(hidden),
+                                           ctypes.c_void_p(self.stream.cuda_stream)), "wsb_encode")
+            self._exit()
+        return hidden
+
+    def generate(self, batch, prompt_ids, eos_id, pad_id, max_length, forced=None, use_graph=True):
+        """Greedy tokens int32 [batch, max_length - len(prompt)] (device) and #positions computed."""
+        n_new = max_length - len(prompt_ids)
+        tokens = torch.empty((batch, n_new), dtype=torch.int32, device=self.device)
+        prompt = (ctypes.c_int32 * len(prompt_ids))(*prompt_ids)
+        n_steps = ctypes.c_int(0)
+        if forced is not None:
+            assert forced.dtype == torch.int32 and forced.shape == (batch, max_length) and forced.is_contiguous()
+        with torch.cuda.device(self.device):
+            self._enter()
+            _lib.check(self.lib.wsb_generate(self.handle, batch, prompt, len(prompt_ids), eos_id, pad_id, max_length,
+                                             _ptr(forced), _ptr(tokens), ctypes.byref(n_steps), 1 if use_graph else 0,
+                                             ctypes.c_void_p(self.stream.cuda_stream)), "wsb_generate")
+            self._exit()
+        return tokens, n_steps.value
+
+    def features(self, fp: FrontendPlan, audio, windows):
+        """Host float32 audio + window list -> device features (H2D through pinned memory)."""
+        with torch.cuda.device(self.device):
+            a = np.ascontiguousarray(audio, dtype=np.float32)
+            host = torch.from_numpy(a) if a.size else torch.zeros(1, dtype=torch.float32)
+            audio_dev = host.pin_memory().to(self.device, non_blocking=True) if a.size else host.to(self.device)
+            desc = np.array([[w.start, 0, len(a)] for w in windows], dtype=np.int64).reshape(-1, 3)
+            desc_dev = torch.from_numpy(desc).to(self.device)
+            self._enter()
+            out = self.logmel.run(fp, audio_dev, desc_dev, len(windows), self.stream)
+            self._exit()
+            out.record_stream(self.stream)
+            audio_dev.record_stream(self.stream)
+            desc_dev.record_stream(self.stream)
+        return out
+
+    def __del__(self):
+        try:
+            self.lib.wsb_model_destroy(self.handle)
+        except Exception:  # noqa: BLE001
+            pass

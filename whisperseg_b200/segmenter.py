@@ -1,0 +1,205 @@
+"""Drop-in segmenter classes: the reference's Python API for the hot path, backed by libwsb.
+
+Mirrors reference model.py:
+  SegmenterBase            (:118-470)  -> SegmenterBase here (same attributes and method names)
+  WhisperSegmenter         (:625-676)  -> WhisperSegmenter
+  WhisperSegmenterFast     (:678-746)  -> WhisperSegmenterFast (same engine; the reference's CT2
+                                          directory layout `<path>/hf_model/` is accepted)
+  WhisperSegmenterForEval  (:572-622)  -> WhisperSegmenterForEval (model_path form)
+`segment()` keeps the reference signature and defaults (model.py:398-414) and returns
+{"onset": [float], "offset": [float], "cluster": [str]}.
+
+Design differences (B200-first):
+  * the front-end runs on the GPU for all windows of a call in one launch (the reference loops
+    over windows on the CPU, model.py:146-165); features never leave HBM;
+  * windows are independent, so `batch_size` only bounds memory: the engine decodes up to
+    `max_batch` windows together whatever `batch_size` says (results do not depend on batching);
+  * decoding is greedy: `num_beams` is accepted for signature compatibility, values != 1 fall
+    back to greedy with a one-time warning (BASELINE.json north_star; beam search is row "next").
+"""
+import json
+import os
+import threading
+import warnings
+
+import numpy as np
+import torch
+
+from . import postprocess as pp
+from .engine import Engine
+from .frontend import FrontendPlan, get_n_fft_given_sr
+from .tokens import TokenTable
+from .weights import load_checkpoint
+
+_warned_beams = False
+
+
+class SegmenterBase:
+    def __init__(self):
+        self.total_spec_columns = None
+        self.precision_bits = 3
+        self.cluster_codebook = None
+        self.inverse_cluster_codebook = None
+        self.default_segmentation_config = {}
+        self.engines = []
+        self.tokenizer = None
+        self.last_stats = {}
+
+    # ------------------------------------------------------------------ construction helpers
+    def _setup(self, model_path, device, device_ids, max_batch):
+        if device is None:
+            device = "cuda"
+        if device == "cpu" or not torch.cuda.is_available():
+            raise RuntimeError("whisperseg_b200 has no CPU path: a CUDA sm_100 (B200) device is required")
+        hf_dir = os.path.join(model_path, "hf_model")
+        ckpt_dir = hf_dir if os.path.isdir(hf_dir) and not os.path.isfile(os.path.join(model_path, "config.json")) else model_path
+        state = load_checkpoint(ckpt_dir)
+        cfg = state[0]
+        self.model_config = cfg
+        self.total_spec_columns = cfg["total_spec_columns"]                      # model.py:639
+        self.cluster_codebook = cfg["cluster_codebook"]                          # model.py:640
+        self.inverse_cluster_codebook = {v: k for k, v in self.cluster_codebook.items()}
+        if "default_segmentation_config" in cfg:                                 # model.py:643-644
+            self.default_segmentation_config.update(cfg["default_segmentation_config"])
+        self.tokenizer = TokenTable.from_pretrained(ckpt_dir)
+        self.device_list = [torch.device("cuda", int(g)) for g in device_ids]
+        self.engines = [Engine(ckpt_dir, dev, max_batch=max_batch, state=state) for dev in self.device_list]
+
+    def update_cluster_codebook(self, cluster_codebook):
+        self.cluster_codebook = cluster_codebook
+        self.inverse_cluster_codebook = {v: k for k, v in cluster_codebook.items()}
+
+    # ------------------------------------------------------------------ hot path
+    def get_sliced_audios_features(self, audio, sr, min_frequency, spec_time_step, num_trials, engine=None):
+        """Same contract as model.py:127-166, except that item[2] is a device tensor view."""
+        plan = FrontendPlan(sr, spec_time_step, min_frequency, total_spec_columns=self.total_spec_columns)
+        wins = plan.windows(len(audio), num_trials)
+        eng = engine or self.engines[0]
+        feats = eng.features(plan, audio, wins)
+        return [(w.trial_id, w.offset_time, feats[i], w.clip_seconds) for i, w in enumerate(wins)]
+
+    def _generate_on(self, eng, feats, max_length, status_monitor, texts_out, slot):
+        """feats: device tensor [n,80,cols] on eng.device -> list of decoded strings."""
+        tok = self.tokenizer
+        texts, n = [], feats.shape[0]
+        steps = 0
+        for pos in range(0, n, eng.max_batch):
+            chunk = feats[pos:pos + eng.max_batch].contiguous()
+            eng.encode(chunk)
+            ids, n_steps = eng.generate(chunk.shape[0], tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length)
+            steps += n_steps
+            texts += tok.batch_decode(ids.cpu().numpy().tolist())
+            if status_monitor is not None:                                       # model.py:672-674
+                status_monitor["progress"] = int(100 * min(1, (pos + eng.max_batch) / max(n, 1)))
+        texts_out[slot] = texts
+        self.last_stats["decode_steps"] = self.last_stats.get("decode_steps", 0) + steps
+
+    def generate_segment_text(self, sliced_audios_features, batch_size, max_length, num_beams, top_k=1, top_p=1.0,
+                              length_penalty=1.0, status_monitor=None):
+        """model.py:169-189: contiguous shards of the window list, one worker per device."""
+        global _warned_beams
+        if num_beams != 1 and not _warned_beams:
+            warnings.warn("whisperseg_b200 decodes greedily; num_beams=%d is treated as 1" % num_beams)
+            _warned_beams = True
+        n = len(sliced_audios_features)
+        if n == 0:
+            return []
+        feats_all = [item[2] for item in sliced_audios_features]
+        n_dev = len(self.engines)
+        per = int(np.ceil(n / n_dev))
+        outs, threads = {}, []
+        for slot, pos in enumerate(range(0, n, per)):
+            eng = self.engines[slot]
+            shard = feats_all[pos:pos + per]
+            stacked = torch.stack([f if torch.is_tensor(f) else torch.from_numpy(np.asarray(f)) for f in shard]).to(eng.device)
+            args = (eng, stacked, max_length, status_monitor if slot == 0 else None, outs, slot)
+            if n_dev == 1:
+                self._generate_on(*args)
+            else:
+                t = threading.Thread(target=self._generate_on, args=args)
+                t.start()
+                threads.append(t)
+        for t in threads:
+            t.join()
+        return [txt for slot in sorted(outs) for txt in outs[slot]]
+
+    def extract_segments(self, text, spec_time_step):
+        return pp.segments_from_text(text, spec_time_step, {v: k for k, v in self.cluster_codebook.items()})
+
+    def parse_generation(self, generated_text_list, sliced_audios_features, min_segment_length, audio_duration,
+                         spec_time_step, num_trials, eps, time_per_frame_for_voting, consolidation_method):
+        return pp.parse_generation(generated_text_list, sliced_audios_features, min_segment_length, audio_duration,
+                                   spec_time_step, num_trials, eps, time_per_frame_for_voting, consolidation_method,
+                                   self.cluster_codebook, self.precision_bits)
+
+    def consolidate_trials_by_clustering(self, trials, eps, min_samples):
+        return pp.consolidate_trials_by_clustering(trials, eps, min_samples)
+
+    def consolidate_trials_by_voting(self, trials, time_per_frame_for_voting):
+        return pp.consolidate_trials_by_voting(trials, time_per_frame_for_voting, self.cluster_codebook)
+
+    @torch.no_grad()
+    def segment(self, audio, sr, min_frequency=None, spec_time_step=None, min_segment_length=None, eps=None,
+                time_per_frame_for_voting=None, consolidation_method="clustering", max_length=448, batch_size=4,
+                num_trials=1, num_beams=4, top_k=1, top_p=1.0, length_penalty=1.0, status_monitor=None):
+        if min_frequency is None:
+            min_frequency = self.default_segmentation_config.get("min_frequency", 0)
+        if spec_time_step is None:
+            spec_time_step = self.default_segmentation_config.get("spec_time_step", 0.0025)
+        ratio = pp.RATIO_DECODING_TIME_STEP_TO_SPEC_TIME_STEP
+        if min_segment_length is None:
+            min_segment_length = spec_time_step * ratio
+        if eps is None:
+            eps = spec_time_step * ratio * 4
+        if time_per_frame_for_voting is None:
+            time_per_frame_for_voting = spec_time_step
+        audio = np.asarray(audio)
+        self.last_stats = {}
+        sliced = self.get_sliced_audios_features(audio, sr, min_frequency, spec_time_step, num_trials)
+        self.last_stats["n_windows"] = len(sliced)
+        texts = self.generate_segment_text(sliced, batch_size, max_length, num_beams, top_k, top_p, length_penalty,
+                                           status_monitor)
+        prediction = self.parse_generation(texts, sliced, min_segment_length, len(audio) / sr, spec_time_step, num_trials,
+                                           eps, time_per_frame_for_voting, consolidation_method)
+        return pp.correct_fft_blur_and_dedupe(prediction, sr, get_n_fft_given_sr(sr))
+
+    # ------------------------------------------------------------------ scoring (model.py:474-569)
+    def compute_syllable_score(self, prediction_on_offset_list, label_on_offset_list, tolerance):
+        return pp.compute_syllable_score(prediction_on_offset_list, label_on_offset_list, tolerance)
+
+    def segment_score(self, prediction, label, target_cluster=None, tolerance=None):
+        return pp.segment_score(prediction, label, target_cluster, tolerance,
+                                self.default_segmentation_config.get("spec_time_step", 0.0025))
+
+    def frame_score(self, prediction, label, target_cluster=None, time_per_frame_for_scoring=None):
+        return pp.frame_score(prediction, label, target_cluster, time_per_frame_for_scoring,
+                              self.default_segmentation_config.get("spec_time_step", 0.0025))
+
+
+class WhisperSegmenter(SegmenterBase):
+    def __init__(self, model_path, device=None, device_ids=[0, ], max_batch=64):
+        super().__init__()
+        self._setup(model_path, device, device_ids, max_batch)
+
+
+class WhisperSegmenterFast(WhisperSegmenter):
+    """The reference's CTranslate2-backed class; here it is the same sm_100a engine."""
+
+
+class WhisperSegmenterForEval(SegmenterBase):
+    def __init__(self, model_path=None, device=None, model=None, tokenizer=None, max_batch=64):
+        super().__init__()
+        if model_path is None:
+            raise ValueError("whisperseg_b200.WhisperSegmenterForEval needs model_path (an in-memory HF model "
+                             "belongs to the training path, which is out of scope)")
+        dev = torch.device(device) if device is not None else torch.device("cuda", 0)
+        self._setup(model_path, "cuda", [dev.index or 0], max_batch)
+        self.device = self.device_list[0]
+
+
+def save_synthetic_config_fields(path, **fields):
+    """Utility for tests/bench: add WhisperSeg fields to a config.json."""
+    p = os.path.join(path, "config.json")
+    cfg = json.load(open(p))
+    cfg.update(fields)
+    json.dump(cfg, open(p, "w"))
