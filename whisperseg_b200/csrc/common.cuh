@@ -17,6 +17,7 @@ const char* get_last_error();
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \
         if (_e != cudaSuccess) {                                                                 \
+            (void)cudaGetLastError(); /* do not leave a non-sticky error behind for the caller */ \
             ::wsb::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " +  \
                                   __FILE__ + ":" + std::to_string(__LINE__));                    \
             return 1;                                                                            \

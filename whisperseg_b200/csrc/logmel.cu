@@ -318,7 +318,7 @@ int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float
     pl->tile_stride = pl->frames_per_cta | 1;
     pl->smem_bytes = sizeof(float) * (static_cast<size_t>(pl->span_floats) + kMels * pl->tile_stride) +
                      sizeof(float2) * (static_cast<size_t>(M) + static_cast<size_t>(pl->n_groups) * 2 * M);
-    if (pl->smem_bytes > static_cast<size_t>(max_smem)) {
+    if (pl->smem_bytes + 1024 > static_cast<size_t>(max_smem)) {
         set_last_error("log-mel plan needs " + std::to_string(pl->smem_bytes) + " B shared memory per CTA (limit " +
                        std::to_string(max_smem) + "): hop/n_fft combination too large for an 8-CTA cluster");
         delete pl;
@@ -359,8 +359,11 @@ int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float
     WSB_CHECK_CUDA(cudaMemcpy(pl->mel_cnt, cnt.data(), sizeof(int) * kMels, cudaMemcpyHostToDevice));
     WSB_CHECK_CUDA(cudaMemcpy(pl->mel_off, off.data(), sizeof(int) * kMels, cudaMemcpyHostToDevice));
     WSB_CHECK_CUDA(cudaMemcpy(pl->mel_w, wts.data(), sizeof(float) * wts.size(), cudaMemcpyHostToDevice));
+    // plans with different shapes share the kernel: always opt in to the device maximum
+    cudaFuncAttributes fa;
+    WSB_CHECK_CUDA(cudaFuncGetAttributes(&fa, logmel_kernel));
     WSB_CHECK_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(pl->smem_bytes)));
+                                        max_smem - static_cast<int>(fa.sharedSizeBytes)));
     *out = pl;
     return 0;
 }
