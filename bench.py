@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds segmented per second on the WhisperSeg hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): whisper-large-architecture WhisperSeg, seeded shaped random-init
+weights, 10 min of synthetic 48 kHz audio PER GPU (sts 0.0025 -> 240 windows of 120 000 samples per
+GPU), num_trials=1, greedy decode with max_length 448.  One "step" = one pass of the hot path over
+that batch: fused log-mel -> encoder -> cross-K/V -> greedy KV-cache decode -> (N>1) one all-gather of
+the token lists.  N>1: one process per GPU (torchrun), windows sharded by index (weak scaling).
+
+  value : whole-job audio-s/s with the audio already resident in HBM (device-timed, max over ranks)
+  e2e   : the same through the public segmenter API with HOST audio: pinned H2D copy of the samples,
+          kernels, D2H of the tokens, host post-processing (wall-clock around synchronised calls)
+  roofline      : encoder GEMM class (tensor-bound), CUDA events inside the timed region
+  kernels       : the other kernel classes (log-mel HBM GB/s, attention, decode streams ...)
+  cpu_baseline  : the oracle port of the reference path timed on the host cores on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR, STS, MIN_FREQ = 48000, 0.0025, 0
+SECONDS_PER_GPU = 600.0
+PROMPT_LEN = 3
+CATS = ["conv1", "enc_gemm", "enc_attn", "enc_ln", "crosskv_gemm", "dec_gemm", "dec_logits", "dec_self_attn",
+        "dec_cross_attn", "dec_ln", "misc"]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+def make_audio(seconds, sr, seed, copies=1):
+    from oracle import synth
+    base = synth.synth_audio(seconds, sr, seed=seed)
+    if copies == 1:
+        return base
+    return np.concatenate([(base * (0.6 + 0.4 * (i + 1) / copies)).astype(np.float32) for i in range(copies)])
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (recipe in B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_sample(state, arch, max_length, n_windows=2, decode_steps=12, threads=None):
+    """Oracle port of the reference path (front-end -> HF-equivalent fp32 Whisper -> greedy) on the host
+    cores.  Measures front-end and encoder on `n_windows` windows and `decode_steps` greedy steps, and
+    scales the decode to the full budget (the per-step cost is constant: weight streaming)."""
+    import torch
+    from oracle import frontend_np as FO
+    from oracle import synth
+    from oracle.whisper_torch import WhisperOracle
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg, sd, gen = state
+    audio = make_audio(n_windows * 1000 * STS, SR, seed=2)
+    t0 = time.perf_counter()
+    feats = FO.sliced_audio_features(audio, SR, MIN_FREQ, STS, 1, dtype=np.float32)
+    t_front = time.perf_counter() - t0
+    orc = WhisperOracle(sd, cfg["encoder_attention_heads"], cfg["encoder_layers"])
+    x = torch.from_numpy(np.asarray([f[2] for f in feats]))
+    t0 = time.perf_counter()
+    enc = orc.encode(x)
+    t_enc = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    orc.greedy(enc, [synth.ID_SOT, synth.ID_EN, synth.ID_NOTIMESTAMPS], -1, synth.ID_EOT, PROMPT_LEN + decode_steps,
+               suppress_tokens=gen["suppress_tokens"])
+    t_dec = time.perf_counter() - t0                     # includes cross-K/V and the 3 prompt positions
+    n = len(feats)
+    per_step = t_dec / (decode_steps + PROMPT_LEN - 1)
+    total = t_front + t_enc + per_step * (max_length - 1)
+    audio_s = n * 1000 * STS
+    return dict(value=audio_s / total, unit="audio-s/s", cores=threads, kind="port",
+                sample="%d windows (%s arch): front-end %.2fs + encoder %.2fs measured, %d greedy steps measured "
+                       "(%.3fs/step at batch %d) and scaled to max_length=%d" %
+                       (n, arch, t_front, t_enc, decode_steps, per_step, n, max_length),
+                frontend_s=t_front, encoder_s=t_enc, decode_s_per_step=per_step)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; /root/reference does not exist on the
+    GPU box and the reference is pure Python + third-party transformers)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import synth
+    state = synth.make_state(args.arch, seed=0)
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_sample(state, args.arch, args.max_length, n_windows=args.ref_windows,
+                                 decode_steps=args.ref_decode_steps)
+        if i >= args.warmup:
+            vals.append(r["value"])
+        last = r
+    v = float(np.mean(vals))
+    n_win = int(SECONDS_PER_GPU / (1000 * STS))
+    line = dict(metric="audio-sec/sec", value=v, unit="audio-s/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1000.0 * SECONDS_PER_GPU / v, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=workload_config(args, n_win),
+                cpu_baseline=dict(value=v, unit="audio-s/s", cores=last["cores"], kind="port", sample=last["sample"]),
+                e2e=dict(value=v, unit="audio-s/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def workload_config(args, n_win):
+    return dict(workload="configs[1]: whisper-%s architecture, %d s synthetic %d Hz audio per GPU, spec_time_step %g, "
+                         "%d windows x %d samples per GPU, num_trials=1, greedy, max_length=%d" %
+                         (args.arch, int(SECONDS_PER_GPU), SR, STS, n_win, int(1000 * STS * SR), args.max_length),
+                arch=args.arch, windows_per_gpu=n_win, max_length=args.max_length, weights="seeded shaped random-init",
+                l2="inputs larger than L2 (weights 3 GB, activations > 1 GB per pass): no flush needed")
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import synth
+    from whisperseg_b200 import _lib
+    from whisperseg_b200.distributed import all_gather_tokens, segment_sharded
+    from whisperseg_b200.frontend import FrontendPlan
+    from whisperseg_b200.segmenter import WhisperSegmenter
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    pk = peaks()
+
+    n_win = int(SECONDS_PER_GPU / (1000 * STS))
+    state = synth.make_state(args.arch, seed=0)
+    tokdir = tempfile.mkdtemp(prefix="wsb_tok_")
+    synth.token_table_files(tokdir)
+    seg = WhisperSegmenter.from_state(state, tokdir, device="cuda", device_ids=[local_rank], max_batch=n_win)
+    eng, tok = seg.engines[0], seg.tokenizer
+    plan = FrontendPlan(SR, STS, MIN_FREQ)
+    max_new = args.max_length - PROMPT_LEN
+
+    # the logical recording is world x 600 s; every rank owns the windows of its own 600 s piece
+    base = make_audio(SECONDS_PER_GPU, SR, seed=2)
+    gain = 0.6 + 0.4 * (rank + 1) / world
+    piece = (base * gain).astype(np.float32) if world > 1 else base
+    wins = plan.windows(len(piece), 1)
+    assert len(wins) == n_win
+    audio_dev = eng.upload_audio(piece)
+    desc_dev = eng.window_descriptors(wins, 0, len(piece))
+    torch.cuda.synchronize()
+
+    def device_step():
+        feats = eng.features_device(plan, audio_dev, desc_dev, n_win)
+        eng.encode(feats)
+        ids, n_steps = eng.generate(n_win, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, args.max_length)
+        if world > 1:
+            ids = all_gather_tokens(ids, n_win, max_new, tok.pad_token_id)
+        return ids, n_steps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib.wsb_profile_enable(0)
+    for _ in range(args.warmup):
+        ids, n_steps = device_step()
+    barrier()
+    lib.wsb_launch_count(1)
+    lib.wsb_profile_enable(1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    steps_done = []
+    for _ in range(args.steps):
+        ids, n_steps = device_step()
+        steps_done.append(n_steps)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = int(lib.wsb_launch_count(0))
+    dt_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([dt_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt_ms = float(t.item())
+    prof = {}
+    import ctypes
+    for i, name in enumerate(CATS):
+        ms, cnt, work = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+        lib.wsb_profile_read(i, ctypes.byref(ms), ctypes.byref(cnt), ctypes.byref(work))
+        prof[name] = (ms.value, cnt.value, work.value)
+    lib.wsb_profile_enable(0)
+    value = world * SECONDS_PER_GPU * args.steps / (dt_ms / 1000.0)
+
+    # ---- kernel-class numbers ------------------------------------------------------------------
+    # log-mel: timed alone with CUDA events on its stream (burst HBM peak applies)
+    lm = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.stream.wait_stream(torch.cuda.current_stream())
+        a.record(eng.stream)
+        eng.logmel.run(plan, audio_dev, desc_dev, n_win, eng.stream)
+        b.record(eng.stream)
+        eng.stream.synchronize()
+        lm.append(a.elapsed_time(b))
+    lm_ms = float(np.median(lm[1:]))
+    lm_bytes = plan.logmel_bytes_per_window() * n_win
+    kernels = {"logmel": dict(bound="hbm", achieved=lm_bytes / lm_ms / 1e6, peak=pk["hbm"], unit="GB/s",
+                              frac=lm_bytes / lm_ms / 1e6 / pk["hbm"], ms_per_launch=lm_ms, launches=1,
+                              algorithmic_bytes_per_launch=lm_bytes,
+                              note="compute-co-limited: %.0f FLOP/B with a radix FFT (SURVEY 7.2-5)" %
+                                   (plan.logmel_flops_per_window() / plan.logmel_bytes_per_window()))}
+    # decode kernel classes: eager (graph-free) teacher-forced pass so every row stays active
+    lib.wsb_profile_enable(1)
+    forced = torch.full((n_win, args.max_length), tok.eos_token_id, dtype=torch.int32, device=dev)
+    forced[:, :PROMPT_LEN] = torch.tensor(tok.prompt_ids, dtype=torch.int32, device=dev)
+    forced[:, PROMPT_LEN:] = ids[rank * n_win:(rank + 1) * n_win] if world > 1 else ids
+    short = min(args.max_length, PROMPT_LEN + 6)
+    eng.generate(n_win, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, short,
+                 forced=forced[:, :short].contiguous(), use_graph=False)
+    torch.cuda.synchronize()
+    dprof = {}
+    for i, name in enumerate(CATS):
+        ms, cnt, work = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+        lib.wsb_profile_read(i, ctypes.byref(ms), ctypes.byref(cnt), ctypes.byref(work))
+        dprof[name] = (ms.value, cnt.value, work.value)
+    lib.wsb_profile_enable(0)
+
+    def tensor_entry(p, peak):
+        ms, cnt, work = p
+        if cnt == 0 or ms <= 0:
+            return None
+        ach = work / ms / 1e9
+        return dict(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, ms_per_launch=ms / cnt,
+                    launches=cnt, algorithmic_flops_per_launch=work / cnt)
+
+    def hbm_entry(p, peak):
+        ms, cnt, work = p
+        if cnt == 0 or ms <= 0 or work <= 0:
+            return None
+        ach = work / ms / 1e6
+        return dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, ms_per_launch=ms / cnt,
+                    launches=cnt, algorithmic_bytes_per_launch=work / cnt)
+
+    roof = tensor_entry(prof["enc_gemm"], pk["bf16_sustained"])
+    kernels["enc_attn"] = tensor_entry(prof["enc_attn"], pk["bf16_sustained"])
+    kernels["crosskv_gemm"] = tensor_entry(prof["crosskv_gemm"], pk["bf16_sustained"])
+    kernels["conv1"] = tensor_entry(prof["conv1"], pk["bf16_sustained"])
+    kernels["enc_ln"] = hbm_entry(prof["enc_ln"], pk["hbm"])
+    kernels["dec_cross_attn"] = hbm_entry(dprof["dec_cross_attn"], pk["hbm"])
+    d, L, H, F = synth.ARCHS[args.arch]
+    dec_weight_bytes = 2.0 * (L * (3 * d * d + d * d + d * d + d * d + 2 * d * F))
+    dg_ms, dg_cnt, _ = dprof["dec_gemm"]
+    if dg_cnt:
+        n_pos = dg_cnt / (6 * L)
+        kernels["dec_gemm"] = dict(bound="hbm", achieved=dec_weight_bytes * n_pos / dg_ms / 1e6, peak=pk["hbm"], unit="GB/s",
+                                   frac=dec_weight_bytes * n_pos / dg_ms / 1e6 / pk["hbm"], ms_per_launch=dg_ms / dg_cnt,
+                                   launches=dg_cnt, algorithmic_bytes_per_launch=dec_weight_bytes / (6 * L),
+                                   note="weight streaming at batch %d" % n_win)
+    shares = {k: v[0] for k, v in prof.items() if v[1]}
+    roofline = dict(bound="tensor", achieved=roof["achieved"], peak=roof["peak"], unit="TFLOP/s", frac=roof["frac"],
+                    traffic=None, kernel="gemm_kernel<BN> (encoder GEMM class: conv2, qkv, out-proj, fc1, fc2)",
+                    ms_per_launch=roof["ms_per_launch"], launches=roof["launches"],
+                    algorithmic_flops_per_launch=roof["algorithmic_flops_per_launch"],
+                    peak_source="%s cuBLAS bf16, sustained figure (kernel timed inside a long step)" % pk["source"])
+
+    # ---- end to end through the public API, host audio ---------------------------------------
+    full_audio = None
+    if world > 1:
+        full_audio = np.concatenate([(base * (0.6 + 0.4 * (r + 1) / world)).astype(np.float32) for r in range(world)])
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step():
+        if world > 1:
+            return segment_sharded(seg, full_audio, SR, MIN_FREQ, STS, max_length=args.max_length, num_trials=1)
+        return seg.segment(piece, SR, MIN_FREQ, STS, max_length=args.max_length, num_trials=1, num_beams=1)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = float(te.item())
+    e2e_value = world * SECONDS_PER_GPU * e2e_steps / t_e2e
+    h2d = len(piece) * 4 + n_win * 24
+    d2h = n_win * max_new * 4
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference_sample(state, args.arch, args.max_length, n_windows=args.ref_windows,
+                                       decode_steps=args.ref_decode_steps)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = dict(metric="audio-sec/sec", value=value, unit="audio-s/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=dt_ms / args.steps, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="bf16", data="synthetic", config=workload_config(args, n_win),
+                    e2e=dict(value=e2e_value, unit="audio-s/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             steps=e2e_steps, segments=len(res["onset"])),
+                    gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=kernels, cpu_baseline=cpu,
+                    decode_positions_per_step=float(np.mean(steps_done)),
+                    step_share_ms={k: v / args.steps for k, v in shares.items()})
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arch", default="large")
+    ap.add_argument("--max-length", type=int, default=448, dest="max_length")
+    ap.add_argument("--ref-windows", type=int, default=2, dest="ref_windows")
+    ap.add_argument("--ref-decode-steps", type=int, default=12, dest="ref_decode_steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -87,6 +87,16 @@ int wsb_generate(wsb_model* model, int batch, const int32_t* prompt, int prompt_
                  int max_length, const int32_t* forced_dev, int32_t* tokens_dev, int* n_steps, int flags,
                  void* stream);
 
+/* ---- CUDA-event profiling of kernel classes (bench.py's roofline numbers) -----------------------
+ * While enabled, every eagerly launched kernel is bracketed by CUDA events on its own stream.
+ * categories: 0 conv1, 1 encoder GEMMs (conv2, qkv, out, fc1, fc2), 2 encoder attention,
+ * 3 encoder LayerNorm, 4 cross-K/V GEMM, 5 decoder GEMMs, 6 logits+arg-max GEMM, 7 decode
+ * self-attention, 8 decode cross-attention, 9 decoder LayerNorm, 10 misc.
+ * wsb_profile_read: call after synchronising the stream; `work` = accumulated algorithmic FLOPs
+ * (GEMMs, attention) or bytes (LayerNorm, decode cross-attention) of the bracketed launches.      */
+int wsb_profile_enable(int enable);
+int wsb_profile_read(int category, double* ms, long long* launches, double* work);
+
 /* ---- individual kernels, exported for parity tests and profiling ------------------------------ */
 /* C = act(A W^T + bias) (+ resid): A bf16 [M][K], W bf16 [N][K], fp32 accumulate.
  * out_f32 != 0: C float32 [M][N] (+ optional float32 residual [M][N]); else C bf16 [M][N].      */

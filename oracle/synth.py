@@ -192,3 +192,102 @@ def synth_audio(seconds, sr, seed, band=(500.0, 8000.0), burst=(0.03, 0.25), gap
         t += dur
     np.clip(out, -1.0, 1.0, out=out)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Direct construction of a shaped checkpoint state (no HF model object): used by bench.py, where
+# instantiating a 1.5 B-parameter nn.Module just to overwrite its weights would waste minutes.
+def hf_config_dict(arch, cluster_codebook=None, default_segmentation_config=None):
+    d, L, H, F = ARCHS[arch]
+    cfg = dict(model_type="whisper", vocab_size=VOCAB_SIZE, num_mel_bins=80, d_model=d, encoder_layers=L,
+               decoder_layers=L, encoder_attention_heads=H, decoder_attention_heads=H, encoder_ffn_dim=F,
+               decoder_ffn_dim=F, max_source_positions=TOTAL_SPEC_COLUMNS // 2, max_target_positions=448,
+               pad_token_id=ID_EOT, bos_token_id=ID_EOT, eos_token_id=ID_EOT, decoder_start_token_id=ID_SOT,
+               activation_function="gelu", scale_embedding=False, total_spec_columns=TOTAL_SPEC_COLUMNS,
+               cluster_codebook=cluster_codebook if cluster_codebook is not None else {"vocal": 0, "b": 1},
+               suppress_tokens=None, begin_suppress_tokens=None)
+    if default_segmentation_config is not None:
+        cfg["default_segmentation_config"] = default_segmentation_config
+    return cfg
+
+
+def sinusoids(length, channels, max_timescale=10000):
+    """HF modeling_whisper.py:55-64 (encoder positional table)."""
+    import torch
+    inc = np.log(max_timescale) / (channels // 2 - 1)
+    inv = torch.exp(-inc * torch.arange(channels // 2, dtype=torch.float32))
+    t = torch.arange(length, dtype=torch.float32).view(-1, 1) * inv.view(1, -1)
+    return torch.cat([t.sin(), t.cos()], dim=1)
+
+
+def make_state(arch="large", seed=0, n_digits=2, eos_scale=2.0, qk_cross=3.0, qk_self=2.0, emb_std=0.05,
+               digit_scale=2.5, dtype=None):
+    """(config dict, state dict, generation dict) of a shaped random checkpoint -- same recipe as
+    shape_weights_, HF parameter names, drawn tensor by tensor from one seeded CPU generator."""
+    import torch
+    d, L, H, F = ARCHS[arch]
+    g = torch.Generator().manual_seed(2000 + seed)
+    sd = {}
+
+    def mat(name, out_f, in_f, gain=1.0, shape=None):
+        w = torch.randn(shape or (out_f, in_f), generator=g) * (gain / in_f ** 0.5)
+        sd[name] = w if dtype is None else w.to(dtype)
+
+    def vec(name, n, std=0.1):
+        sd[name] = torch.randn(n, generator=g) * std
+
+    def ln(prefix):
+        sd[prefix + ".weight"] = torch.ones(d)
+        sd[prefix + ".bias"] = torch.zeros(d)
+
+    def attn(prefix, qk):
+        mat(prefix + "q_proj.weight", d, d, qk)
+        vec(prefix + "q_proj.bias", d)
+        mat(prefix + "k_proj.weight", d, d, qk)
+        mat(prefix + "v_proj.weight", d, d)
+        vec(prefix + "v_proj.bias", d)
+        mat(prefix + "out_proj.weight", d, d)
+        vec(prefix + "out_proj.bias", d)
+
+    def mlp(prefix):
+        mat(prefix + "fc1.weight", F, d)
+        vec(prefix + "fc1.bias", F)
+        mat(prefix + "fc2.weight", d, F)
+        vec(prefix + "fc2.bias", d)
+
+    mat("model.encoder.conv1.weight", d, 80 * 3, shape=(d, 80, 3))
+    vec("model.encoder.conv1.bias", d)
+    mat("model.encoder.conv2.weight", d, d * 3, shape=(d, d, 3))
+    vec("model.encoder.conv2.bias", d)
+    sd["model.encoder.embed_positions.weight"] = sinusoids(TOTAL_SPEC_COLUMNS // 2, d)
+    for i in range(L):
+        p = "model.encoder.layers.%d." % i
+        ln(p + "self_attn_layer_norm")
+        attn(p + "self_attn.", qk_self)
+        ln(p + "final_layer_norm")
+        mlp(p)
+    ln("model.encoder.layer_norm")
+    emb = torch.randn(VOCAB_SIZE, d, generator=g) * emb_std
+    emb[ID_DIGIT0:ID_DIGIT0 + n_digits] *= digit_scale
+    emb[ID_EOT] *= eos_scale
+    sd["model.decoder.embed_tokens.weight"] = emb
+    sd["model.decoder.embed_positions.weight"] = torch.randn(448, d, generator=g)
+    for i in range(L):
+        p = "model.decoder.layers.%d." % i
+        ln(p + "self_attn_layer_norm")
+        attn(p + "self_attn.", qk_self)
+        ln(p + "encoder_attn_layer_norm")
+        attn(p + "encoder_attn.", qk_cross)
+        ln(p + "final_layer_norm")
+        mlp(p)
+    ln("model.decoder.layer_norm")
+    allowed = set(allowed_token_ids())
+    gen = dict(suppress_tokens=[i for i in range(VOCAB_SIZE) if i not in allowed], begin_suppress_tokens=None)
+    return hf_config_dict(arch), sd, gen
+
+
+def token_table_files(path):
+    """Write just the tokenizer files (tokenizer.json ...) so the product can build its TokenTable."""
+    os.makedirs(path, exist_ok=True)
+    build_tokenizer().save_pretrained(path)
+    return path

@@ -22,6 +22,72 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* get_last_error() { return g_last_error.c_str(); }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---------------------------------------------------------------------------- event profiling
+// Optional CUDA-event bracketing of kernel classes on the launching stream (bench.py's roofline
+// numbers).  Only eager launches are bracketed (never inside a graph capture).
+enum ProfCat : int {
+    PROF_CONV1 = 0, PROF_ENC_GEMM, PROF_ENC_ATTN, PROF_ENC_LN, PROF_CROSSKV_GEMM, PROF_DEC_GEMM, PROF_DEC_LOGITS,
+    PROF_DEC_SELF_ATTN, PROF_DEC_CROSS_ATTN, PROF_DEC_LN, PROF_DEC_MISC, PROF_NCAT
+};
+struct ProfRec {
+    cudaEvent_t a, b;
+    int cat;
+    double work;
+};
+struct Profiler {
+    bool enabled = false;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    double ms[PROF_NCAT] = {0};
+    double work[PROF_NCAT] = {0};
+    long long count[PROF_NCAT] = {0};
+    cudaEvent_t get() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void collect() {
+        for (auto& r : recs) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+                ms[r.cat] += t;
+                work[r.cat] += r.work;
+                count[r.cat] += 1;
+            }
+            pool.push_back(r.a);
+            pool.push_back(r.b);
+        }
+        recs.clear();
+    }
+};
+static Profiler g_prof;
+static bool g_capturing = false;
+struct ProfScope {
+    cudaStream_t s;
+    bool on;
+    ProfRec r;
+    ProfScope(int cat, double work, cudaStream_t stream) : s(stream), on(g_prof.enabled && !g_capturing) {
+        if (on) {
+            r.a = g_prof.get();
+            r.b = g_prof.get();
+            r.cat = cat;
+            r.work = work;
+            cudaEventRecord(r.a, s);
+        }
+    }
+    ~ProfScope() {
+        if (on) {
+            cudaEventRecord(r.b, s);
+            g_prof.recs.push_back(r);
+        }
+    }
+};
+
 struct EncLayer {
     const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
     const __nv_bfloat16 *qkv_w, *o_w, *fc1_w, *fc2_w;
@@ -56,6 +122,7 @@ struct Model {
     // CUDA graph of one steady-state decode step, keyed by batch
     cudaGraphExec_t graph_exec = nullptr;
     int graph_batch = -1;
+    int graph_kernels = 0;
     int* pinned_active = nullptr;
 };
 
@@ -200,7 +267,8 @@ static void model_destroy(Model* m) {
     } while (0)
 
 static int linear(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, int M, int N, int K, int act,
-                  const float* resid, void* out, int out_mode, cudaStream_t s, int block_n = 0) {
+                  const float* resid, void* out, int out_mode, cudaStream_t s, int block_n = 0, int cat = PROF_ENC_GEMM) {
+    ProfScope ps(cat, 2.0 * M * N * K, s);
     GemmArgs g;
     g.A = A;
     g.lda = K;
@@ -224,7 +292,10 @@ static int encode(Model* m, const float* feats, int B, float* hidden_f32, cudaSt
     WSB_REQUIRE(B >= 1 && B <= c.max_batch, "batch exceeds the model's max_batch");
     const int d = c.d_model, T = m->T, rows = B * T;
     const long long h1_stride = static_cast<long long>(c.n_cols + 1) * d;
-    WSB_RUN(conv1_gelu(feats, m->conv1_wt, m->conv1_b, m->h1p, B, c.n_cols, d, h1_stride, s));
+    {
+        ProfScope ps(PROF_CONV1, 2.0 * B * c.n_cols * 240.0 * d, s);
+        WSB_RUN(conv1_gelu(feats, m->conv1_wt, m->conv1_b, m->h1p, B, c.n_cols, d, h1_stride, s));
+    }
     {   // conv2 (k=3, stride 2, pad 1) as an im2col-free GEMM: row t' of batch b is the contiguous span
         // h1p[b][2t' .. 2t'+2][:] (3d elements), i.e. a strided, overlapping view of h1p.
         GemmArgs g;
@@ -243,15 +314,25 @@ static int encode(Model* m, const float* feats, int B, float* hidden_f32, cudaSt
         g.out = m->x;
         g.ldc = d;
         g.out_mode = GEMM_OUT_F32;
+        ProfScope ps(PROF_ENC_GEMM, 2.0 * rows * d * 3.0 * d, s);
         WSB_RUN(gemm_bf16(g, s));
     }
     for (int l = 0; l < c.n_layers; ++l) {
         const EncLayer& e = m->enc[l];
-        WSB_RUN(layernorm_f32_to_bf16(m->x, e.ln1_g, e.ln1_b, m->xn, nullptr, rows, d, s));
+        {
+            ProfScope ps(PROF_ENC_LN, 6.0 * rows * d, s);
+            WSB_RUN(layernorm_f32_to_bf16(m->x, e.ln1_g, e.ln1_b, m->xn, nullptr, rows, d, s));
+        }
         WSB_RUN(linear(m->xn, e.qkv_w, e.qkv_b, rows, 3 * d, d, GEMM_ACT_NONE, nullptr, m->qkv, GEMM_OUT_BF16, s));
-        WSB_RUN(encoder_attention(m->qkv, m->att, B, T, c.n_heads, s));
+        {
+            ProfScope ps(PROF_ENC_ATTN, 4.0 * B * c.n_heads * T * T * 64.0, s);
+            WSB_RUN(encoder_attention(m->qkv, m->att, B, T, c.n_heads, s));
+        }
         WSB_RUN(linear(m->att, e.o_w, e.o_b, rows, d, d, GEMM_ACT_NONE, m->x, m->x, GEMM_OUT_F32, s));
-        WSB_RUN(layernorm_f32_to_bf16(m->x, e.ln2_g, e.ln2_b, m->xn, nullptr, rows, d, s));
+        {
+            ProfScope ps(PROF_ENC_LN, 6.0 * rows * d, s);
+            WSB_RUN(layernorm_f32_to_bf16(m->x, e.ln2_g, e.ln2_b, m->xn, nullptr, rows, d, s));
+        }
         WSB_RUN(linear(m->xn, e.fc1_w, e.fc1_b, rows, c.ffn_dim, d, GEMM_ACT_GELU, nullptr, m->ff, GEMM_OUT_BF16, s));
         WSB_RUN(linear(m->ff, e.fc2_w, e.fc2_b, rows, d, c.ffn_dim, GEMM_ACT_NONE, m->x, m->x, GEMM_OUT_F32, s));
     }
@@ -270,18 +351,33 @@ static int decode_step(Model* m, int B, bool with_logits, bool first_generated, 
     const long long cache_l = static_cast<long long>(B) * H * tmax * 64;
     for (int l = 0; l < L; ++l) {
         const DecLayer& e = m->dec[l];
-        WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln1_g, e.ln1_b, m->dxn, nullptr, B, d, s));
-        WSB_RUN(linear(m->dxn, e.sqkv_w, e.sqkv_b, B, 3 * d, d, GEMM_ACT_NONE, nullptr, m->dqkv, GEMM_OUT_BF16, s));
+        {
+            ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
+            WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln1_g, e.ln1_b, m->dxn, nullptr, B, d, s));
+        }
+        WSB_RUN(linear(m->dxn, e.sqkv_w, e.sqkv_b, B, 3 * d, d, GEMM_ACT_NONE, nullptr, m->dqkv, GEMM_OUT_BF16, s, 0, PROF_DEC_GEMM));
+        {
+            ProfScope ps(PROF_DEC_SELF_ATTN, 0.0, s);
         WSB_RUN(decode_self_attention(m->dqkv, d, m->k_cache + l * cache_l, m->v_cache + l * cache_l, tmax, m->step, 0,
                                       fin, m->datt, B, H, s));
-        WSB_RUN(linear(m->datt, e.so_w, e.so_b, B, d, d, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s));
-        WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln2_g, e.ln2_b, m->dxn, nullptr, B, d, s));
-        WSB_RUN(linear(m->dxn, e.cq_w, e.cq_b, B, d, d, GEMM_ACT_NONE, nullptr, m->dq, GEMM_OUT_BF16, s));
-        WSB_RUN(decode_cross_attention(m->dq, d, m->cross_kv, l, L, T, fin, m->datt, B, H, s));
-        WSB_RUN(linear(m->datt, e.co_w, e.co_b, B, d, d, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s));
-        WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln3_g, e.ln3_b, m->dxn, nullptr, B, d, s));
-        WSB_RUN(linear(m->dxn, e.fc1_w, e.fc1_b, B, F, d, GEMM_ACT_GELU, nullptr, m->dff, GEMM_OUT_BF16, s));
-        WSB_RUN(linear(m->dff, e.fc2_w, e.fc2_b, B, d, F, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s));
+        }
+        WSB_RUN(linear(m->datt, e.so_w, e.so_b, B, d, d, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s, 0, PROF_DEC_GEMM));
+        {
+            ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
+            WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln2_g, e.ln2_b, m->dxn, nullptr, B, d, s));
+        }
+        WSB_RUN(linear(m->dxn, e.cq_w, e.cq_b, B, d, d, GEMM_ACT_NONE, nullptr, m->dq, GEMM_OUT_BF16, s, 0, PROF_DEC_GEMM));
+        {
+            ProfScope ps(PROF_DEC_CROSS_ATTN, 4.0 * B * H * T * 64.0, s);   // bytes: K and V blocks, bf16
+            WSB_RUN(decode_cross_attention(m->dq, d, m->cross_kv, l, L, T, fin, m->datt, B, H, s));
+        }
+        WSB_RUN(linear(m->datt, e.co_w, e.co_b, B, d, d, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s, 0, PROF_DEC_GEMM));
+        {
+            ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
+            WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln3_g, e.ln3_b, m->dxn, nullptr, B, d, s));
+        }
+        WSB_RUN(linear(m->dxn, e.fc1_w, e.fc1_b, B, F, d, GEMM_ACT_GELU, nullptr, m->dff, GEMM_OUT_BF16, s, 0, PROF_DEC_GEMM));
+        WSB_RUN(linear(m->dff, e.fc2_w, e.fc2_b, B, d, F, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s, 0, PROF_DEC_GEMM));
     }
     if (!with_logits) return prefill_advance(m->next_token, forced, forced_ld, m->prompt_dev, m->step, B, s);
     WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec_ln_g, m->dec_ln_b, m->dxn, nullptr, B, d, s));
@@ -298,7 +394,10 @@ static int decode_step(Model* m, int B, bool with_logits, bool first_generated, 
     g.argmax_val = m->am_val;
     g.argmax_idx = m->am_idx;
     g.block_n = m->logits_bn;
-    WSB_RUN(gemm_bf16(g, s));
+    {
+        ProfScope ps(PROF_DEC_LOGITS, 2.0 * B * c.vocab_size * d, s);
+        WSB_RUN(gemm_bf16(g, s));
+    }
     return argmax_finalize(m->am_val, m->am_idx, m->am_tiles, m->tokens, max_new, prompt_len - 1, m->next_token, forced,
                            forced_ld, m->finished, m->step, m->n_active, eos_id, pad_id, B, s);
 }
@@ -325,6 +424,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
         g.out = m->cross_kv;
         g.out_mode = GEMM_OUT_HEADMAJOR;
         g.rows_per_batch = T;
+        ProfScope ps(PROF_CROSSKV_GEMM, 2.0 * rows * 2.0 * L * d * d, s);
         WSB_RUN(gemm_bf16(g, s));
     }
     // decode state
@@ -358,7 +458,12 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
         }
         cudaGraph_t graph = nullptr;
         WSB_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        g_capturing = true;
+        const long long before = g_launches.load();
         int rc = decode_step(m, B, true, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s);
+        m->graph_kernels = static_cast<int>(g_launches.load() - before);
+        g_launches.store(before);                       // captured, not executed
+        g_capturing = false;
         cudaError_t ce = cudaStreamEndCapture(s, &graph);
         if (rc) return rc;
         WSB_CHECK_CUDA(ce);
@@ -370,7 +475,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     while (steps_done < max_new) {
         if (use_graph) {
             WSB_CHECK_CUDA(cudaGraphLaunch(m->graph_exec, s));
-            count_launch(0);
+            count_launch(m->graph_kernels);
         } else {
             WSB_RUN(decode_step(m, B, true, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
         }
@@ -455,6 +560,27 @@ int wsb_generate(wsb_model* model, int batch, const int32_t* prompt, int prompt_
     WSB_REQUIRE(model != nullptr && prompt != nullptr && tokens_dev != nullptr, "null argument");
     return generate(model->impl, batch, prompt, prompt_len, eos_id, pad_id, max_length, forced_dev, tokens_dev, n_steps,
                     flags, static_cast<cudaStream_t>(stream));
+}
+
+int wsb_profile_enable(int enable) {
+    g_prof.enabled = enable != 0;
+    if (enable) {
+        g_prof.collect();
+        for (int i = 0; i < PROF_NCAT; ++i) {
+            g_prof.ms[i] = 0;
+            g_prof.work[i] = 0;
+            g_prof.count[i] = 0;
+        }
+    }
+    return 0;
+}
+int wsb_profile_read(int category, double* ms, long long* launches, double* work) {
+    WSB_REQUIRE(category >= 0 && category < PROF_NCAT, "bad profile category");
+    g_prof.collect();                                   // caller has synchronised the stream
+    if (ms) *ms = g_prof.ms[category];
+    if (launches) *launches = g_prof.count[category];
+    if (work) *work = g_prof.work[category];
+    return 0;
 }
 
 int wsb_gemm_bf16(const void* a_dev, const void* w_dev, int M, int N, int K, const float* bias_dev, int gelu,

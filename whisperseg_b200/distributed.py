@@ -1,0 +1,105 @@
+"""Multi-GPU: one process per GPU (torchrun), windows sharded by index, one small all-gather.
+
+The reference fans windows out to one Python *thread* per GPU inside a single process and
+concatenates the per-thread text lists (reference model.py:169-189); there is no collective.
+Here every rank computes the same window plan, takes a contiguous shard of the window list
+(the reference's `ceil(n / n_devices)` split, model.py:172-173), uploads only the samples its
+windows touch, runs front-end + encoder + decode locally, and the generated token ids are
+exchanged with ONE all-gather of a padded int32 [windows_per_rank, max_new] tensor (NCCL over
+NVLink on GPUs, gloo in the CPU tests).  Post-processing then runs identically on every rank.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import postprocess as pp
+from .frontend import FrontendPlan, get_n_fft_given_sr
+
+
+def shard_bounds(n_items, world_size, rank):
+    per = int(np.ceil(n_items / world_size)) if n_items else 0
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per), per
+
+
+def all_gather_tokens(local_ids, per, max_new, pad_id, group=None):
+    """local_ids: int32 [n_local, max_new] (torch, any device).  Returns int32 [world*per, max_new]
+    on the same device; rows beyond a rank's shard are pad."""
+    world = dist.get_world_size(group)
+    buf = torch.full((per, max_new), pad_id, dtype=torch.int32, device=local_ids.device)
+    if local_ids.numel():
+        buf[:local_ids.shape[0]] = local_ids
+    out = torch.empty((world * per, max_new), dtype=torch.int32, device=local_ids.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    return out
+
+
+def local_slice(audio, windows, clip_len):
+    """Samples the shard's windows touch: (slice_start, audio[slice_start:slice_end])."""
+    if not windows:
+        return 0, np.zeros(0, dtype=np.float32)
+    lo = max(0, min(w.start for w in windows))
+    hi = min(len(audio), max(w.start + clip_len for w in windows))
+    hi = max(hi, lo)
+    lo -= lo % 4                                        # keep float4 alignment of the device buffer
+    return lo, np.ascontiguousarray(audio[lo:hi], dtype=np.float32)
+
+
+def segment_sharded(segmenter, audio, sr, min_frequency=None, spec_time_step=None, min_segment_length=None, eps=None,
+                    time_per_frame_for_voting=None, consolidation_method="clustering", max_length=448, num_trials=1,
+                    group=None, generate_fn=None):
+    """Drop-in for `segmenter.segment(...)` under torch.distributed: same result on every rank.
+
+    `generate_fn(windows, plan, audio_slice, slice_start) -> int32 tensor [n_local, max_new]` can be
+    injected (the gloo CPU tests use a scripted generator); by default the rank's engine runs."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    cfgd = segmenter.default_segmentation_config
+    if min_frequency is None:
+        min_frequency = cfgd.get("min_frequency", 0)
+    if spec_time_step is None:
+        spec_time_step = cfgd.get("spec_time_step", 0.0025)
+    ratio = pp.RATIO_DECODING_TIME_STEP_TO_SPEC_TIME_STEP
+    if min_segment_length is None:
+        min_segment_length = spec_time_step * ratio
+    if eps is None:
+        eps = spec_time_step * ratio * 4
+    if time_per_frame_for_voting is None:
+        time_per_frame_for_voting = spec_time_step
+    audio = np.asarray(audio)
+    plan = FrontendPlan(sr, spec_time_step, min_frequency, total_spec_columns=segmenter.total_spec_columns)
+    wins = plan.windows(len(audio), num_trials)
+    lo, hi, per = shard_bounds(len(wins), world, rank)
+    mine = wins[lo:hi]
+    tok = segmenter.tokenizer
+    max_new = max_length - len(tok.prompt_ids)
+    s0, piece = local_slice(audio, mine, plan.clip_len)
+    if generate_fn is None:
+        local_ids = _engine_generate(segmenter, plan, mine, piece, s0, len(audio), max_length)
+    else:
+        local_ids = generate_fn(mine, plan, piece, s0)
+    gathered = all_gather_tokens(local_ids, per, max_new, tok.pad_token_id, group)
+    rows = gathered.cpu().numpy()
+    texts = []
+    for r in range(world):
+        a, b, _ = shard_bounds(len(wins), world, r)
+        texts += tok.batch_decode(rows[r * per:r * per + (b - a)].tolist())
+    pred = pp.parse_generation(texts, [w.as_tuple() for w in wins], min_segment_length, len(audio) / sr, spec_time_step,
+                               num_trials, eps, time_per_frame_for_voting, consolidation_method,
+                               segmenter.cluster_codebook, segmenter.precision_bits)
+    return pp.correct_fft_blur_and_dedupe(pred, sr, get_n_fft_given_sr(sr))
+
+
+def _engine_generate(segmenter, plan, windows, piece, slice_start, n_total, max_length):
+    eng = segmenter.engines[0]
+    tok = segmenter.tokenizer
+    max_new = max_length - len(tok.prompt_ids)
+    if not windows:
+        return torch.zeros((0, max_new), dtype=torch.int32, device=eng.device)
+    feats = eng.features_sliced(plan, piece, windows, slice_start, n_total)
+    outs = []
+    for pos in range(0, len(windows), eng.max_batch):
+        chunk = feats[pos:pos + eng.max_batch].contiguous()
+        eng.encode(chunk)
+        ids, _ = eng.generate(chunk.shape[0], tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length)
+        outs.append(ids)
+    return torch.cat(outs, 0)

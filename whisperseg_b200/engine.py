@@ -122,18 +122,33 @@ class Engine:
 
     def features(self, fp: FrontendPlan, audio, windows):
         """Host float32 audio + window list -> device features (H2D through pinned memory)."""
+        return self.features_sliced(fp, audio, windows, 0, len(audio))
+
+    def features_sliced(self, fp: FrontendPlan, piece, windows, slice_start, n_total):
+        """`piece` = audio[slice_start : slice_start + len(piece)] holds every in-range sample the
+        windows touch; window starts are given in whole-recording coordinates."""
         with torch.cuda.device(self.device):
-            a = np.ascontiguousarray(audio, dtype=np.float32)
-            host = torch.from_numpy(a) if a.size else torch.zeros(1, dtype=torch.float32)
-            audio_dev = host.pin_memory().to(self.device, non_blocking=True) if a.size else host.to(self.device)
-            desc = np.array([[w.start, 0, len(a)] for w in windows], dtype=np.int64).reshape(-1, 3)
-            desc_dev = torch.from_numpy(desc).to(self.device)
+            audio_dev = self.upload_audio(piece)
+            desc_dev = self.window_descriptors(windows, slice_start, len(piece))
+            return self.features_device(fp, audio_dev, desc_dev, len(windows))
+
+    def upload_audio(self, piece):
+        a = np.ascontiguousarray(piece, dtype=np.float32)
+        if a.size == 0:
+            return torch.zeros(4, dtype=torch.float32, device=self.device)
+        return torch.from_numpy(a).pin_memory().to(self.device, non_blocking=True)
+
+    def window_descriptors(self, windows, slice_start, n_valid):
+        desc = np.array([[w.start - slice_start, 0, n_valid] for w in windows], dtype=np.int64).reshape(-1, 3)
+        return torch.from_numpy(desc).to(self.device)
+
+    def features_device(self, fp: FrontendPlan, audio_dev, desc_dev, n_windows):
+        with torch.cuda.device(self.device):
             self._enter()
-            out = self.logmel.run(fp, audio_dev, desc_dev, len(windows), self.stream)
+            out = self.logmel.run(fp, audio_dev, desc_dev, n_windows, self.stream)
             self._exit()
-            out.record_stream(self.stream)
-            audio_dev.record_stream(self.stream)
-            desc_dev.record_stream(self.stream)
+            for t in (out, audio_dev, desc_dev):
+                t.record_stream(self.stream)
         return out
 
     def __del__(self):

@@ -46,14 +46,18 @@ class SegmenterBase:
         self.last_stats = {}
 
     # ------------------------------------------------------------------ construction helpers
-    def _setup(self, model_path, device, device_ids, max_batch):
+    def _setup(self, model_path, device, device_ids, max_batch, state=None, tokenizer_dir=None):
         if device is None:
             device = "cuda"
         if device == "cpu" or not torch.cuda.is_available():
             raise RuntimeError("whisperseg_b200 has no CPU path: a CUDA sm_100 (B200) device is required")
-        hf_dir = os.path.join(model_path, "hf_model")
-        ckpt_dir = hf_dir if os.path.isdir(hf_dir) and not os.path.isfile(os.path.join(model_path, "config.json")) else model_path
-        state = load_checkpoint(ckpt_dir)
+        if state is None:
+            hf_dir = os.path.join(model_path, "hf_model")
+            ckpt_dir = hf_dir if os.path.isdir(hf_dir) and not os.path.isfile(os.path.join(model_path, "config.json")) else model_path
+            state = load_checkpoint(ckpt_dir)
+            tokenizer_dir = ckpt_dir
+        else:
+            ckpt_dir = None
         cfg = state[0]
         self.model_config = cfg
         self.total_spec_columns = cfg["total_spec_columns"]                      # model.py:639
@@ -61,7 +65,7 @@ class SegmenterBase:
         self.inverse_cluster_codebook = {v: k for k, v in self.cluster_codebook.items()}
         if "default_segmentation_config" in cfg:                                 # model.py:643-644
             self.default_segmentation_config.update(cfg["default_segmentation_config"])
-        self.tokenizer = TokenTable.from_pretrained(ckpt_dir)
+        self.tokenizer = TokenTable.from_pretrained(tokenizer_dir)
         self.device_list = [torch.device("cuda", int(g)) for g in device_ids]
         self.engines = [Engine(ckpt_dir, dev, max_batch=max_batch, state=state) for dev in self.device_list]
 
@@ -180,6 +184,15 @@ class WhisperSegmenter(SegmenterBase):
     def __init__(self, model_path, device=None, device_ids=[0, ], max_batch=64):
         super().__init__()
         self._setup(model_path, device, device_ids, max_batch)
+
+    @classmethod
+    def from_state(cls, state, tokenizer_dir, device=None, device_ids=(0,), max_batch=64):
+        """Build from an in-memory (config dict, state dict, generation dict) triple -- what
+        weights.load_checkpoint returns -- plus a directory holding the tokenizer files."""
+        self = cls.__new__(cls)
+        SegmenterBase.__init__(self)
+        self._setup(None, device, list(device_ids), max_batch, state=state, tokenizer_dir=tokenizer_dir)
+        return self
 
 
 class WhisperSegmenterFast(WhisperSegmenter):
