@@ -1,0 +1,121 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the window sharding + single all-gather.  The
+generation step is a scripted stand-in (tokens are a deterministic function of the window index), so
+the test pins sharding, padding, gather order and rank-identical post-processing."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from whisperseg_b200 import postprocess as pp
+from whisperseg_b200.distributed import segment_sharded, shard_bounds
+from whisperseg_b200.frontend import FrontendPlan, get_n_fft_given_sr
+
+SR, STS, MAX_LEN = 16000, 0.01, 40
+BOOK = {"vocal": 0, "b": 1}
+TS0, EOT, PROMPT = 50364, 50257, [50258, 50259, 50363]
+
+
+class _Tok:
+    prompt_ids = PROMPT
+    eos_token_id = pad_token_id = EOT
+
+    def batch_decode(self, rows, skip_special_tokens=False):
+        out = []
+        for row in rows:
+            s = ""
+            for t in row:
+                s += "<|%d|>" % (t - TS0) if t >= TS0 else ("<|endoftext|>" if t == EOT else str(t - 15))
+            out.append(s)
+        return out
+
+
+class _Seg:
+    default_segmentation_config = {}
+    total_spec_columns = 1000
+    cluster_codebook = BOOK
+    precision_bits = 3
+    tokenizer = _Tok()
+
+
+def _tokens_for(global_index, n_new):
+    rng = np.random.default_rng(1000 + global_index)
+    row, t = [], 0
+    while len(row) + 3 <= n_new - 1:
+        t += int(rng.integers(5, 80))
+        d = int(rng.integers(2, 40))
+        if t + d > 500:
+            break
+        row += [TS0 + t, 15 + int(rng.integers(0, 2)), TS0 + t + d]
+        t += d
+    row.append(EOT)
+    return row + [EOT] * (n_new - len(row))
+
+
+def _expected(audio, num_trials):
+    plan = FrontendPlan(SR, STS, 0)
+    wins = plan.windows(len(audio), num_trials)
+    texts = _Tok().batch_decode([_tokens_for(i, MAX_LEN - 3) for i in range(len(wins))])
+    pred = pp.parse_generation(texts, [w.as_tuple() for w in wins], STS * 2, len(audio) / SR, STS, num_trials, STS * 8, STS,
+                               "clustering", BOOK)
+    return pp.correct_fft_blur_and_dedupe(pred, SR, get_n_fft_given_sr(SR))
+
+
+def _worker(rank, world, port, n_samples, num_trials, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    audio = np.zeros(n_samples, dtype=np.float32)
+    plan = FrontendPlan(SR, STS, 0)
+    n_win = len(plan.windows(n_samples, num_trials))
+    lo, hi, per = shard_bounds(n_win, world, rank)
+    seen = {}
+
+    def gen(windows, plan_, piece, slice_start):
+        seen["n"] = len(windows)
+        seen["slice"] = (slice_start, len(piece))
+        return torch.tensor([_tokens_for(lo + i, MAX_LEN - 3) for i in range(len(windows))], dtype=torch.int32).reshape(-1, MAX_LEN - 3)
+    res = segment_sharded(_Seg(), audio, SR, 0, STS, max_length=MAX_LEN, num_trials=num_trials, generate_fn=gen)
+    q.put((rank, res, seen["n"], hi - lo, seen["slice"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("seconds,num_trials", [(73.0, 1), (31.0, 3), (4.0, 1)])
+def test_sharded_segment_world2_gloo(seconds, num_trials):
+    n = int(seconds * SR)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, num_trials, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    exp = _expected(np.zeros(n, dtype=np.float32), num_trials)
+    assert len(exp["onset"]) > 0
+    for rank, res, n_seen, n_mine, sl in got:
+        assert res == exp, "rank %d result differs from the single-process result" % rank
+        assert n_seen == n_mine
+        assert sl[0] % 4 == 0 and sl[1] <= n
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 240, 361):
+        for world in (1, 2, 4, 8):
+            spans = [shard_bounds(n, world, r)[:2] for r in range(world)]
+            flat = [i for a, b in spans for i in range(a, b)]
+            assert flat == list(range(n))

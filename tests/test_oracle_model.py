@@ -1,0 +1,117 @@
+"""The torch restatement of the Whisper network + greedy loop (oracle/whisper_torch.py) is pinned
+against (a) HuggingFace transformers' own WhisperForConditionalGeneration -- the third-party code the
+reference calls at model.py:609/655 -- and (b) the golden ids/segments produced by the unmodified
+reference (tests/golden/model_tiny.npz)."""
+import copy
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import frontend_np as FO
+from oracle import postprocess_ref as PR
+from oracle import synth
+from oracle.whisper_torch import WhisperOracle, oracle_from_hf
+
+
+@pytest.fixture(scope="module")
+def tiny(tiny_checkpoint):
+    path, hf = tiny_checkpoint
+    audio = synth.synth_audio(47.0, 16000, seed=11)
+    feats = FO.sliced_audio_features(audio, 16000, 0, 0.01, 1, dtype=np.float32)
+    x = torch.from_numpy(np.asarray([f[2] for f in feats]))
+    return dict(path=path, hf=hf, orc=oracle_from_hf(hf), audio=audio, feats=feats, x=x)
+
+
+def test_restatement_exact_in_float64(tiny):
+    """In float64 the restatement and HF agree to 1e-9: same function, only rounding differs."""
+    hf64 = copy.deepcopy(tiny["hf"]).double()
+    x = tiny["x"][:2].double()
+    o64 = WhisperOracle(tiny["hf"].state_dict(), 6, 4)
+    o64.w = {k: v.double() for k, v in tiny["hf"].state_dict().items()}
+    with torch.no_grad():
+        enc_hf = hf64.model.encoder(x).last_hidden_state
+        h = o64.conv_stem(x)
+        for i in range(4):
+            h = o64.encoder_layer(h, i)
+        import torch.nn.functional as F
+        enc = F.layer_norm(h, (h.shape[-1],), o64.w["model.encoder.layer_norm.weight"], o64.w["model.encoder.layer_norm.bias"], 1e-5)
+        assert (enc - enc_hf).abs().max().item() < 1e-9
+        dec_in = torch.tensor([[synth.ID_SOT, synth.ID_EN, synth.ID_NOTIMESTAMPS, synth.ID_TS0 + 5, 15, synth.ID_TS0 + 9]] * 2)
+        lg_hf = hf64(encoder_outputs=(enc_hf,), decoder_input_ids=dec_in).logits
+        lg = o64.decode_logits(dec_in, enc=enc)
+        assert (lg - lg_hf).abs().max().item() < 1e-8
+
+
+def test_encoder_vs_hf_fp32(tiny):
+    with torch.no_grad():
+        enc_hf = tiny["hf"].model.encoder(tiny["x"]).last_hidden_state
+    enc = tiny["orc"].encode(tiny["x"])
+    assert (enc - enc_hf).abs().max().item() < 2e-3
+
+
+def test_greedy_vs_golden_reference_ids(tiny, golden_dir):
+    """ids produced by the reference's own generate call (HF, do_sample + top_k=1)."""
+    g = np.load(golden_dir + "/model_tiny.npz")
+    meta = json.loads(bytes(g["meta"]).decode())
+    hf, orc = tiny["hf"], tiny["orc"]
+    enc = orc.encode(tiny["x"])
+    ids, margins = orc.greedy(enc, [synth.ID_SOT, synth.ID_EN, synth.ID_NOTIMESTAMPS], synth.ID_EOT, synth.ID_EOT,
+                              meta["max_length"], suppress_tokens=hf.generation_config.suppress_tokens,
+                              begin_suppress_tokens=hf.generation_config.begin_suppress_tokens, return_margins=True)
+    gold = torch.from_numpy(g["ids"].astype(np.int64))
+    n = min(ids.shape[1], gold.shape[1])
+    same = (ids[:, :n] == gold[:, :n])
+    # fp32 reduction-order differences can flip a near-tie; everything before the first flip must match
+    for b in range(ids.shape[0]):
+        bad = (~same[b]).nonzero()
+        if len(bad):
+            assert margins[b, bad[0, 0]].item() < 1e-2, "mismatch at a confident position"
+    assert same.float().mean().item() > 0.9
+
+
+def test_segments_from_golden_texts(tiny, golden_dir):
+    g = np.load(golden_dir + "/model_tiny.npz")
+    texts = json.loads(bytes(g["texts"]).decode())
+    gold = json.loads(bytes(g["segments"]).decode())
+    wins = FO.window_plan(len(tiny["audio"]), 16000, 0.01, 1)
+    res = PR.segment_from_texts(texts, [[w[0], w[1], w[4]] for w in wins], len(tiny["audio"]), 16000, 0.01,
+                                tiny["hf"].config.cluster_codebook, 512)
+    assert res == gold
+
+
+def test_token_table_matches_hf_tokenizer(tiny):
+    from whisperseg_b200.tokens import TokenTable
+    tok = synth.build_tokenizer()
+    table = TokenTable.from_pretrained(tiny["path"])
+    assert table.prompt_ids == [synth.ID_SOT, synth.ID_EN, synth.ID_NOTIMESTAMPS]
+    assert (table.eos_token_id, table.pad_token_id) == (tok.eos_token_id, tok.pad_token_id)
+    rng = np.random.default_rng(0)
+    allowed = np.array(synth.allowed_token_ids())
+    rows = [allowed[rng.integers(0, len(allowed), size=40)].tolist() for _ in range(20)]
+    rows.append([synth.ID_TS0 + 10, 16, 17, synth.ID_TS0 + 60, synth.ID_EOT, synth.ID_EOT, 300, 220, 128, 200, 15])
+    rows.append(rng.integers(0, 51372, size=64).tolist())
+    assert table.batch_decode(rows) == tok.batch_decode(rows, skip_special_tokens=False)
+
+
+def test_weight_preparation_layouts(tiny):
+    """conv2's (k, ci) K-ordering over the strided im2col-free view, q pre-scaling, cross-K/V packing."""
+    import torch.nn.functional as F
+    from whisperseg_b200.weights import load_checkpoint, prepare_tensors
+    cfg, sd, gen = load_checkpoint(tiny["path"])
+    t = prepare_tensors(cfg, sd, gen, "cpu")
+    d, T = cfg["d_model"], cfg["max_source_positions"]
+    h1 = torch.randn(1, 1000, d)
+    h1p = torch.cat([torch.zeros(1, 1, d), h1], 1).reshape(-1)
+    rows = torch.stack([h1p[2 * tt * d:2 * tt * d + 3 * d] for tt in range(T)])          # the strided view
+    got = rows @ sd["model.encoder.conv2.weight"].permute(0, 2, 1).reshape(d, 3 * d).t()
+    ref = F.conv1d(h1.transpose(1, 2), sd["model.encoder.conv2.weight"], stride=2, padding=1)[0].t()
+    assert (got - ref).abs().max().item() < 1e-3
+    assert t["enc.conv2.w"].shape == (d, 3 * d) and t["enc.conv1.wt"].shape == (240, d)
+    q = sd["model.encoder.layers.0.self_attn.q_proj.weight"] * 0.125
+    assert torch.equal(t["enc.0.qkv.w"][:d].float(), q.to(torch.bfloat16).float())
+    assert torch.all(t["enc.0.qkv.b"][d:2 * d] == 0)
+    L = cfg["encoder_layers"]
+    assert t["dec.crosskv.w"].shape == (2 * L * d, d)
+    assert (t["dec.suppress"] == 0).sum().item() == len(synth.allowed_token_ids())

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(kAttThreads, 1)
 encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                          __nv_bfloat16* __restrict__ out, int T, int d) {
     extern __shared__ unsigned char att_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = att_smem_raw + ((1024u - (smem_u32(att_smem_raw) & 1023u)) & 1023u);
     unsigned char* sQ = smem;                                   // 16 KB
     unsigned char* sK = sQ + kAttQ * kHd * 2;                   // 64 KB
     unsigned char* sV = sK + kAttKeys * kHd * 2;                // 64 KB

@@ -5,7 +5,7 @@
 // Replaces every nn.Linear / conv2 the reference reaches through HF WhisperEncoder/Decoder
 // (modeling_whisper.py:279-282, 376-377, 619-625) -- cuBLAS/cuDNN library calls there.
 //
-// Structure (one CTA per SM, 256 threads, tiles 128 x BN x 64):
+// Structure (one CTA per SM, 384 threads, tiles 128 x BN x 64):
 //   warp 0   TMA producer: cp.async.bulk.tensor loads of the A and W tiles into a STAGES-deep ring
 //            of 128B-swizzled shared-memory buffers, completion signalled on `full` mbarriers;
 //   warp 1   MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
@@ -13,8 +13,10 @@
 //            k-block, publishes the accumulator (`tmem_full`);
 //   warp 2   TMEM allocator (2 accumulator buffers of BN columns, so the epilogue of tile i overlaps
 //            the main loop of tile i+1);
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused bias / GELU /
-//            positional row-vector / fp32 residual / arg-max -> global.
+//   warps 4-11 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> 32x32 transpose through a
+//            padded shared-memory tile (so every global access is a coalesced 128-byte row) -> fused
+//            bias / GELU / positional row-vector / fp32 residual -> global; the arg-max mode keeps a
+//            row per thread and never materialises the [M,N] logits.
 // Tiles are visited n-fastest so the A tile is read from HBM once and re-used out of L2 by the other
 // n-tiles, while W (<= a few MB) stays L2 resident.
 #include "common.cuh"
@@ -24,7 +26,8 @@ namespace wsb {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;           // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
 constexpr int kABytes = kBM * kBK * 2;
 
 struct GemmDev {
@@ -51,17 +54,25 @@ struct GemmCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
     static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kEpiBytes = kEpiWarps * 32 * 33 * 4;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// epilogue variants are compile-time: the per-row loops must be branch-free and small enough to stay in
+// the instruction cache (runtime mode flags made the epilogue fetch- and branch-bound)
+enum Epi : int { EPI_BF16 = 0, EPI_BF16_GELU, EPI_F32, EPI_F32_RESID, EPI_F32_GELU_ROWVEC, EPI_HEADMAJOR, EPI_ARGMAX };
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
     using Cfg = GemmCfg<BN>;
     constexpr int S = Cfg::kStages;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+    // align inside the shared window with pointer arithmetic (an integer round-trip would demote every
+    // later access through this pointer to a generic LD/ST)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* epi_buf = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes + Cfg::kEpiBytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + S;
     uint64_t* tmem_full = bars + 2 * S;
@@ -82,7 +93,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 128);
+            mbar_init(&tmem_empty[i], kEpiWarps * 32);
         }
         fence_mbar_init();
     }
@@ -154,115 +165,139 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else if (warp >= 4) {
-        const int q = warp - 4;
-        const int row_in_tile = q * 32 + lane;
+        // ---- epilogue: 8 warps; warp (4 + e) owns TMEM lanes 32*(e%4).. (hardware restriction: a warp
+        // may only touch the lane quarter warp_id % 4) and the 32-column chunks c with c % 2 == e / 4.
+        const int e = warp - 4;
+        const int q = e & 3, half = e >> 2;
+        float* tbuf = epi_buf + e * (32 * 33);            // per-warp 32x32 transpose tile (padded)
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
             const int as = local & 1;
             const uint32_t aphase = (local >> 1) & 1;
-            long long grow;
-            int brow;                                  // row index within its batch (for rowvec / head-major)
-            bool valid;
+            long long grow0;                            // global row of this warp's first lane
+            int nvalid;                                 // valid rows in the 32-row slab
             if (tiles_per_batch > 0) {
                 const int b = mt / tiles_per_batch;
-                brow = (mt - b * tiles_per_batch) * kBM + row_in_tile;
-                valid = brow < p.a_rows_per_batch;
-                grow = static_cast<long long>(b) * p.a_rows_per_batch + brow;
+                const int brow0 = (mt - b * tiles_per_batch) * kBM + q * 32;
+                nvalid = min(32, max(0, p.a_rows_per_batch - brow0));
+                grow0 = static_cast<long long>(b) * p.a_rows_per_batch + brow0;
             } else {
-                grow = static_cast<long long>(mt) * kBM + row_in_tile;
-                valid = grow < p.M;
-                brow = p.rows_per_batch > 0 ? static_cast<int>(grow % p.rows_per_batch) : 0;
+                grow0 = static_cast<long long>(mt) * kBM + q * 32;
+                nvalid = static_cast<int>(min(32LL, max(0LL, static_cast<long long>(p.M) - grow0)));
             }
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
-            float best = -INFINITY;
-            int best_idx = nt * BN;
+            const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            if constexpr (EPI == EPI_ARGMAX) {
+                // row-per-thread running arg-max over this tile's columns (first 4 epilogue warps only)
+                if (half == 0) {
+                    float best = -INFINITY;
+                    int best_idx = nt * BN;
+                    const bool valid = lane < nvalid;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, r);
-                tmem_ld_wait();
-                const int n0 = nt * BN + c * 32;
-                if (!valid || n0 >= p.N) continue;
-                float v[32];
+                    for (int c = 0; c < BN / 32; ++c) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(t_base + c * 32, r);
+                        tmem_ld_wait();
+                        const int n0 = nt * BN + c * 32;
+                        if (!valid || n0 >= p.N) continue;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                const bool full_chunk = (n0 + 32 <= p.N);
-                if (p.bias) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (full_chunk || n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
-                }
-                if (p.bias2) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (full_chunk || n0 + i < p.N) v[i] += __ldg(p.bias2 + n0 + i);
-                }
-                if (p.act == GEMM_ACT_GELU) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-                }
-                if (p.rowvec) {
-                    const float* rv = p.rowvec + static_cast<long long>(brow) * p.N + n0;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(rv + i));
-                        v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
-                    }
-                }
-                if (p.resid) {
-                    const float* rs = p.resid + grow * p.ldr + n0;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 t = *reinterpret_cast<const float4*>(rs + i);
-                        v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
-                    }
-                }
-                if (p.out_mode == GEMM_OUT_F32) {
-                    float* o = reinterpret_cast<float*>(p.out) + grow * p.ldc + n0;
-                    if (full_chunk) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    } else {
-                        for (int i = 0; i < 32 && n0 + i < p.N; ++i) o[i] = v[i];
-                    }
-                } else if (p.out_mode == GEMM_OUT_BF16 || p.out_mode == GEMM_OUT_HEADMAJOR) {
-                    __nv_bfloat16* o;
-                    if (p.out_mode == GEMM_OUT_BF16) {
-                        o = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + n0;
-                    } else {
-                        const long long b = grow / p.rows_per_batch;
-                        const long long t = grow - b * p.rows_per_batch;
-                        o = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                            ((b * (p.N >> 6) + (n0 >> 6)) * p.rows_per_batch + t) * 64 + (n0 & 63);
-                    }
-                    if (full_chunk) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            uint4 pk;
-                            pk.x = pack_bf16x2(v[i], v[i + 1]);
-                            pk.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                            pk.z = pack_bf16x2(v[i + 4], v[i + 5]);
-                            pk.w = pack_bf16x2(v[i + 6], v[i + 7]);
-                            *reinterpret_cast<uint4*>(o + i) = pk;
+                        for (int i = 0; i < 32; ++i) {
+                            if (n0 + i < p.N) {
+                                float v = __uint_as_float(r[i]);
+                                if (p.bias) v += __ldg(p.bias + n0 + i);
+                                if (p.bias2) v += __ldg(p.bias2 + n0 + i);
+                                if (v > best) {
+                                    best = v;
+                                    best_idx = n0 + i;
+                                }
+                            }
                         }
-                    } else {
-                        for (int i = 0; i < 32 && n0 + i < p.N; ++i) o[i] = __float2bfloat16(v[i]);
                     }
-                } else {   // GEMM_OUT_ARGMAX
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if ((full_chunk || n0 + i < p.N) && v[i] > best) {
-                            best = v[i];
-                            best_idx = n0 + i;
-                        }
+                    if (valid) {
+                        p.argmax_val[(grow0 + lane) * p.n_tiles + nt] = best;
+                        p.argmax_idx[(grow0 + lane) * p.n_tiles + nt] = best_idx;
+                    }
                 }
-            }
-            if (p.out_mode == GEMM_OUT_ARGMAX && valid) {
-                p.argmax_val[grow * p.n_tiles + nt] = best;
-                p.argmax_idx[grow * p.n_tiles + nt] = best_idx;
+            } else {
+#pragma unroll 1
+                for (int c = half; c < BN / 32; c += 2) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_base + c * 32, r);
+                    tmem_ld_wait();
+                    const int n0 = nt * BN + c * 32;
+                    if (n0 >= p.N || nvalid == 0) continue;             // warp-uniform
+                    // transpose through shared memory: lane r holds row r -> lane c holds column c, so that
+                    // bias / residual / output accesses are 128-byte coalesced rows
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) tbuf[lane * 33 + i] = __uint_as_float(r[i]);
+                    __syncwarp();
+                    const int col = n0 + lane;
+                    const bool cvalid = col < p.N;
+                    float bias_v = 0.0f;
+                    if (cvalid && p.bias) bias_v = __ldg(p.bias + col);
+                    if constexpr (EPI == EPI_F32_RESID) {
+                        // the residual aliases the output (in-place stream update): batch the loads ahead of
+                        // the stores explicitly, the compiler may not reorder them
+                        const float* rs = p.resid + grow0 * p.ldr + col;
+                        float* o = reinterpret_cast<float*>(p.out) + grow0 * p.ldc + col;
+#pragma unroll
+                        for (int r0 = 0; r0 < 32; r0 += 16) {
+                            float res[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                res[j] = (cvalid && r0 + j < nvalid) ? rs[static_cast<long long>(r0 + j) * p.ldr] : 0.0f;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (cvalid && r0 + j < nvalid)
+                                    o[static_cast<long long>(r0 + j) * p.ldc] = tbuf[(r0 + j) * 33 + lane] + bias_v + res[j];
+                        }
+                    } else if constexpr (EPI == EPI_F32 || EPI == EPI_F32_GELU_ROWVEC) {
+                        float* o = reinterpret_cast<float*>(p.out) + grow0 * p.ldc + col;
+#pragma unroll 8
+                        for (int rr = 0; rr < 32; ++rr) {
+                            if (rr >= nvalid) break;
+                            float v = tbuf[rr * 33 + lane] + bias_v;
+                            if constexpr (EPI == EPI_F32_GELU_ROWVEC) {
+                                v = gelu_fast(v);
+                                const long long brow = (grow0 + rr) % p.rows_per_batch;
+                                if (cvalid) v += __ldg(p.rowvec + brow * p.N + col);
+                            }
+                            if (cvalid) o[static_cast<long long>(rr) * p.ldc] = v;
+                        }
+                    } else {   // bf16 outputs: EPI_BF16, EPI_BF16_GELU, EPI_HEADMAJOR
+                        auto store_row = [&](int rr) {
+                            float v = tbuf[rr * 33 + lane] + bias_v;
+                            if constexpr (EPI == EPI_BF16_GELU) v = gelu_fast(v);
+                            const float hi = __shfl_down_sync(0xffffffffu, v, 1);
+                            const long long grow = grow0 + rr;
+                            __nv_bfloat16* o;
+                            if constexpr (EPI == EPI_HEADMAJOR) {
+                                const long long b = grow / p.rows_per_batch;
+                                const long long t = grow - b * p.rows_per_batch;
+                                o = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                    ((b * (p.N >> 6) + (col >> 6)) * p.rows_per_batch + t) * 64 + (col & 63);
+                            } else {
+                                o = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + col;
+                            }
+                            if ((lane & 1) == 0) {
+                                if (col + 1 < p.N) {
+                                    *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v, hi);
+                                } else if (cvalid) {
+                                    *o = __float2bfloat16(v);
+                                }
+                            }
+                        };
+                        if (nvalid == 32) {
+#pragma unroll
+                            for (int rr = 0; rr < 32; ++rr) store_row(rr);
+                        } else {
+                            for (int rr = 0; rr < nvalid; ++rr) store_row(rr);
+                        }
+                    }
+                    __syncwarp();
+                }
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[as]);
@@ -335,13 +370,13 @@ int gemm_pick_block_n(int M, int N) {
 }
 int gemm_n_tiles(int N, int block_n) { return ceil_div(N, block_n); }
 
-template <int BN>
+template <int BN, int EPI>
 static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     static int num_sms = 0;
     if (!attr_set) {
-        WSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        WSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         int dev = 0;
         WSB_CHECK_CUDA(cudaGetDevice(&dev));
         WSB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -396,7 +431,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.n_tiles = ceil_div(a.N, BN);
     const int total = p.m_tiles * p.n_tiles;
     const int grid = std::min(total, num_sms);
-    gemm_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+    gemm_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
     WSB_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -413,13 +448,39 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
     if (a.out_mode == GEMM_OUT_F32) WSB_REQUIRE(a.ldc % 4 == 0, "ldc must be a multiple of 4 for fp32 output");
     if (a.out_mode == GEMM_OUT_BF16) WSB_REQUIRE(a.ldc % 8 == 0, "ldc must be a multiple of 8 for bf16 output");
     int bn = a.block_n ? a.block_n : gemm_pick_block_n(a.M, a.N);
+    // map the requested epilogue onto a compiled variant
+    int epi = -1;
+    if (a.out_mode == GEMM_OUT_ARGMAX && !a.resid && !a.rowvec && a.act == GEMM_ACT_NONE) epi = EPI_ARGMAX;
+    else if (a.bias2) epi = -1;
+    else if (a.out_mode == GEMM_OUT_HEADMAJOR && !a.resid && !a.rowvec && a.act == GEMM_ACT_NONE) epi = EPI_HEADMAJOR;
+    else if (a.out_mode == GEMM_OUT_BF16 && !a.resid && !a.rowvec) epi = a.act == GEMM_ACT_GELU ? EPI_BF16_GELU : EPI_BF16;
+    else if (a.out_mode == GEMM_OUT_F32 && a.resid && !a.rowvec && a.act == GEMM_ACT_NONE) epi = EPI_F32_RESID;
+    else if (a.out_mode == GEMM_OUT_F32 && !a.resid && a.rowvec && a.act == GEMM_ACT_GELU) epi = EPI_F32_GELU_ROWVEC;
+    else if (a.out_mode == GEMM_OUT_F32 && !a.resid && !a.rowvec && a.act == GEMM_ACT_NONE) epi = EPI_F32;
+    if (epi < 0) {
+        set_last_error("gemm_bf16: unsupported epilogue combination");
+        return 2;
+    }
+    if (a.rowvec) WSB_REQUIRE(a.rows_per_batch > 0, "row-vector epilogue needs rows_per_batch");
+#define WSB_GEMM_CASE(BN_)                                                                     \
+    case BN_:                                                                                  \
+        switch (epi) {                                                                         \
+            case EPI_BF16: return launch_gemm<BN_, EPI_BF16>(a, stream);                       \
+            case EPI_BF16_GELU: return launch_gemm<BN_, EPI_BF16_GELU>(a, stream);             \
+            case EPI_F32: return launch_gemm<BN_, EPI_F32>(a, stream);                         \
+            case EPI_F32_RESID: return launch_gemm<BN_, EPI_F32_RESID>(a, stream);             \
+            case EPI_F32_GELU_ROWVEC: return launch_gemm<BN_, EPI_F32_GELU_ROWVEC>(a, stream); \
+            case EPI_HEADMAJOR: return launch_gemm<BN_, EPI_HEADMAJOR>(a, stream);             \
+            default: return launch_gemm<BN_, EPI_ARGMAX>(a, stream);                           \
+        }
     switch (bn) {
-        case 256: return launch_gemm<256>(a, stream);
-        case 128: return launch_gemm<128>(a, stream);
-        case 64: return launch_gemm<64>(a, stream);
-        case 32: return launch_gemm<32>(a, stream);
+        WSB_GEMM_CASE(256)
+        WSB_GEMM_CASE(128)
+        WSB_GEMM_CASE(64)
+        WSB_GEMM_CASE(32)
         default: set_last_error("unsupported block_n"); return 2;
     }
+#undef WSB_GEMM_CASE
 }
 
 }  // namespace wsb

@@ -65,6 +65,16 @@ __device__ __forceinline__ float2 twiddle(const float2* __restrict__ tw, int idx
     return idx >= m ? make_float2(-t.x, -t.y) : t;
 }
 
+// barrier among the G threads that cooperate on one frame (a warp, or a named barrier per group), so
+// the frame groups of a CTA run their FFT passes independently of each other
+__device__ __forceinline__ void group_sync(int g, int G) {
+    if (G == 32) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(G) : "memory");
+    }
+}
+
 __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelParams p) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = static_cast<int>(cluster.block_rank());
@@ -150,7 +160,7 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
                 bufA[j] = make_float2(x[2 * j] * h.x, x[2 * j + 1] * h.y);
             }
         }
-        __syncthreads();
+        group_sync(g, G);
         float2* src = bufA;
         float2* dst = bufB;
         int ns = 1, lg = 0;
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
                     dst[2 * j + 1] = make_float2(u0.x - u1.x, u0.y - u1.y);
                 }
             }
-            __syncthreads();
+            group_sync(g, G);
             float2* t = src; src = dst; dst = t;
             ns = 2; lg = 1;
         }
@@ -193,7 +203,7 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
                     dst[j0 + 3 * ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
                 }
             }
-            __syncthreads();
+            group_sync(g, G);
             float2* t = src; src = dst; dst = t;
         }
         // real-FFT untangle + power spectrum: P[k], k = 0..M, into dst (as floats)
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
                 power[k] = re * re + im * im;
             }
         }
-        __syncthreads();
+        group_sync(g, G);
         // sparse mel: 8 lanes cooperate on one filter
         if (active) {
             const int sub = gt >> 3, sl = gt & 7, nsub = G >> 3;
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
                 }
             }
         }
-        __syncthreads();
+        group_sync(g, G);
     }
 
     // ---- window-global max / min across the cluster ---------------------------------------------
@@ -305,8 +315,6 @@ int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float
     pl->n_frames = clip_len / hop;
     const int M = n_fft / 2;
     pl->log2m = ilog2(M);
-    pl->group_threads = std::min(kLogmelThreads, std::max(32, M / 4));
-    pl->n_groups = kLogmelThreads / pl->group_threads;
 
     // pick the largest cluster (<= 8) and the frame slice so that everything fits in shared memory
     int dev = 0, max_smem = 0;
@@ -316,6 +324,15 @@ int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float
     pl->frames_per_cta = std::max(1, ceil_div(std::max(pl->n_frames, 1), pl->cluster));
     pl->span_floats = ((pl->frames_per_cta - 1) * hop + n_fft + 3) & ~3;
     pl->tile_stride = pl->frames_per_cta | 1;
+    // as many independent frame groups as shared memory allows (a warp per frame when possible): the
+    // FFT passes of different frames then overlap instead of serialising on block-wide barriers
+    const size_t fixed_bytes = sizeof(float) * (static_cast<size_t>(pl->span_floats) + kMels * pl->tile_stride) +
+                               sizeof(float2) * static_cast<size_t>(M) + 2048;
+    pl->group_threads = 32;
+    while (pl->group_threads < kLogmelThreads &&
+           fixed_bytes + sizeof(float2) * 2 * M * (kLogmelThreads / pl->group_threads) > static_cast<size_t>(max_smem))
+        pl->group_threads *= 2;
+    pl->n_groups = kLogmelThreads / pl->group_threads;
     pl->smem_bytes = sizeof(float) * (static_cast<size_t>(pl->span_floats) + kMels * pl->tile_stride) +
                      sizeof(float2) * (static_cast<size_t>(M) + static_cast<size_t>(pl->n_groups) * 2 * M);
     if (pl->smem_bytes + 1024 > static_cast<size_t>(max_smem)) {
