@@ -76,6 +76,143 @@ int layernorm_f32_to_bf16(const float* x, const float* gamma, const float* beta,
     return 0;
 }
 
+// ------------------------------------------------------------------------------ split-K second phase
+// One 128-thread CTA per output row (decode batches are a few hundred rows: a CTA per row keeps every
+// load of the S partial planes independent and in flight at once).  The planes are summed in a fixed
+// order (deterministic), then the fused epilogue runs: bias (+GELU) -> bf16, or bias + fp32 residual
+// update (+ LayerNorm -> bf16 for the next GEMM), so a decoder layer needs no stand-alone LayerNorm.
+constexpr int kRedThreads = 128;
+constexpr int kRedMaxSplits = 16;
+
+__global__ void __launch_bounds__(kRedThreads) splitk_reduce_bf16_kernel(const float* __restrict__ partial, int splits,
+                                                                         long long split_stride, int N,
+                                                                         const float* __restrict__ bias, int gelu,
+                                                                         __nv_bfloat16* __restrict__ out) {
+    const int row = blockIdx.x;
+    const int nvec = N >> 2;
+    const float4* base = reinterpret_cast<const float4*>(partial + static_cast<long long>(row) * N);
+    const long long sv = split_stride >> 2;
+    for (int j = threadIdx.x; j < nvec; j += kRedThreads) {
+        float4 t[kRedMaxSplits];
+#pragma unroll
+        for (int sp = 0; sp < kRedMaxSplits; ++sp)
+            if (sp < splits) t[sp] = base[sp * sv + j];
+        float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int sp = 0; sp < kRedMaxSplits; ++sp)
+            if (sp < splits) {
+                acc.x += t[sp].x; acc.y += t[sp].y; acc.z += t[sp].z; acc.w += t[sp].w;
+            }
+        if (gelu) {
+            acc.x = gelu_fast(acc.x); acc.y = gelu_fast(acc.y); acc.z = gelu_fast(acc.z); acc.w = gelu_fast(acc.w);
+        }
+        uint2 pk;
+        pk.x = pack_bf16x2(acc.x, acc.y);
+        pk.y = pack_bf16x2(acc.z, acc.w);
+        reinterpret_cast<uint2*>(out + static_cast<long long>(row) * N)[j] = pk;
+    }
+}
+
+constexpr int kRedLnVec = 3;   // float4 per thread -> N <= 1536
+
+__global__ void __launch_bounds__(kRedThreads) splitk_reduce_resid_ln_kernel(const float* __restrict__ partial, int splits,
+                                                                             long long split_stride, int N,
+                                                                             const float* __restrict__ bias,
+                                                                             float* __restrict__ x,
+                                                                             const float* __restrict__ gamma,
+                                                                             const float* __restrict__ beta,
+                                                                             __nv_bfloat16* __restrict__ xn) {
+    __shared__ float s_red[2][kRedThreads / 32];
+    const int row = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nvec = N >> 2;
+    const float4* base = reinterpret_cast<const float4*>(partial + static_cast<long long>(row) * N);
+    const long long sv = split_stride >> 2;
+    float4* xr = reinterpret_cast<float4*>(x + static_cast<long long>(row) * N);
+    float4 v[kRedLnVec];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kRedLnVec; ++i) {
+        const int j = tid + kRedThreads * i;
+        if (j < nvec) {
+            float4 t[kRedMaxSplits];
+#pragma unroll
+            for (int sp = 0; sp < kRedMaxSplits; ++sp)
+                if (sp < splits) t[sp] = base[sp * sv + j];
+            float4 acc = xr[j];
+            if (bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + j);
+                acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+            }
+#pragma unroll
+            for (int sp = 0; sp < kRedMaxSplits; ++sp)
+                if (sp < splits) {
+                    acc.x += t[sp].x; acc.y += t[sp].y; acc.z += t[sp].z; acc.w += t[sp].w;
+                }
+            xr[j] = acc;
+            v[i] = acc;
+            sum += (acc.x + acc.y) + (acc.z + acc.w);
+        }
+    }
+    if (gamma == nullptr) return;
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[0][warp] = sum;
+    __syncthreads();
+    float tot = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kRedThreads / 32; ++i) tot += s_red[0][i];
+    const float mean = tot / N;
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kRedLnVec; ++i) {
+        const int j = tid + kRedThreads * i;
+        if (j < nvec) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+            sq += (a * a + b * b) + (c * c + e * e);
+        }
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) s_red[1][warp] = sq;
+    __syncthreads();
+    float tsq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kRedThreads / 32; ++i) tsq += s_red[1][i];
+    const float rstd = rsqrtf(tsq / N + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < kRedLnVec; ++i) {
+        const int j = tid + kRedThreads * i;
+        if (j < nvec) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + j);
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + j);
+            uint2 pk;
+            pk.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + bt.x, (v[i].y - mean) * rstd * g.y + bt.y);
+            pk.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + bt.z, (v[i].w - mean) * rstd * g.w + bt.w);
+            reinterpret_cast<uint2*>(xn + static_cast<long long>(row) * N)[j] = pk;
+        }
+    }
+}
+
+int splitk_reduce_bf16(const float* partial, int splits, int64_t split_stride, int M, int N, const float* bias, int gelu,
+                       __nv_bfloat16* out, cudaStream_t stream) {
+    WSB_REQUIRE(N % 4 == 0 && split_stride % 4 == 0 && splits <= kRedMaxSplits, "split-K reduce shape");
+    if (M <= 0) return 0;
+    splitk_reduce_bf16_kernel<<<M, kRedThreads, 0, stream>>>(partial, splits, split_stride, N, bias, gelu, out);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int splitk_reduce_resid_ln(const float* partial, int splits, int64_t split_stride, int M, int N, const float* bias,
+                           float* x, const float* gamma, const float* beta, __nv_bfloat16* xn, cudaStream_t stream) {
+    WSB_REQUIRE(N % 4 == 0 && N <= kRedLnVec * kRedThreads * 4 && split_stride % 4 == 0 && splits <= kRedMaxSplits,
+                "split-K reduce shape (row width <= 1536)");
+    if (M <= 0) return 0;
+    splitk_reduce_resid_ln_kernel<<<M, kRedThreads, 0, stream>>>(partial, splits, split_stride, N, bias, x, gamma, beta, xn);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------ conv1 + GELU
 // out[b][1 + t][co] = gelu(bias[co] + sum_{ci,k} w[co][ci][k] * x[b][ci][t + k - 1]),  t in [0, n_cols)
 // x: f32 [B][80][n_cols] (K1's output layout); wt: f32 [80*3][d] (pre-transposed, co contiguous);

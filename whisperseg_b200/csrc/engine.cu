@@ -8,6 +8,7 @@
 #include "decode.h"
 #include "../../include/wsb.h"
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -114,7 +115,8 @@ struct Model {
     char* ws = nullptr;
     size_t ws_bytes = 0;
     __nv_bfloat16 *h1p, *xn, *qkv, *att, *ff, *enc_out, *cross_kv, *k_cache, *v_cache, *dxn, *dqkv, *datt, *dq, *dff;
-    float *x, *dx, *am_val;
+    float *x, *dx, *am_val, *dpart;
+    size_t dpart_floats = 0;
     int *am_idx, *tokens, *next_token, *step, *n_active, *prompt_dev;
     unsigned char* finished;
     int am_tiles = 0, logits_bn = 0;
@@ -156,6 +158,8 @@ static int model_layout(Model* m, bool assign) {
     m->datt = carve<__nv_bfloat16>(p, B * d);
     m->dq = carve<__nv_bfloat16>(p, B * d);
     m->dff = carve<__nv_bfloat16>(p, B * F);
+    m->dpart_floats = 16 * B * std::max<size_t>(F, 3 * d);
+    m->dpart = carve<float>(p, m->dpart_floats);
     m->am_val = carve<float>(p, B * m->am_tiles);
     m->am_idx = carve<int>(p, B * m->am_tiles);
     m->tokens = carve<int>(p, B * c.max_target_positions);
@@ -341,6 +345,38 @@ static int encode(Model* m, const float* feats, int B, float* hidden_f32, cudaSt
     return 0;
 }
 
+// skinny (decode) linear layer: split-K tcgen05 GEMM into fp32 partial planes, then the fused second phase
+//   mode 0: out_bf16 = act(sum + bias)         mode 1: x += sum + bias; xn = LayerNorm(x) (if gamma)
+static int skinny_linear(Model* m, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, int B, int N, int K,
+                         int gelu, __nv_bfloat16* out_bf16, float* x, const float* gamma, const float* beta,
+                         __nv_bfloat16* xn, cudaStream_t s) {
+    int bn = 128, splits = 1;
+    gemm_pick_skinny(B, N, K, &bn, &splits);
+    const int64_t plane = static_cast<int64_t>(B) * N;
+    WSB_REQUIRE(static_cast<size_t>(plane) * splits <= m->dpart_floats, "split-K workspace too small");
+    {
+        ProfScope ps(PROF_DEC_GEMM, 2.0 * B * N * K, s);
+        GemmArgs g;
+        g.A = A;
+        g.lda = K;
+        g.W = W;
+        g.M = B;
+        g.N = N;
+        g.K = K;
+        g.out = m->dpart;
+        g.ldc = N;
+        g.out_mode = GEMM_OUT_F32;
+        g.block_n = bn;
+        g.splits = splits;
+        g.split_stride = plane;
+        WSB_RUN(gemm_bf16(g, s));
+    }
+    ProfScope ps(PROF_DEC_LN, 4.0 * B * N * (splits + 1), s);
+    const int eff = gemm_effective_splits(K, splits);
+    if (out_bf16) return splitk_reduce_bf16(m->dpart, eff, plane, B, N, bias, gelu, out_bf16, s);
+    return splitk_reduce_resid_ln(m->dpart, eff, plane, B, N, bias, x, gamma, beta, xn, s);
+}
+
 // one decoder position for all rows.  with_logits: project + arg-max + finalize; else prefill advance.
 static int decode_step(Model* m, int B, bool with_logits, bool first_generated, int prompt_len, int max_new,
                        const int* forced, int forced_ld, int eos_id, int pad_id, cudaStream_t s) {
@@ -349,38 +385,32 @@ static int decode_step(Model* m, int B, bool with_logits, bool first_generated, 
     const unsigned char* fin = forced ? nullptr : m->finished;
     WSB_RUN(embed_tokens_step(m->next_token, m->step, 0, m->dec_emb, m->dec_pos, m->dx, B, d, s));
     const long long cache_l = static_cast<long long>(B) * H * tmax * 64;
+    {
+        ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
+        WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec[0].ln1_g, m->dec[0].ln1_b, m->dxn, nullptr, B, d, s));
+    }
     for (int l = 0; l < L; ++l) {
         const DecLayer& e = m->dec[l];
-        {
-            ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
-            WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln1_g, e.ln1_b, m->dxn, nullptr, B, d, s));
-        }
-        WSB_RUN(linear(m->dxn, e.sqkv_w, e.sqkv_b, B, 3 * d, d, GEMM_ACT_NONE, nullptr, m->dqkv, GEMM_OUT_BF16, s, 0, PROF_DEC_GEMM));
+        // every LayerNorm after the first is fused into the preceding residual reduction
+        const float* next_g = (l + 1 < L) ? m->dec[l + 1].ln1_g : m->dec_ln_g;
+        const float* next_b = (l + 1 < L) ? m->dec[l + 1].ln1_b : m->dec_ln_b;
+        WSB_RUN(skinny_linear(m, m->dxn, e.sqkv_w, e.sqkv_b, B, 3 * d, d, 0, m->dqkv, nullptr, nullptr, nullptr, nullptr, s));
         {
             ProfScope ps(PROF_DEC_SELF_ATTN, 0.0, s);
-        WSB_RUN(decode_self_attention(m->dqkv, d, m->k_cache + l * cache_l, m->v_cache + l * cache_l, tmax, m->step, 0,
-                                      fin, m->datt, B, H, s));
+            WSB_RUN(decode_self_attention(m->dqkv, d, m->k_cache + l * cache_l, m->v_cache + l * cache_l, tmax, m->step, 0,
+                                          fin, m->datt, B, H, s));
         }
-        WSB_RUN(linear(m->datt, e.so_w, e.so_b, B, d, d, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s, 0, PROF_DEC_GEMM));
-        {
-            ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
-            WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln2_g, e.ln2_b, m->dxn, nullptr, B, d, s));
-        }
-        WSB_RUN(linear(m->dxn, e.cq_w, e.cq_b, B, d, d, GEMM_ACT_NONE, nullptr, m->dq, GEMM_OUT_BF16, s, 0, PROF_DEC_GEMM));
+        WSB_RUN(skinny_linear(m, m->datt, e.so_w, e.so_b, B, d, d, 0, nullptr, m->dx, e.ln2_g, e.ln2_b, m->dxn, s));
+        WSB_RUN(skinny_linear(m, m->dxn, e.cq_w, e.cq_b, B, d, d, 0, m->dq, nullptr, nullptr, nullptr, nullptr, s));
         {
             ProfScope ps(PROF_DEC_CROSS_ATTN, 4.0 * B * H * T * 64.0, s);   // bytes: K and V blocks, bf16
             WSB_RUN(decode_cross_attention(m->dq, d, m->cross_kv, l, L, T, fin, m->datt, B, H, s));
         }
-        WSB_RUN(linear(m->datt, e.co_w, e.co_b, B, d, d, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s, 0, PROF_DEC_GEMM));
-        {
-            ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
-            WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln3_g, e.ln3_b, m->dxn, nullptr, B, d, s));
-        }
-        WSB_RUN(linear(m->dxn, e.fc1_w, e.fc1_b, B, F, d, GEMM_ACT_GELU, nullptr, m->dff, GEMM_OUT_BF16, s, 0, PROF_DEC_GEMM));
-        WSB_RUN(linear(m->dff, e.fc2_w, e.fc2_b, B, d, F, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s, 0, PROF_DEC_GEMM));
+        WSB_RUN(skinny_linear(m, m->datt, e.co_w, e.co_b, B, d, d, 0, nullptr, m->dx, e.ln3_g, e.ln3_b, m->dxn, s));
+        WSB_RUN(skinny_linear(m, m->dxn, e.fc1_w, e.fc1_b, B, F, d, 1, m->dff, nullptr, nullptr, nullptr, nullptr, s));
+        WSB_RUN(skinny_linear(m, m->dff, e.fc2_w, e.fc2_b, B, d, F, 0, nullptr, m->dx, next_g, next_b, m->dxn, s));
     }
     if (!with_logits) return prefill_advance(m->next_token, forced, forced_ld, m->prompt_dev, m->step, B, s);
-    WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec_ln_g, m->dec_ln_b, m->dxn, nullptr, B, d, s));
     GemmArgs g;
     g.A = m->dxn;
     g.lda = d;

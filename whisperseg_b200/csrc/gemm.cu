@@ -46,6 +46,8 @@ struct GemmDev {
     float* argmax_val;
     int* argmax_idx;
     int m_tiles, n_tiles;
+    int splits, kb_per_split;      // split-K: tile space is m_tiles x n_tiles x splits, fp32 partial planes
+    long long split_stride;        // elements between partial planes of the output
 };
 
 template <int BN>
@@ -103,7 +105,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
     const int k_blocks = p.K / kBK;
     const int tiles_per_batch = p.a_rows_per_batch > 0 ? (p.a_rows_per_batch + kBM - 1) / kBM : 0;
 
@@ -112,7 +114,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+                const int sp = tile % p.splits, mn = tile / p.splits;
+                const int mt = mn / p.n_tiles, nt = mn - mt * p.n_tiles;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
                 int a_row, a_batch;
                 if (tiles_per_batch > 0) {
                     a_batch = mt / tiles_per_batch;
@@ -121,7 +125,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     a_batch = 0;
                     a_row = mt * kBM;
                 }
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* sa = smem + stage * Cfg::kStageBytes;
                     mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
@@ -141,12 +145,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t phase = 0;
             int local = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+                const int sp = tile % p.splits;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
                 const int as = local & 1;
                 const uint32_t aphase = (local >> 1) & 1;
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -154,9 +160,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const uint64_t db = umma_desc_k_sw128(sa + kABytes);
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k)
-                        umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     umma_commit(&empty[stage]);
-                    if (kb == k_blocks - 1) umma_commit(&tmem_full[as]);
+                    if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1;
@@ -172,7 +178,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         float* tbuf = epi_buf + e * (32 * 33);            // per-warp 32x32 transpose tile (padded)
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-            const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+            const int sp = tile % p.splits, mn = tile / p.splits;
+            const int mt = mn / p.n_tiles, nt = mn - mt * p.n_tiles;
             const int as = local & 1;
             const uint32_t aphase = (local >> 1) & 1;
             long long grow0;                            // global row of this warp's first lane
@@ -254,19 +261,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     o[static_cast<long long>(r0 + j) * p.ldc] = tbuf[(r0 + j) * 33 + lane] + bias_v + res[j];
                         }
                     } else if constexpr (EPI == EPI_F32 || EPI == EPI_F32_GELU_ROWVEC) {
-                        float* o = reinterpret_cast<float*>(p.out) + grow0 * p.ldc + col;
+                        float* o = reinterpret_cast<float*>(p.out) + sp * p.split_stride + grow0 * p.ldc + col;
+                        int brow = 0;
+                        if constexpr (EPI == EPI_F32_GELU_ROWVEC) brow = static_cast<int>(grow0 % p.rows_per_batch);
 #pragma unroll 8
                         for (int rr = 0; rr < 32; ++rr) {
                             if (rr >= nvalid) break;
                             float v = tbuf[rr * 33 + lane] + bias_v;
                             if constexpr (EPI == EPI_F32_GELU_ROWVEC) {
                                 v = gelu_fast(v);
-                                const long long brow = (grow0 + rr) % p.rows_per_batch;
-                                if (cvalid) v += __ldg(p.rowvec + brow * p.N + col);
+                                if (cvalid) v += __ldg(p.rowvec + static_cast<long long>(brow) * p.N + col);
+                                if (++brow == p.rows_per_batch) brow = 0;
                             }
                             if (cvalid) o[static_cast<long long>(rr) * p.ldc] = v;
                         }
                     } else {   // bf16 outputs: EPI_BF16, EPI_BF16_GELU, EPI_HEADMAJOR
+                        long long hm_b = 0;
+                        int hm_t = 0;
+                        if constexpr (EPI == EPI_HEADMAJOR) {
+                            hm_b = grow0 / p.rows_per_batch;
+                            hm_t = static_cast<int>(grow0 - hm_b * p.rows_per_batch);
+                        }
                         auto store_row = [&](int rr) {
                             float v = tbuf[rr * 33 + lane] + bias_v;
                             if constexpr (EPI == EPI_BF16_GELU) v = gelu_fast(v);
@@ -274,8 +289,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             const long long grow = grow0 + rr;
                             __nv_bfloat16* o;
                             if constexpr (EPI == EPI_HEADMAJOR) {
-                                const long long b = grow / p.rows_per_batch;
-                                const long long t = grow - b * p.rows_per_batch;
+                                int t = hm_t + rr;
+                                long long b = hm_b;
+                                if (t >= p.rows_per_batch) {           // a 32-row slab crosses at most one batch boundary
+                                    t -= p.rows_per_batch;
+                                    b += 1;
+                                }
                                 o = reinterpret_cast<__nv_bfloat16*>(p.out) +
                                     ((b * (p.N >> 6) + (col >> 6)) * p.rows_per_batch + t) * 64 + (col & 63);
                             } else {
@@ -429,7 +448,11 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     else
         p.m_tiles = ceil_div(a.M, kBM);
     p.n_tiles = ceil_div(a.N, BN);
-    const int total = p.m_tiles * p.n_tiles;
+    p.splits = a.splits > 1 ? a.splits : 1;
+    p.kb_per_split = ceil_div(a.K / kBK, p.splits);
+    p.splits = ceil_div(a.K / kBK, p.kb_per_split);          // drop empty trailing splits
+    p.split_stride = a.split_stride;
+    const int total = p.m_tiles * p.n_tiles * p.splits;
     const int grid = std::min(total, num_sms);
     gemm_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
     WSB_CHECK_CUDA(cudaGetLastError());
@@ -462,6 +485,9 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
         return 2;
     }
     if (a.rowvec) WSB_REQUIRE(a.rows_per_batch > 0, "row-vector epilogue needs rows_per_batch");
+    if (a.splits > 1) WSB_REQUIRE(epi == EPI_F32 && !a.bias && a.split_stride >= static_cast<int64_t>(a.M) * a.ldc,
+                                  "split-K writes raw fp32 partial planes (no bias / activation)");
+    if (a.rows_per_batch > 0) WSB_REQUIRE(a.rows_per_batch >= 32, "rows_per_batch must be >= 32");
 #define WSB_GEMM_CASE(BN_)                                                                     \
     case BN_:                                                                                  \
         switch (epi) {                                                                         \
@@ -481,6 +507,40 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
         default: set_last_error("unsupported block_n"); return 2;
     }
 #undef WSB_GEMM_CASE
+}
+
+}  // namespace wsb
+
+namespace wsb {
+
+int gemm_effective_splits(int K, int splits) {
+    const int kb = K / kBK;
+    const int s = splits > 1 ? splits : 1;
+    const int per = ceil_div(kb, s);
+    return ceil_div(kb, per);
+}
+
+void gemm_pick_skinny(int M, int N, int K, int* block_n, int* splits) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int m_tiles = ceil_div(M, kBM), kb = K / kBK;
+    int best_bn = 128, best_s = 1, best_ctas = 0;
+    for (int bn : {128, 256}) {
+        if (N % bn != 0) continue;
+        const int base = m_tiles * (N / bn);
+        for (int s = 1; s <= kb && s <= 16; ++s) {
+            const int eff = gemm_effective_splits(K, s);
+            const int ctas = base * eff;
+            if (ctas > sms) break;
+            if (ctas > best_ctas) {
+                best_ctas = ctas;
+                best_bn = bn;
+                best_s = eff;
+            }
+        }
+    }
+    *block_n = best_bn;
+    *splits = best_s;
 }
 
 }  // namespace wsb

@@ -47,7 +47,13 @@ struct GemmArgs {
     float* argmax_val = nullptr;        // [M, n_tiles]
     int* argmax_idx = nullptr;          // [M, n_tiles]
     int block_n = 0;                    // 0 = choose
+    int splits = 1;                     // split-K factor (GEMM_OUT_F32 without bias only): partial plane s is
+    int64_t split_stride = 0;           //   written at out + s * split_stride; see splitk_reduce_* below
 };
+// effective number of partial planes gemm_bf16 will write for (K, splits)
+int gemm_effective_splits(int K, int splits);
+// pick (block_n, splits) for a skinny GEMM so that ~all SMs stream distinct weight bytes
+void gemm_pick_skinny(int M, int N, int K, int* block_n, int* splits);
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
 int gemm_n_tiles(int N, int block_n);
 int gemm_pick_block_n(int M, int N);
@@ -57,6 +63,13 @@ int layernorm_f32_to_bf16(const float* x, const float* gamma, const float* beta,
                           float* out_f32, int rows, int d, cudaStream_t stream);
 int conv1_gelu(const float* feats, const float* w /*[d][80][3]*/, const float* b, __nv_bfloat16* out, int B,
                int n_cols, int d, int64_t out_batch_stride, cudaStream_t stream);
+// split-K second phase: out = epilogue(sum_s partial[s]) -- deterministic summation order.
+//   bf16 variant : out_bf16[M][N] = act(sum + bias)
+//   resid+LN     : x[M][N] += sum + bias (fp32, in place); if gamma: xn_bf16 = LayerNorm(x) (N <= 1536)
+int splitk_reduce_bf16(const float* partial, int splits, int64_t split_stride, int M, int N, const float* bias, int gelu,
+                       __nv_bfloat16* out, cudaStream_t stream);
+int splitk_reduce_resid_ln(const float* partial, int splits, int64_t split_stride, int M, int N, const float* bias,
+                           float* x, const float* gamma, const float* beta, __nv_bfloat16* xn, cudaStream_t stream);
 int embed_tokens(const int* tokens, const int* positions, const __nv_bfloat16* emb, const float* pos_emb, float* x,
                  int B, int d, cudaStream_t stream);
 
