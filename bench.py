@@ -355,6 +355,8 @@ def run_ours(args):
     h2d = len(piece) * 4 + n_win * 24
     d2h = n_win * max_new * 4
 
+    ids_host = (ids[rank * n_win:(rank + 1) * n_win] if world > 1 else ids).cpu().numpy()
+    row_len = (ids_host != tok.eos_token_id).sum(axis=1)
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -368,6 +370,10 @@ def run_ours(args):
                              steps=e2e_steps, segments=len(res["onset"])),
                     gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=kernels, cpu_baseline=cpu,
                     decode_positions_per_step=float(np.mean(steps_done)),
+                    decode_row_lengths=dict(mean=float(row_len.mean()), median=float(np.median(row_len)),
+                                            p95=float(np.percentile(row_len, 95)), max=int(row_len.max()),
+                                            mean_positions_per_batch_of_4=float(np.mean(
+                                                [min(max_new, r.max() + 1) for r in row_len[:len(row_len) // 4 * 4].reshape(-1, 4)]))),
                     step_share_ms={k: v / args.steps for k, v in shares.items()})
         print(json.dumps(line))
     if world > 1:

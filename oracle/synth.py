@@ -77,10 +77,18 @@ def build_tokenizer():
     return tok
 
 
-def allowed_token_ids():
-    """Ids the shaped model may emit: timestamps <|0|>..<|1000|>, digits, EOS."""
-    return sorted(list(range(ID_TS0, ID_TS0 + TOTAL_SPEC_COLUMNS + 1)) +
-                  list(range(ID_DIGIT0, ID_DIGIT0 + 10)) + [ID_EOT])
+def allowed_token_ids(ts_step=25, n_digits=4):
+    """Ids the shaped model may emit: every `ts_step`-th timestamp token <|0|>..<|1000|>, the first
+    `n_digits` digit tokens and EOS.  The size of this set sets the statistics of the random model's
+    output: P(EOS) = 1/len -> geometric decode lengths with mean ~len (the labelled marmoset example
+    has 7.6 segments ~ 24 tokens per 2.5 s window), P(digit) = n_digits/len -> how often the
+    `<|on|>cluster<|off|>` grammar is hit by chance."""
+    return sorted(list(range(ID_TS0, ID_TS0 + TOTAL_SPEC_COLUMNS + 1, ts_step)) +
+                  list(range(ID_DIGIT0, ID_DIGIT0 + n_digits)) + [ID_EOT])
+
+
+GELU_MEAN = 0.28209479177387814       # E[gelu(h)], h ~ N(0,1)
+DEFAULT_CODEBOOK = {"vocal": 0, "b": 1, "c": 2, "d": 3}
 
 
 def make_hf_model(arch="tiny", seed=0, shaped=True, cluster_codebook=None,
@@ -98,7 +106,7 @@ def make_hf_model(arch="tiny", seed=0, shaped=True, cluster_codebook=None,
                         decoder_start_token_id=ID_SOT, dropout=0.0, attention_dropout=0.0,
                         activation_dropout=0.0)
     cfg.total_spec_columns = TOTAL_SPEC_COLUMNS
-    cfg.cluster_codebook = cluster_codebook if cluster_codebook is not None else {"vocal": 0, "b": 1}
+    cfg.cluster_codebook = cluster_codebook if cluster_codebook is not None else dict(DEFAULT_CODEBOOK)
     cfg.species_codebook = {s[2:-2]: s for s in SPECIES}
     if default_segmentation_config is not None:
         cfg.default_segmentation_config = default_segmentation_config
@@ -106,8 +114,15 @@ def make_hf_model(arch="tiny", seed=0, shaped=True, cluster_codebook=None,
     model = WhisperForConditionalGeneration(cfg)
     model.eval()
     if shaped:
+        ts_step = shape_kw.pop("ts_step", 25)
+        n_allowed_digits = shape_kw.pop("n_allowed_digits", 4)
         shape_weights_(model, seed, **shape_kw)
-        allowed = set(allowed_token_ids())
+        allowed = set(allowed_token_ids(ts_step, n_allowed_digits))
+        if getattr(model, "_wsb_calibrate", True):
+            sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+            calibrate_output_bias_(sd, H, L, sorted(allowed), seed)
+            with torch.no_grad():
+                model.model.decoder.layer_norm.bias.copy_(sd["model.decoder.layer_norm.bias"])
         sup = [i for i in range(VOCAB_SIZE) if i not in allowed]
         model.generation_config.suppress_tokens = sup
         model.generation_config.begin_suppress_tokens = None
@@ -116,8 +131,9 @@ def make_hf_model(arch="tiny", seed=0, shaped=True, cluster_codebook=None,
     return model
 
 
-def shape_weights_(model, seed, n_digits=2, eos_scale=2.0, qk_cross=3.0, qk_self=2.0, emb_std=0.05,
-                   digit_scale=2.5):
+def shape_weights_(model, seed, n_digits=2, eos_scale=1.3, qk_cross=3.0, qk_self=2.0, emb_std=0.05,
+                   digit_scale=1.0, conv_gain=2.0, bias_std=0.02, cancel_gelu_mean=True,
+                   dec_pos_std=2.0, cross_out_gain=2.0, calibrate=True):
     """SURVEY.md section 7.2-1 recipe (constants tuned so rows end with EOS at varied lengths)."""
     import torch
     g = torch.Generator().manual_seed(1000 + seed)
@@ -131,20 +147,29 @@ def shape_weights_(model, seed, n_digits=2, eos_scale=2.0, qk_cross=3.0, qk_self
             if name.endswith("embed_tokens.weight") or name == "proj_out.weight":
                 continue
             if name.endswith("decoder.embed_positions.weight"):
-                p.copy_(torch.randn(p.shape, generator=g))
+                p.copy_(torch.randn(p.shape, generator=g) * dec_pos_std)
                 continue
             if p.dim() >= 2:
                 fan_in = p[0].numel()
                 p.copy_(torch.randn(p.shape, generator=g) / fan_in ** 0.5)
                 if name.endswith("q_proj.weight") or name.endswith("k_proj.weight"):
                     p.mul_(qk_cross if "encoder_attn" in name else qk_self)
+                if name.endswith("encoder.conv1.weight"):
+                    p.mul_(conv_gain)
+                if name.endswith("encoder_attn.out_proj.weight"):
+                    p.mul_(cross_out_gain)
             else:
-                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+                p.copy_(torch.randn(p.shape, generator=g) * bias_std)
+        if cancel_gelu_mean:
+            for name, p in sd.items():
+                if name.endswith("fc2.bias"):
+                    p.sub_(GELU_MEAN * sd[name[:-4] + "weight"].sum(dim=1))
         emb = model.model.decoder.embed_tokens.weight
         emb.copy_(torch.randn(emb.shape, generator=g) * emb_std)
         emb[ID_DIGIT0:ID_DIGIT0 + n_digits] *= digit_scale
         emb[ID_EOT] *= eos_scale
     model.tie_weights()
+    model._wsb_calibrate = calibrate
 
 
 def save_checkpoint(model, path, tokenizer=None):
@@ -204,7 +229,7 @@ def hf_config_dict(arch, cluster_codebook=None, default_segmentation_config=None
                decoder_ffn_dim=F, max_source_positions=TOTAL_SPEC_COLUMNS // 2, max_target_positions=448,
                pad_token_id=ID_EOT, bos_token_id=ID_EOT, eos_token_id=ID_EOT, decoder_start_token_id=ID_SOT,
                activation_function="gelu", scale_embedding=False, total_spec_columns=TOTAL_SPEC_COLUMNS,
-               cluster_codebook=cluster_codebook if cluster_codebook is not None else {"vocal": 0, "b": 1},
+               cluster_codebook=cluster_codebook if cluster_codebook is not None else dict(DEFAULT_CODEBOOK),
                suppress_tokens=None, begin_suppress_tokens=None)
     if default_segmentation_config is not None:
         cfg["default_segmentation_config"] = default_segmentation_config
@@ -220,12 +245,20 @@ def sinusoids(length, channels, max_timescale=10000):
     return torch.cat([t.sin(), t.cos()], dim=1)
 
 
-def make_state(arch="large", seed=0, n_digits=2, eos_scale=2.0, qk_cross=3.0, qk_self=2.0, emb_std=0.05,
-               digit_scale=2.5, dtype=None):
+# per-architecture EOS boost: deeper networks need a larger one for rows to terminate (tuned on the GPU
+# with tools/tune_large.py: large/3.0 -> median 16, mean ~110 generated tokens, ~5 % of rows never stop)
+ARCH_EOS_SCALE = {"tiny": 1.3, "base": 1.3, "small": 1.3, "large": 3.0}
+
+
+def make_state(arch="large", seed=0, n_digits=2, eos_scale=None, qk_cross=3.0, qk_self=2.0, emb_std=0.05,
+               digit_scale=1.0, conv_gain=2.0, ts_step=25, n_allowed_digits=4, bias_std=0.02,
+               cancel_gelu_mean=True, dec_pos_std=2.0, cross_out_gain=2.0, calibrate=True, dtype=None):
     """(config dict, state dict, generation dict) of a shaped random checkpoint -- same recipe as
     shape_weights_, HF parameter names, drawn tensor by tensor from one seeded CPU generator."""
     import torch
     d, L, H, F = ARCHS[arch]
+    if eos_scale is None:
+        eos_scale = ARCH_EOS_SCALE.get(arch, 1.3)
     g = torch.Generator().manual_seed(2000 + seed)
     sd = {}
 
@@ -233,20 +266,20 @@ def make_state(arch="large", seed=0, n_digits=2, eos_scale=2.0, qk_cross=3.0, qk
         w = torch.randn(shape or (out_f, in_f), generator=g) * (gain / in_f ** 0.5)
         sd[name] = w if dtype is None else w.to(dtype)
 
-    def vec(name, n, std=0.1):
-        sd[name] = torch.randn(n, generator=g) * std
+    def vec(name, n, std=None):
+        sd[name] = torch.randn(n, generator=g) * (bias_std if std is None else std)
 
     def ln(prefix):
         sd[prefix + ".weight"] = torch.ones(d)
         sd[prefix + ".bias"] = torch.zeros(d)
 
-    def attn(prefix, qk):
+    def attn(prefix, qk, out_gain=1.0):
         mat(prefix + "q_proj.weight", d, d, qk)
         vec(prefix + "q_proj.bias", d)
         mat(prefix + "k_proj.weight", d, d, qk)
         mat(prefix + "v_proj.weight", d, d)
         vec(prefix + "v_proj.bias", d)
-        mat(prefix + "out_proj.weight", d, d)
+        mat(prefix + "out_proj.weight", d, d, out_gain)
         vec(prefix + "out_proj.bias", d)
 
     def mlp(prefix):
@@ -254,8 +287,12 @@ def make_state(arch="large", seed=0, n_digits=2, eos_scale=2.0, qk_cross=3.0, qk
         vec(prefix + "fc1.bias", F)
         mat(prefix + "fc2.weight", d, F)
         vec(prefix + "fc2.bias", d)
+        if cancel_gelu_mean:
+            # E[gelu(h)] for h ~ N(0,1) is 1/sqrt(4 pi): without this every MLP adds the same constant
+            # vector at every position and window, and a handful of tokens win every arg-max
+            sd[prefix + "fc2.bias"] = sd[prefix + "fc2.bias"] - GELU_MEAN * sd[prefix + "fc2.weight"].float().sum(dim=1)
 
-    mat("model.encoder.conv1.weight", d, 80 * 3, shape=(d, 80, 3))
+    mat("model.encoder.conv1.weight", d, 80 * 3, gain=conv_gain, shape=(d, 80, 3))
     vec("model.encoder.conv1.bias", d)
     mat("model.encoder.conv2.weight", d, d * 3, shape=(d, d, 3))
     vec("model.encoder.conv2.bias", d)
@@ -271,19 +308,42 @@ def make_state(arch="large", seed=0, n_digits=2, eos_scale=2.0, qk_cross=3.0, qk
     emb[ID_DIGIT0:ID_DIGIT0 + n_digits] *= digit_scale
     emb[ID_EOT] *= eos_scale
     sd["model.decoder.embed_tokens.weight"] = emb
-    sd["model.decoder.embed_positions.weight"] = torch.randn(448, d, generator=g)
+    sd["model.decoder.embed_positions.weight"] = torch.randn(448, d, generator=g) * dec_pos_std
     for i in range(L):
         p = "model.decoder.layers.%d." % i
         ln(p + "self_attn_layer_norm")
         attn(p + "self_attn.", qk_self)
         ln(p + "encoder_attn_layer_norm")
-        attn(p + "encoder_attn.", qk_cross)
+        attn(p + "encoder_attn.", qk_cross, cross_out_gain)
         ln(p + "final_layer_norm")
         mlp(p)
     ln("model.decoder.layer_norm")
-    allowed = set(allowed_token_ids())
+    allowed = set(allowed_token_ids(ts_step, n_allowed_digits))
     gen = dict(suppress_tokens=[i for i in range(VOCAB_SIZE) if i not in allowed], begin_suppress_tokens=None)
+    if calibrate:
+        calibrate_output_bias_(sd, H, L, sorted(allowed), seed)
     return hf_config_dict(arch), sd, gen
+
+
+def calibrate_output_bias_(sd, n_heads, n_layers, allowed, seed, n_windows=2, n_positions=24):
+    """Remove the position- and window-independent component of the decoder's final hidden state by
+    folding its negative mean into `decoder.layer_norm.bias`.  A random deep network otherwise carries
+    a large constant vector to the output projection and the same 3-4 tokens win every arg-max; with
+    the bias calibrated the emitted tokens follow the audio (cross-attention) and the position."""
+    import torch
+    from . import frontend_np as FO
+    from .whisper_torch import WhisperOracle
+    audio = synth_audio(n_windows * 2.5, 32000, seed=9000 + seed)
+    feats = FO.sliced_audio_features(audio, 32000, 0, 0.0025, 1, dtype=np.float32)
+    x = torch.from_numpy(np.asarray([f[2] for f in feats]))
+    orc = WhisperOracle(sd, n_heads, n_layers)
+    enc = orc.encode(x)
+    rng = np.random.default_rng(9000 + seed)
+    ids = torch.from_numpy(rng.choice(np.array(allowed), size=(x.shape[0], n_positions)))
+    ids[:, :3] = torch.tensor([ID_SOT, ID_EN, ID_NOTIMESTAMPS])
+    hidden = orc.decode_logits(ids, enc=enc, return_hidden=True)
+    mean = hidden[:, 3:].reshape(-1, hidden.shape[-1]).mean(dim=0)
+    sd["model.decoder.layer_norm.bias"] = sd["model.decoder.layer_norm.bias"].float() - mean
 
 
 def token_table_files(path):

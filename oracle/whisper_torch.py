@@ -96,7 +96,7 @@ class WhisperOracle:
         return kv
 
     @torch.no_grad()
-    def decode_logits(self, ids, enc=None, cross=None, cache=None):
+    def decode_logits(self, ids, enc=None, cross=None, cache=None, return_hidden=False):
         """Teacher-forced logits f32 [B,T,V] for decoder input ids [B,T] (positions 0..T-1 unless
         `cache` holds past self-attention K/V, in which case ids are the new tokens)."""
         w = self.w
@@ -126,6 +126,8 @@ class WhisperOracle:
             h = F.gelu(F.linear(h, w[p + "fc1.weight"], w[p + "fc1.bias"]))
             x = x + F.linear(h, w[p + "fc2.weight"], w[p + "fc2.bias"])
         x = _ln(x, w["model.decoder.layer_norm.weight"], w["model.decoder.layer_norm.bias"])
+        if return_hidden:
+            return x
         return F.linear(x, w["model.decoder.embed_tokens.weight"])
 
     @torch.no_grad()
