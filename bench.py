@@ -33,6 +33,11 @@ sys.path.insert(0, ROOT)
 SR, STS, MIN_FREQ = 48000, 0.0025, 0
 SECONDS_PER_GPU = 600.0
 PROMPT_LEN = 3
+# Decode positions the REFERENCE executes per generate() call on this workload: it decodes batch_size=4
+# windows together (segment() default, reference model.py:407) until the longest row emits EOS or hits
+# max_length.  Measured with this seed/recipe on the GPU path (bench JSON key
+# decode_row_lengths.mean_positions_per_batch_of_4, identical tokens by construction): 305 of 445.
+REF_POSITIONS_PER_BATCH4 = {"large": 305.0}
 CATS = ["conv1", "enc_gemm", "enc_attn", "enc_ln", "crosskv_gemm", "dec_gemm", "dec_logits", "dec_self_attn",
         "dec_cross_attn", "dec_ln", "misc"]
 
@@ -129,12 +134,14 @@ def cpu_reference_sample(state, arch, max_length, n_windows=2, decode_steps=12, 
     t_dec = time.perf_counter() - t0                     # includes cross-K/V and the 3 prompt positions
     n = len(feats)
     per_step = t_dec / (decode_steps + PROMPT_LEN - 1)
-    total = t_front + t_enc + per_step * (max_length - 1)
+    positions = REF_POSITIONS_PER_BATCH4.get(arch, float(max_length - PROMPT_LEN)) if max_length == 448 else float(max_length - PROMPT_LEN)
+    total = t_front + t_enc + per_step * (positions + PROMPT_LEN - 1)
     audio_s = n * 1000 * STS
     return dict(value=audio_s / total, unit="audio-s/s", cores=threads, kind="port",
-                sample="%d windows (%s arch): front-end %.2fs + encoder %.2fs measured, %d greedy steps measured "
-                       "(%.3fs/step at batch %d) and scaled to max_length=%d" %
-                       (n, arch, t_front, t_enc, decode_steps, per_step, n, max_length),
+                sample="%d windows = one reference batch (%s arch): front-end %.2fs + encoder %.2fs measured, %d greedy "
+                       "steps measured (%.3fs/step at batch %d) and scaled to the %.0f decode positions the reference "
+                       "runs per batch of 4 on this workload (max_length=%d)" %
+                       (n, arch, t_front, t_enc, decode_steps, per_step, n, positions, max_length),
                 frontend_s=t_front, encoder_s=t_enc, decode_s_per_step=per_step)
 
 
@@ -388,7 +395,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="large")
     ap.add_argument("--max-length", type=int, default=448, dest="max_length")
-    ap.add_argument("--ref-windows", type=int, default=2, dest="ref_windows")
+    ap.add_argument("--ref-windows", type=int, default=4, dest="ref_windows")
     ap.add_argument("--ref-decode-steps", type=int, default=12, dest="ref_decode_steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
