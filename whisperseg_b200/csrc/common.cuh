@@ -35,11 +35,37 @@ const char* get_last_error();
 // counts kernels launched by this library since the last reset (bench.py's "gpu_launches")
 void count_launch(int n = 1);
 
+// Programmatic dependent launch (PDL): while the engine has this flag set (decode step), kernels are
+// launched with programmaticStreamSerialization so the next kernel's launch + prologue overlaps the tail
+// of the previous one; every such kernel calls pdl_wait() before touching its inputs.
+extern thread_local bool g_use_pdl;
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                        Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// wait for the preceding kernel in the stream (no-op without a programmatic dependency), then let the
+// next kernel start its own prologue
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -39,10 +39,18 @@ struct DaParams {
     __nv_bfloat16* out;           // [B][d]
     int d;
     int self_mode;
+    // optional fused split-K second phase: q (and the new k, v in self mode) = bias + sum of fp32 partial planes
+    const float* part;            // [splits][B][part_ld] or null (then q / new_k / new_v bf16 are read)
+    int splits;
+    long long split_stride;
+    int part_ld;
+    const float* bias;            // [part_ld]
 };
 
 __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaParams p) {
     const int h = blockIdx.x, b = blockIdx.y;
+    pdl_wait();
+    pdl_launch_dependents();
     if (p.finished && p.finished[b]) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     __shared__ float s_q[64];
@@ -54,21 +62,30 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaPa
     const __nv_bfloat16* K = p.k_base + blk;
     const __nv_bfloat16* V = p.v_base + blk;
     int n_keys;
+    // value of column `col` of this row's projection output: bf16 activation, or bias + split-K planes
+    auto proj = [&](int col, const __nv_bfloat16* act) -> float {
+        if (p.part == nullptr) return __bfloat162float(act[static_cast<long long>(b) * p.q_ld + h * 64 + (col & 63)]);
+        float acc = __ldg(p.bias + col);
+        const float* src = p.part + static_cast<long long>(b) * p.part_ld + col;
+        for (int sp = 0; sp < p.splits; ++sp) acc += src[sp * p.split_stride];
+        return acc;
+    };
     if (p.self_mode) {
         const int pos = p.pos_offset + *p.step_ptr;
         n_keys = pos + 1;
         if (tid < 64) {
-            const __nv_bfloat16 kv = p.new_k[static_cast<long long>(b) * p.q_ld + h * 64 + tid];
-            p.k_cache[blk + static_cast<long long>(pos) * 64 + tid] = kv;
+            const float kv = proj(p.d + h * 64 + tid, p.new_k);
+            p.k_cache[blk + static_cast<long long>(pos) * 64 + tid] = __float2bfloat16(kv);
         } else {
             const int e = tid - 64;
-            const __nv_bfloat16 vv = p.new_v[static_cast<long long>(b) * p.q_ld + h * 64 + e];
-            p.v_cache[blk + static_cast<long long>(pos) * 64 + e] = vv;
+            const float vv = proj(2 * p.d + h * 64 + e, p.new_v);
+            p.v_cache[blk + static_cast<long long>(pos) * 64 + e] = __float2bfloat16(vv);
         }
     } else {
         n_keys = p.n_keys_fixed;
     }
-    if (tid < 64) s_q[tid] = __bfloat162float(p.q[static_cast<long long>(b) * p.q_ld + h * 64 + tid]);
+    // q is rounded to bf16 like the stand-alone second phase would, so both paths give identical results
+    if (tid < 64) s_q[tid] = __bfloat162float(__float2bfloat16(proj(h * 64 + tid, p.q)));
     __syncthreads();                                   // also orders the cache append before the reads below
 
     // scores: a warp covers 4 keys per iteration; lane = (key % 4) * 8 + 16-byte chunk
@@ -154,9 +171,9 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaPa
     }
 }
 
-int decode_self_attention(const __nv_bfloat16* qkv, int d, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int t_max,
-                          const int* step_ptr, int pos_offset, const unsigned char* finished, __nv_bfloat16* out,
-                          int B, int n_heads, cudaStream_t stream) {
+int decode_self_attention(const __nv_bfloat16* qkv, const SplitkInput* part, int d, __nv_bfloat16* k_cache,
+                          __nv_bfloat16* v_cache, int t_max, const int* step_ptr, int pos_offset,
+                          const unsigned char* finished, __nv_bfloat16* out, int B, int n_heads, cudaStream_t stream) {
     WSB_REQUIRE(t_max <= kDaMaxKeys, "self-attention cache longer than 512 positions");
     if (B <= 0) return 0;
     DaParams p;
@@ -177,14 +194,18 @@ int decode_self_attention(const __nv_bfloat16* qkv, int d, __nv_bfloat16* k_cach
     p.out = out;
     p.d = d;
     p.self_mode = 1;
-    decode_attention_kernel<<<dim3(n_heads, B), kDaThreads, 0, stream>>>(p);
-    WSB_CHECK_CUDA(cudaGetLastError());
+    p.part = part ? part->planes : nullptr;
+    p.splits = part ? part->splits : 0;
+    p.split_stride = part ? part->split_stride : 0;
+    p.part_ld = 3 * d;
+    p.bias = part ? part->bias : nullptr;
+    WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel, dim3(n_heads, B), dim3(kDaThreads), 0, stream, p));
     count_launch();
     return 0;
 }
 
-int decode_cross_attention(const __nv_bfloat16* q, int d, const __nv_bfloat16* cross_kv, int layer, int n_layers,
-                           int T, const unsigned char* finished, __nv_bfloat16* out, int B, int n_heads,
+int decode_cross_attention(const __nv_bfloat16* q, const SplitkInput* part, int d, const __nv_bfloat16* cross_kv, int layer,
+                           int n_layers, int T, const unsigned char* finished, __nv_bfloat16* out, int B, int n_heads,
                            cudaStream_t stream) {
     WSB_REQUIRE(T <= kDaMaxKeys, "cross-attention over more than 512 encoder positions");
     if (B <= 0) return 0;
@@ -208,8 +229,12 @@ int decode_cross_attention(const __nv_bfloat16* q, int d, const __nv_bfloat16* c
     p.out = out;
     p.d = d;
     p.self_mode = 0;
-    decode_attention_kernel<<<dim3(n_heads, B), kDaThreads, 0, stream>>>(p);
-    WSB_CHECK_CUDA(cudaGetLastError());
+    p.part = part ? part->planes : nullptr;
+    p.splits = part ? part->splits : 0;
+    p.split_stride = part ? part->split_stride : 0;
+    p.part_ld = d;
+    p.bias = part ? part->bias : nullptr;
+    WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel, dim3(n_heads, B), dim3(kDaThreads), 0, stream, p));
     count_launch();
     return 0;
 }
@@ -226,6 +251,8 @@ __global__ void argmax_finalize_kernel(const float* __restrict__ val, const int*
                                        unsigned char* __restrict__ finished, const int* __restrict__ step_ptr,
                                        int* __restrict__ n_active, int eos_id, int pad_id, int B) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    pdl_wait();
+    pdl_launch_dependents();
     const int pos = *step_ptr;
     if (warp < B) {
         float best = -INFINITY;
@@ -265,18 +292,20 @@ __global__ void argmax_finalize_kernel(const float* __restrict__ val, const int*
         }
     }
 }
-__global__ void step_increment_kernel(int* step_ptr) { *step_ptr += 1; }
+__global__ void step_increment_kernel(int* step_ptr) {
+    pdl_wait();
+    pdl_launch_dependents();
+    *step_ptr += 1;
+}
 
 int argmax_finalize(const float* val, const int* idx, int n_tiles, int* tokens_out, int max_new, int out_offset,
                     int* next_token, const int* forced, int forced_ld, unsigned char* finished, int* step_ptr,
                     int* n_active, int eos_id, int pad_id, int B, cudaStream_t stream) {
     if (B <= 0) return 0;
-    argmax_finalize_kernel<<<ceil_div(B * 32, 256), 256, 0, stream>>>(val, idx, n_tiles, tokens_out, max_new, out_offset,
-                                                                       next_token, forced, forced_ld, finished, step_ptr,
-                                                                       n_active, eos_id, pad_id, B);
-    WSB_CHECK_CUDA(cudaGetLastError());
-    step_increment_kernel<<<1, 1, 0, stream>>>(step_ptr);
-    WSB_CHECK_CUDA(cudaGetLastError());
+    WSB_CHECK_CUDA(launch_kernel(argmax_finalize_kernel, dim3(ceil_div(B * 32, 256)), dim3(256), 0, stream, val, idx, n_tiles,
+                                 tokens_out, max_new, out_offset, next_token, forced, forced_ld, finished,
+                                 static_cast<const int*>(step_ptr), n_active, eos_id, pad_id, B));
+    WSB_CHECK_CUDA(launch_kernel(step_increment_kernel, dim3(1), dim3(1), 0, stream, step_ptr));
     count_launch(2);
     return 0;
 }
@@ -284,6 +313,8 @@ int argmax_finalize(const float* val, const int* idx, int n_tiles, int* tokens_o
 // prompt positions before the last one: no logits, just feed the next prompt token
 __global__ void prefill_advance_kernel(int* __restrict__ next_token, const int* __restrict__ forced, int forced_ld,
                                        const int* __restrict__ prompt, int* __restrict__ step_ptr, int B) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int pos = *step_ptr;
     for (int b = threadIdx.x; b < B; b += blockDim.x)
         next_token[b] = forced ? forced[static_cast<long long>(b) * forced_ld + pos + 1] : prompt[pos + 1];
@@ -293,8 +324,8 @@ __global__ void prefill_advance_kernel(int* __restrict__ next_token, const int* 
 
 int prefill_advance(int* next_token, const int* forced, int forced_ld, const int* prompt_dev, int* step_ptr, int B,
                     cudaStream_t stream) {
-    prefill_advance_kernel<<<1, 256, 0, stream>>>(next_token, forced, forced_ld, prompt_dev, step_ptr, B);
-    WSB_CHECK_CUDA(cudaGetLastError());
+    WSB_CHECK_CUDA(launch_kernel(prefill_advance_kernel, dim3(1), dim3(256), 0, stream, next_token, forced, forced_ld, prompt_dev,
+                                 step_ptr, B));
     count_launch();
     return 0;
 }

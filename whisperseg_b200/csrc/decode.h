@@ -5,11 +5,18 @@
 
 namespace wsb {
 
-int decode_self_attention(const __nv_bfloat16* qkv, int d, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int t_max,
-                          const int* step_ptr, int pos_offset, const unsigned char* finished, __nv_bfloat16* out,
-                          int B, int n_heads, cudaStream_t stream);
-int decode_cross_attention(const __nv_bfloat16* q, int d, const __nv_bfloat16* cross_kv, int layer, int n_layers,
-                           int T, const unsigned char* finished, __nv_bfloat16* out, int B, int n_heads,
+// fp32 split-K partial planes of the projection feeding an attention kernel (fused second phase)
+struct SplitkInput {
+    const float* planes;
+    int splits;
+    long long split_stride;
+    const float* bias;
+};
+int decode_self_attention(const __nv_bfloat16* qkv, const SplitkInput* part, int d, __nv_bfloat16* k_cache,
+                          __nv_bfloat16* v_cache, int t_max, const int* step_ptr, int pos_offset,
+                          const unsigned char* finished, __nv_bfloat16* out, int B, int n_heads, cudaStream_t stream);
+int decode_cross_attention(const __nv_bfloat16* q, const SplitkInput* part, int d, const __nv_bfloat16* cross_kv, int layer,
+                           int n_layers, int T, const unsigned char* finished, __nv_bfloat16* out, int B, int n_heads,
                            cudaStream_t stream);
 int argmax_finalize(const float* val, const int* idx, int n_tiles, int* tokens_out, int max_new, int out_offset,
                     int* next_token, const int* forced, int forced_ld, unsigned char* finished, int* step_ptr,

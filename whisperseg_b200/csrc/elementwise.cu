@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         float* __restrict__ out_f32, int rows, int d) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_wait();
+    pdl_launch_dependents();
     if (row >= rows) return;
     const int nvec = d >> 2;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d);
@@ -69,9 +71,8 @@ int layernorm_f32_to_bf16(const float* x, const float* gamma, const float* beta,
     WSB_REQUIRE(d % 4 == 0 && d <= kLnMaxVec * 128, "LayerNorm width must be a multiple of 4 and <= 1536");
     if (rows <= 0) return 0;
     const int rows_per_block = 8;
-    layernorm_kernel<<<ceil_div(rows, rows_per_block), rows_per_block * 32, 0, stream>>>(x, gamma, beta, out_bf16,
-                                                                                         out_f32, rows, d);
-    WSB_CHECK_CUDA(cudaGetLastError());
+    WSB_CHECK_CUDA(launch_kernel(layernorm_kernel, dim3(ceil_div(rows, rows_per_block)), dim3(rows_per_block * 32), 0, stream, x,
+                                 gamma, beta, out_bf16, out_f32, rows, d));
     count_launch();
     return 0;
 }
@@ -90,6 +91,8 @@ __global__ void __launch_bounds__(kRedThreads) splitk_reduce_bf16_kernel(const f
                                                                          __nv_bfloat16* __restrict__ out) {
     const int row = blockIdx.x;
     const int nvec = N >> 2;
+    pdl_wait();
+    pdl_launch_dependents();
     const float4* base = reinterpret_cast<const float4*>(partial + static_cast<long long>(row) * N);
     const long long sv = split_stride >> 2;
     for (int j = threadIdx.x; j < nvec; j += kRedThreads) {
@@ -123,6 +126,8 @@ __global__ void __launch_bounds__(kRedThreads) splitk_reduce_resid_ln_kernel(con
                                                                              const float* __restrict__ beta,
                                                                              __nv_bfloat16* __restrict__ xn) {
     __shared__ float s_red[2][kRedThreads / 32];
+    pdl_wait();
+    pdl_launch_dependents();
     const int row = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nvec = N >> 2;
@@ -196,8 +201,8 @@ int splitk_reduce_bf16(const float* partial, int splits, int64_t split_stride, i
                        __nv_bfloat16* out, cudaStream_t stream) {
     WSB_REQUIRE(N % 4 == 0 && split_stride % 4 == 0 && splits <= kRedMaxSplits, "split-K reduce shape");
     if (M <= 0) return 0;
-    splitk_reduce_bf16_kernel<<<M, kRedThreads, 0, stream>>>(partial, splits, split_stride, N, bias, gelu, out);
-    WSB_CHECK_CUDA(cudaGetLastError());
+    WSB_CHECK_CUDA(launch_kernel(splitk_reduce_bf16_kernel, dim3(M), dim3(kRedThreads), 0, stream, partial, splits,
+                                 static_cast<long long>(split_stride), N, bias, gelu, out));
     count_launch();
     return 0;
 }
@@ -207,8 +212,8 @@ int splitk_reduce_resid_ln(const float* partial, int splits, int64_t split_strid
     WSB_REQUIRE(N % 4 == 0 && N <= kRedLnVec * kRedThreads * 4 && split_stride % 4 == 0 && splits <= kRedMaxSplits,
                 "split-K reduce shape (row width <= 1536)");
     if (M <= 0) return 0;
-    splitk_reduce_resid_ln_kernel<<<M, kRedThreads, 0, stream>>>(partial, splits, split_stride, N, bias, x, gamma, beta, xn);
-    WSB_CHECK_CUDA(cudaGetLastError());
+    WSB_CHECK_CUDA(launch_kernel(splitk_reduce_resid_ln_kernel, dim3(M), dim3(kRedThreads), 0, stream, partial, splits,
+                                 static_cast<long long>(split_stride), N, bias, x, gamma, beta, xn));
     count_launch();
     return 0;
 }
@@ -304,6 +309,8 @@ int conv1_gelu(const float* feats, const float* wt, const float* b, __nv_bfloat1
 __global__ void embed_kernel(const int* __restrict__ tokens, const int* __restrict__ step_ptr, int pos_offset,
                              const __nv_bfloat16* __restrict__ emb, const float* __restrict__ pos_emb,
                              float* __restrict__ x, int d) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.x;
     const int tok = tokens[b];
     const int pos = pos_offset + (step_ptr ? *step_ptr : 0);
@@ -315,8 +322,7 @@ __global__ void embed_kernel(const int* __restrict__ tokens, const int* __restri
 int embed_tokens_step(const int* tokens, const int* step_ptr, int pos_offset, const __nv_bfloat16* emb,
                       const float* pos_emb, float* x, int B, int d, cudaStream_t stream) {
     if (B <= 0) return 0;
-    embed_kernel<<<B, 256, 0, stream>>>(tokens, step_ptr, pos_offset, emb, pos_emb, x, d);
-    WSB_CHECK_CUDA(cudaGetLastError());
+    WSB_CHECK_CUDA(launch_kernel(embed_kernel, dim3(B), dim3(256), 0, stream, tokens, step_ptr, pos_offset, emb, pos_emb, x, d));
     count_launch();
     return 0;
 }

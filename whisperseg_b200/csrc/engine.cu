@@ -22,6 +22,7 @@ static std::atomic<long long> g_launches{0};
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* get_last_error() { return g_last_error.c_str(); }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+thread_local bool g_use_pdl = false;
 
 // ---------------------------------------------------------------------------- event profiling
 // Optional CUDA-event bracketing of kernel classes on the launching stream (bench.py's roofline
@@ -125,6 +126,7 @@ struct Model {
     cudaGraphExec_t graph_exec = nullptr;
     int graph_batch = -1;
     int graph_kernels = 0;
+    bool use_pdl = false;
     int* pinned_active = nullptr;
 };
 
@@ -349,7 +351,7 @@ static int encode(Model* m, const float* feats, int B, float* hidden_f32, cudaSt
 //   mode 0: out_bf16 = act(sum + bias)         mode 1: x += sum + bias; xn = LayerNorm(x) (if gamma)
 static int skinny_linear(Model* m, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, int B, int N, int K,
                          int gelu, __nv_bfloat16* out_bf16, float* x, const float* gamma, const float* beta,
-                         __nv_bfloat16* xn, cudaStream_t s) {
+                         __nv_bfloat16* xn, cudaStream_t s, SplitkInput* planes_only = nullptr) {
     int bn = 128, splits = 1;
     gemm_pick_skinny(B, N, K, &bn, &splits);
     const int64_t plane = static_cast<int64_t>(B) * N;
@@ -371,8 +373,15 @@ static int skinny_linear(Model* m, const __nv_bfloat16* A, const __nv_bfloat16* 
         g.split_stride = plane;
         WSB_RUN(gemm_bf16(g, s));
     }
-    ProfScope ps(PROF_DEC_LN, 4.0 * B * N * (splits + 1), s);
     const int eff = gemm_effective_splits(K, splits);
+    if (planes_only) {                                  // the consumer kernel performs the second phase itself
+        planes_only->planes = m->dpart;
+        planes_only->splits = eff;
+        planes_only->split_stride = plane;
+        planes_only->bias = bias;
+        return 0;
+    }
+    ProfScope ps(PROF_DEC_LN, 4.0 * B * N * (splits + 1), s);
     if (out_bf16) return splitk_reduce_bf16(m->dpart, eff, plane, B, N, bias, gelu, out_bf16, s);
     return splitk_reduce_resid_ln(m->dpart, eff, plane, B, N, bias, x, gamma, beta, xn, s);
 }
@@ -383,6 +392,11 @@ static int decode_step(Model* m, int B, bool with_logits, bool first_generated, 
     const wsb_model_config& c = m->cfg;
     const int d = c.d_model, F = c.ffn_dim, L = c.n_layers, H = c.n_heads, T = m->T, tmax = c.max_target_positions;
     const unsigned char* fin = forced ? nullptr : m->finished;
+    struct PdlScope {
+        bool prev;
+        explicit PdlScope(bool on) : prev(g_use_pdl) { g_use_pdl = on; }
+        ~PdlScope() { g_use_pdl = prev; }
+    } pdl_scope(m->use_pdl);
     WSB_RUN(embed_tokens_step(m->next_token, m->step, 0, m->dec_emb, m->dec_pos, m->dx, B, d, s));
     const long long cache_l = static_cast<long long>(B) * H * tmax * 64;
     {
@@ -394,17 +408,18 @@ static int decode_step(Model* m, int B, bool with_logits, bool first_generated, 
         // every LayerNorm after the first is fused into the preceding residual reduction
         const float* next_g = (l + 1 < L) ? m->dec[l + 1].ln1_g : m->dec_ln_g;
         const float* next_b = (l + 1 < L) ? m->dec[l + 1].ln1_b : m->dec_ln_b;
-        WSB_RUN(skinny_linear(m, m->dxn, e.sqkv_w, e.sqkv_b, B, 3 * d, d, 0, m->dqkv, nullptr, nullptr, nullptr, nullptr, s));
+        SplitkInput part;
+        WSB_RUN(skinny_linear(m, m->dxn, e.sqkv_w, e.sqkv_b, B, 3 * d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, &part));
         {
             ProfScope ps(PROF_DEC_SELF_ATTN, 0.0, s);
-            WSB_RUN(decode_self_attention(m->dqkv, d, m->k_cache + l * cache_l, m->v_cache + l * cache_l, tmax, m->step, 0,
+            WSB_RUN(decode_self_attention(nullptr, &part, d, m->k_cache + l * cache_l, m->v_cache + l * cache_l, tmax, m->step, 0,
                                           fin, m->datt, B, H, s));
         }
         WSB_RUN(skinny_linear(m, m->datt, e.so_w, e.so_b, B, d, d, 0, nullptr, m->dx, e.ln2_g, e.ln2_b, m->dxn, s));
-        WSB_RUN(skinny_linear(m, m->dxn, e.cq_w, e.cq_b, B, d, d, 0, m->dq, nullptr, nullptr, nullptr, nullptr, s));
+        WSB_RUN(skinny_linear(m, m->dxn, e.cq_w, e.cq_b, B, d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, &part));
         {
             ProfScope ps(PROF_DEC_CROSS_ATTN, 4.0 * B * H * T * 64.0, s);   // bytes: K and V blocks, bf16
-            WSB_RUN(decode_cross_attention(m->dq, d, m->cross_kv, l, L, T, fin, m->datt, B, H, s));
+            WSB_RUN(decode_cross_attention(nullptr, &part, d, m->cross_kv, l, L, T, fin, m->datt, B, H, s));
         }
         WSB_RUN(skinny_linear(m, m->datt, e.co_w, e.co_b, B, d, d, 0, nullptr, m->dx, e.ln3_g, e.ln3_b, m->dxn, s));
         WSB_RUN(skinny_linear(m, m->dxn, e.fc1_w, e.fc1_b, B, F, d, 1, m->dff, nullptr, nullptr, nullptr, nullptr, s));
@@ -440,6 +455,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     WSB_REQUIRE(max_length > prompt_len && max_length <= c.max_target_positions, "max_length in (prompt_len, max_target_positions]");
     const int d = c.d_model, L = c.n_layers, T = m->T, rows = B * T;
     const int max_new = max_length - prompt_len;
+    m->use_pdl = (flags & 2) != 0;                      // bit1: programmatic dependent launch (measured slower: off)
     // cross-attention K/V of every decoder layer in one GEMM, scattered head-major:
     // cross_kv[b][layer][k|v][head][t][64]   (HF modeling_whisper.py:326-336, computed once and cached)
     {

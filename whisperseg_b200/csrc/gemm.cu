@@ -104,6 +104,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (descriptor prefetch, barrier init, TMEM allocation) overlapped the previous kernel
+    pdl_wait();
+    pdl_launch_dependents();
 
     const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
     const int k_blocks = p.K / kBK;
@@ -454,8 +457,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.split_stride = a.split_stride;
     const int total = p.m_tiles * p.n_tiles * p.splits;
     const int grid = std::min(total, num_sms);
-    gemm_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
-    WSB_CHECK_CUDA(cudaGetLastError());
+    WSB_CHECK_CUDA(launch_kernel(gemm_kernel<BN, EPI>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmB, p));
     count_launch();
     return 0;
 }

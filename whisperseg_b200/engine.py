@@ -1,6 +1,7 @@
 """Thin Python driver over the C ABI: owns device tensors (torch is used for memory and streams
 only) and calls libwsb for every piece of arithmetic."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -115,7 +116,8 @@ class Engine:
         with torch.cuda.device(self.device):
             self._enter()
             _lib.check(self.lib.wsb_generate(self.handle, batch, prompt, len(prompt_ids), eos_id, pad_id, max_length,
-                                             _ptr(forced), _ptr(tokens), ctypes.byref(n_steps), 1 if use_graph else 0,
+                                             _ptr(forced), _ptr(tokens), ctypes.byref(n_steps),
+                                             (1 if use_graph else 0) | (2 if os.environ.get("WSB_PDL") else 0),
                                              ctypes.c_void_p(self.stream.cuda_stream)), "wsb_generate")
             self._exit()
         return tokens, n_steps.value
