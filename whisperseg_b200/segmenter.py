@@ -167,6 +167,63 @@ class SegmenterBase:
                                            eps, time_per_frame_for_voting, consolidation_method)
         return pp.correct_fft_blur_and_dedupe(prediction, sr, get_n_fft_given_sr(sr))
 
+    @torch.no_grad()
+    def segment_many(self, audios, sr, min_frequency=None, spec_time_step=None, min_segment_length=None, eps=None,
+                     time_per_frame_for_voting=None, consolidation_method="clustering", max_length=448, num_trials=1,
+                     status_monitor=None):
+        """Folder mode (reference scripts/segment.py:39-56 loops over files and calls segment() on each, so a
+        0.5 s clip runs at batch size 1).  Here the windows of ALL clips are flattened into one list: one H2D
+        copy of the concatenated samples, one log-mel launch (per-window [lo, hi) bounds keep clips from
+        leaking into each other), encoder/decoder batches filled across clip boundaries, then the token
+        streams are regrouped per clip and post-processed exactly like segment().  Returns a list of
+        predictions, one per clip, identical to per-clip segment() calls."""
+        if min_frequency is None:
+            min_frequency = self.default_segmentation_config.get("min_frequency", 0)
+        if spec_time_step is None:
+            spec_time_step = self.default_segmentation_config.get("spec_time_step", 0.0025)
+        ratio = pp.RATIO_DECODING_TIME_STEP_TO_SPEC_TIME_STEP
+        if min_segment_length is None:
+            min_segment_length = spec_time_step * ratio
+        if eps is None:
+            eps = spec_time_step * ratio * 4
+        if time_per_frame_for_voting is None:
+            time_per_frame_for_voting = spec_time_step
+        plan = FrontendPlan(sr, spec_time_step, min_frequency, total_spec_columns=self.total_spec_columns)
+        eng = self.engines[0]
+        pieces, descs, owners, per_clip_windows = [], [], [], []
+        base = 0
+        for ci, a in enumerate(audios):
+            a = np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+            wins = plan.windows(len(a), num_trials)
+            per_clip_windows.append(wins)
+            for w in wins:
+                descs.append([base + w.start, base, base + len(a)])
+                owners.append(ci)
+            pieces.append(a)
+            pad = (-len(a)) % 4                          # keep every clip 16-byte aligned in the device buffer
+            if pad:
+                pieces.append(np.zeros(pad, dtype=np.float32))
+            base += len(a) + pad
+        if not descs:
+            return []
+        audio_dev = eng.upload_audio(np.concatenate(pieces) if pieces else np.zeros(0, np.float32))
+        desc_dev = torch.from_numpy(np.asarray(descs, dtype=np.int64)).to(eng.device)
+        feats = eng.features_device(plan, audio_dev, desc_dev, len(descs))
+        self.last_stats = {"n_windows": len(descs)}
+        outs = {}
+        self._generate_on(eng, feats, max_length, status_monitor, outs, 0)
+        texts = outs[0]
+        results, pos = [], 0
+        n_fft = get_n_fft_given_sr(sr)
+        for ci, a in enumerate(audios):
+            wins = per_clip_windows[ci]
+            clip_texts = texts[pos:pos + len(wins)]
+            pos += len(wins)
+            pred = self.parse_generation(clip_texts, [w.as_tuple() for w in wins], min_segment_length, len(a) / sr,
+                                         spec_time_step, num_trials, eps, time_per_frame_for_voting, consolidation_method)
+            results.append(pp.correct_fft_blur_and_dedupe(pred, sr, n_fft))
+        return results
+
     # ------------------------------------------------------------------ scoring (model.py:474-569)
     def compute_syllable_score(self, prediction_on_offset_list, label_on_offset_list, tolerance):
         return pp.compute_syllable_score(prediction_on_offset_list, label_on_offset_list, tolerance)
