@@ -3,7 +3,7 @@
 // Replaces HF WhisperAttention.forward for the encoder (modeling_whisper.py:310-357): softmax(q k^T) v
 // with q already scaled (the 1/sqrt(64) factor is folded into the q projection weights at load time).
 //
-// One CTA per (128-query tile, head, window).  Q, K and V tiles are TMA-loaded straight out of the
+// One CTA per (head, window), looping over the 128-query tiles.  Q, K and V are TMA-loaded straight out of the
 // packed [B*T, 3d] QKV activation (128-byte swizzle; keys beyond T are zero-filled by TMA and masked).
 //   S = Q K^T      : 2 x (M=128, N=256, K=64) tcgen05.mma into all 512 TMEM columns (fp32)
 //   softmax        : thread r owns TMEM lane r = query row r: pass 1 row max, pass 2 exp2 + row sum,
@@ -17,35 +17,44 @@
 
 namespace wsb {
 
-constexpr int kAttThreads = 128;
-constexpr int kAttQ = 128;          // query rows per CTA
+constexpr int kAttThreads = 512;    // four warps per TMEM lane quarter: each owns a quarter of the key columns
+constexpr int kAttQ = 128;          // query rows per tile
 constexpr int kAttKeys = 512;       // padded key count
 constexpr int kHd = 64;
-constexpr int kAttSmem = (kAttQ * kHd + 2 * kAttKeys * kHd + 2 * kAttQ * kHd) * 2 + 1024 + 64;
+constexpr int kAttChunk = 128;      // keys per P tile / PV MMA group
+constexpr int kAttSmem = (kAttQ * kHd + 2 * kAttKeys * kHd + 2 * kAttQ * kAttChunk) * 2 + 1024 + 128;
 
+// One CTA per (head, window): K and V are loaded once and shared by all query tiles; Q tiles are
+// double-buffered; TMEM (512 columns) is allocated once.
 __global__ void __launch_bounds__(kAttThreads, 1)
 encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                          __nv_bfloat16* __restrict__ out, int T, int d) {
     extern __shared__ unsigned char att_smem_raw[];
     unsigned char* smem = att_smem_raw + ((1024u - (smem_u32(att_smem_raw) & 1023u)) & 1023u);
-    unsigned char* sQ = smem;                                   // 16 KB
+    unsigned char* sQ = smem;                                   // 16 KB (reloaded as soon as S = QK^T has completed)
     unsigned char* sK = sQ + kAttQ * kHd * 2;                   // 64 KB
     unsigned char* sV = sK + kAttKeys * kHd * 2;                // 64 KB
-    unsigned char* sP = sV + kAttKeys * kHd * 2;                // 2 x 16 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kAttQ * kHd * 2);
-    uint64_t* bar_load = bars;
-    uint64_t* bar_s = bars + 1;
-    uint64_t* bar_p = bars + 2;                                 // [2] P buffer consumed by the tensor core
-    uint64_t* bar_o = bars + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    unsigned char* sP = sV + kAttKeys * kHd * 2;                // 2 x 32 KB (each: two 128x64 swizzled sub-tiles)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kAttQ * kAttChunk * 2);
+    uint64_t* bar_kv = bars;
+    uint64_t* bar_q = bars + 1;                                 // (+1 spare)
+    uint64_t* bar_s = bars + 3;
+    uint64_t* bar_p = bars + 4;                                 // [2] P buffer consumed by the tensor core
+    uint64_t* bar_o = bars + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int quarter = warp & 3, colgrp = warp >> 2;   // TMEM lanes 32*quarter.., key-column group (0..3)
+    __shared__ float s_xchg[4][kAttQ];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int n_qt = (T + kAttQ - 1) / kAttQ;
 
     if (tid == 0) {
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_kv);
-        mbar_init(bar_load, 1);
+        mbar_init(bar_kv, 1);
+        mbar_init(&bar_q[0], 1);
+        mbar_init(&bar_q[1], 1);
         mbar_init(bar_s, 1);
         mbar_init(&bar_p[0], 1);
         mbar_init(&bar_p[1], 1);
@@ -59,119 +68,153 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     const uint32_t tmem = *tmem_slot;
 
     if (tid == 0) {
-        mbar_arrive_expect_tx(bar_load, (kAttQ + 2 * kAttKeys) * kHd * 2);
-        tma_load_3d(sQ, &tm_q, bar_load, h * kHd, qt * kAttQ, b);
-        tma_load_3d(sK, &tm_kv, bar_load, d + h * kHd, 0, b);
-        tma_load_3d(sK + 256 * kHd * 2, &tm_kv, bar_load, d + h * kHd, 256, b);
-        tma_load_3d(sV, &tm_kv, bar_load, 2 * d + h * kHd, 0, b);
-        tma_load_3d(sV + 256 * kHd * 2, &tm_kv, bar_load, 2 * d + h * kHd, 256, b);
-        mbar_wait(bar_load, 0);
-        tc_fence_after();
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256, 0, 0);
-        const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + half * 256 * kHd * 2));
-#pragma unroll
-            for (int k = 0; k < kHd / 16; ++k)
-                umma_bf16_ss(tmem + half * 256, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-        }
-        umma_commit(bar_s);
+        mbar_arrive_expect_tx(bar_kv, 2 * kAttKeys * kHd * 2);
+        tma_load_3d(sK, &tm_kv, bar_kv, d + h * kHd, 0, b);
+        tma_load_3d(sK + 256 * kHd * 2, &tm_kv, bar_kv, d + h * kHd, 256, b);
+        tma_load_3d(sV, &tm_kv, bar_kv, 2 * d + h * kHd, 0, b);
+        tma_load_3d(sV + 256 * kHd * 2, &tm_kv, bar_kv, 2 * d + h * kHd, 256, b);
+        mbar_arrive_expect_tx(bar_q, kAttQ * kHd * 2);
+        tma_load_3d(sQ, &tm_q, bar_q, h * kHd, 0, b);
     }
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
 
-    const uint32_t lane_base = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     constexpr float kLog2e = 1.4426950408889634f;
+    const int row = tid & (kAttQ - 1);                     // query row within the tile == TMEM lane
 
-    // pass 1: row max over the T valid keys
-    float rmax = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < kAttKeys / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(lane_base + c * 32, r);
-        tmem_ld_wait();
-        const int n0 = c * 32;
+    for (int qt = 0; qt < n_qt; ++qt) {
+        if (tid == 0) {
+            if (qt == 0) mbar_wait(bar_kv, 0);
+            mbar_wait(bar_q, qt & 1);
+            tc_fence_after();
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256, 0, 0);
+            const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (n0 + i < T) rmax = fmaxf(rmax, __uint_as_float(r[i]));
-    }
-    const float mscaled = rmax * kLog2e;
-
-    // pass 2: P chunks + PV MMAs
-    float rsum = 0.0f;
-    const int row = tid;                                   // query row within the tile == TMEM lane
-#pragma unroll 1
-    for (int c = 0; c < kAttKeys / 64; ++c) {
-        const int buf = c & 1;
-        if (c >= 2) mbar_wait(&bar_p[buf], ((c >> 1) - 1) & 1);
-        unsigned char* pbuf = sP + buf * kAttQ * kHd * 2 + row * 128;
+            for (int half = 0; half < 2; ++half) {
+                const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + half * 256 * kHd * 2));
 #pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-            uint32_t r[32];
-            tmem_ld_32x32(lane_base + c * 64 + hlf * 32, r);
-            tmem_ld_wait();
-            const int n0 = c * 64 + hlf * 32;
-            float pv[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float e = (n0 + i < T) ? exp2f(fmaf(__uint_as_float(r[i]), kLog2e, -mscaled)) : 0.0f;
-                const float eb = __bfloat162float(__float2bfloat16(e));
-                pv[i] = eb;
-                rsum += eb;
+                for (int k = 0; k < kHd / 16; ++k)
+                    umma_bf16_ss(tmem + half * 256, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
             }
+            umma_commit(bar_s);
+        }
+        mbar_wait(bar_s, qt & 1);
+        tc_fence_after();
+        if (tid == 0 && qt + 1 < n_qt) {                   // S is in TMEM: the Q buffer is free, prefetch the next tile
+            mbar_arrive_expect_tx(bar_q, kAttQ * kHd * 2);
+            tma_load_3d(sQ, &tm_q, bar_q, h * kHd, (qt + 1) * kAttQ, b);
+        }
+
+        // pass 1: row max over the T valid keys (each warp of the pair scans its 256-column half)
+        float rmax = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < kAttKeys / 128; ++c) {
+            uint32_t r[32];
+            const int n0 = colgrp * 128 + c * 32;
+            tmem_ld_32x32(lane_base + n0, r);
+            tmem_ld_wait();
+            if (n0 + 32 <= T) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {                  // four 16-byte chunks of this 32-key half
-                uint4 pk;
-                pk.x = pack_bf16x2(pv[8 * j + 0], pv[8 * j + 1]);
-                pk.y = pack_bf16x2(pv[8 * j + 2], pv[8 * j + 3]);
-                pk.z = pack_bf16x2(pv[8 * j + 4], pv[8 * j + 5]);
-                pk.w = pack_bf16x2(pv[8 * j + 6], pv[8 * j + 7]);
-                const int chunk = hlf * 4 + j;             // 16-byte chunk index within the 128-byte row
-                *reinterpret_cast<uint4*>(pbuf + ((chunk ^ (row & 7)) << 4)) = pk;
+                for (int i = 0; i < 32; ++i) rmax = fmaxf(rmax, __uint_as_float(r[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (n0 + i < T) rmax = fmaxf(rmax, __uint_as_float(r[i]));
             }
         }
-        fence_proxy_async_smem();                          // generic-proxy smem writes -> visible to the MMA
+        s_xchg[colgrp][row] = rmax;
+        __syncthreads();
+        rmax = fmaxf(fmaxf(s_xchg[0][row], s_xchg[1][row]), fmaxf(s_xchg[2][row], s_xchg[3][row]));
+        const float mscaled = rmax * kLog2e;
+
+        // pass 2: P chunks + PV MMAs
+        float rsum = 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < kAttKeys / kAttChunk; ++c) {
+            const int buf = c & 1;
+            const int use = qt * (kAttKeys / kAttChunk / 2) + (c >> 1);  // how many times this buffer was used before
+            if (use > 0) mbar_wait(&bar_p[buf], (use - 1) & 1);
+            // this warp's 32 of the chunk's 128 keys: sub-tile (64 keys) colgrp>>1, 32-key half colgrp&1
+            unsigned char* pbuf = sP + buf * kAttQ * kAttChunk * 2 + (colgrp >> 1) * kAttQ * kHd * 2 + row * 128;
+            {
+                const int hlf = colgrp & 1;
+                uint32_t r[32];
+                tmem_ld_32x32(lane_base + c * kAttChunk + colgrp * 32, r);
+                tmem_ld_wait();
+                const int n0 = c * kAttChunk + colgrp * 32;
+                float pv[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(__uint_as_float(r[i]), kLog2e, -mscaled)));
+                    pv[i] = e;
+                }
+                if (n0 + 32 > T) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (n0 + i >= T) pv[i] = 0.0f;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) rsum += pv[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                  // four 16-byte chunks of this 32-key half
+                    uint4 pk;
+                    pk.x = pack_bf16x2(pv[8 * j + 0], pv[8 * j + 1]);
+                    pk.y = pack_bf16x2(pv[8 * j + 2], pv[8 * j + 3]);
+                    pk.z = pack_bf16x2(pv[8 * j + 4], pv[8 * j + 5]);
+                    pk.w = pack_bf16x2(pv[8 * j + 6], pv[8 * j + 7]);
+                    const int chunk = hlf * 4 + j;             // 16-byte chunk index within the 128-byte row
+                    *reinterpret_cast<uint4*>(pbuf + ((chunk ^ (row & 7)) << 4)) = pk;
+                }
+            }
+            fence_proxy_async_smem();                          // generic-proxy smem writes -> visible to the MMA
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);     // B (= V) is MN-major
+                const uint64_t dv = umma_desc_mn_sw128(smem_u32(sV + c * kAttChunk * kHd * 2));
+#pragma unroll
+                for (int k = 0; k < kAttChunk / 16; ++k) {     // 16 keys per MMA: P advances 32 B (next sub-tile after
+                                                               // 64 keys), V advances 16 rows = 2048 B
+                    const uint64_t dp = umma_desc_k_sw128(smem_u32(sP + buf * kAttQ * kAttChunk * 2 + (k >> 2) * kAttQ * kHd * 2));
+                    umma_bf16_ss(tmem, dp + 2 * (k & 3), dv + ((16 * kHd * 2) >> 4) * k, idesc_o, (c > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&bar_p[buf]);
+                if (c == kAttKeys / kAttChunk - 1) umma_commit(bar_o);
+            }
+        }
+        mbar_wait(bar_o, qt & 1);
+        tc_fence_after();
+
+        // epilogue: O / rowsum (row sums of the two column halves are combined through shared memory)
+        __syncthreads();                                       // s_xchg was last read right after pass 1
+        s_xchg[colgrp][row] = rsum;
+        __syncthreads();
+        const int q_row = qt * kAttQ + row;
+        const float inv = 1.0f / ((s_xchg[0][row] + s_xchg[1][row]) + (s_xchg[2][row] + s_xchg[3][row]));
+        if (colgrp < 2) {
+            const int hlf = colgrp;                            // 32 of the 64 output dims (warp groups 0 and 1)
+            uint32_t r[32];
+            tmem_ld_32x32(lane_base + hlf * 32, r);
+            tmem_ld_wait();
+            if (q_row < T) {
+                __nv_bfloat16* o = out + (static_cast<size_t>(b) * T + q_row) * d + h * kHd + hlf * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 pk;
+                    pk.x = pack_bf16x2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+                    pk.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
+                    pk.z = pack_bf16x2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
+                    pk.w = pack_bf16x2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
+                    *reinterpret_cast<uint4*>(o + i) = pk;
+                }
+            }
+        }
+        // the next tile's S MMA overwrites the TMEM columns O was just read from
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);     // B (= V) is MN-major
-            const uint64_t dp = umma_desc_k_sw128(smem_u32(sP + buf * kAttQ * kHd * 2));
-            const uint64_t dv = umma_desc_mn_sw128(smem_u32(sV + c * 64 * kHd * 2));
-#pragma unroll
-            for (int k = 0; k < 4; ++k)                    // 16 keys per MMA: P advances 32 B, V advances 16 rows
-                umma_bf16_ss(tmem, dp + 2 * k, dv + ((16 * kHd * 2) >> 4) * k, idesc_o, (c > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&bar_p[buf]);
-            if (c == kAttKeys / 64 - 1) umma_commit(bar_o);
-        }
     }
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-
-    // epilogue: O / rowsum
-    const int q_row = qt * kAttQ + row;
-    const float inv = 1.0f / rsum;
-#pragma unroll
-    for (int hlf = 0; hlf < 2; ++hlf) {
-        uint32_t r[32];
-        tmem_ld_32x32(lane_base + hlf * 32, r);
-        tmem_ld_wait();
-        if (q_row < T) {
-            __nv_bfloat16* o = out + (static_cast<size_t>(b) * T + q_row) * d + h * kHd + hlf * 32;
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                uint4 pk;
-                pk.x = pack_bf16x2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
-                pk.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
-                pk.z = pack_bf16x2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
-                pk.w = pack_bf16x2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
-                *reinterpret_cast<uint4*>(o + i) = pk;
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
@@ -193,7 +236,7 @@ int encoder_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T
     if (rc) return rc;
     rc = make_tmap_bf16(&tm_kv, qkv, 3, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    dim3 grid(ceil_div(T, kAttQ), n_heads, B);
+    dim3 grid(n_heads, B);
     encoder_attention_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(tm_q, tm_kv, out, T, d);
     WSB_CHECK_CUDA(cudaGetLastError());
     count_launch();
