@@ -88,11 +88,13 @@ constexpr int kRedMaxSplits = 16;
 __global__ void __launch_bounds__(kRedThreads) splitk_reduce_bf16_kernel(const float* __restrict__ partial, int splits,
                                                                          long long split_stride, int N,
                                                                          const float* __restrict__ bias, int gelu,
-                                                                         __nv_bfloat16* __restrict__ out) {
+                                                                         __nv_bfloat16* __restrict__ out,
+                                                                         const unsigned char* __restrict__ row_skip) {
     const int row = blockIdx.x;
     const int nvec = N >> 2;
     pdl_wait();
     pdl_launch_dependents();
+    if (row_skip && row_skip[row]) return;
     const float4* base = reinterpret_cast<const float4*>(partial + static_cast<long long>(row) * N);
     const long long sv = split_stride >> 2;
     for (int j = threadIdx.x; j < nvec; j += kRedThreads) {
@@ -124,11 +126,13 @@ __global__ void __launch_bounds__(kRedThreads) splitk_reduce_resid_ln_kernel(con
                                                                              float* __restrict__ x,
                                                                              const float* __restrict__ gamma,
                                                                              const float* __restrict__ beta,
-                                                                             __nv_bfloat16* __restrict__ xn) {
+                                                                             __nv_bfloat16* __restrict__ xn,
+                                                                             const unsigned char* __restrict__ row_skip) {
     __shared__ float s_red[2][kRedThreads / 32];
     pdl_wait();
     pdl_launch_dependents();
     const int row = blockIdx.x;
+    if (row_skip && row_skip[row]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nvec = N >> 2;
     const float4* base = reinterpret_cast<const float4*>(partial + static_cast<long long>(row) * N);
@@ -198,22 +202,23 @@ __global__ void __launch_bounds__(kRedThreads) splitk_reduce_resid_ln_kernel(con
 }
 
 int splitk_reduce_bf16(const float* partial, int splits, int64_t split_stride, int M, int N, const float* bias, int gelu,
-                       __nv_bfloat16* out, cudaStream_t stream) {
+                       __nv_bfloat16* out, const unsigned char* row_skip, cudaStream_t stream) {
     WSB_REQUIRE(N % 4 == 0 && split_stride % 4 == 0 && splits <= kRedMaxSplits, "split-K reduce shape");
     if (M <= 0) return 0;
     WSB_CHECK_CUDA(launch_kernel(splitk_reduce_bf16_kernel, dim3(M), dim3(kRedThreads), 0, stream, partial, splits,
-                                 static_cast<long long>(split_stride), N, bias, gelu, out));
+                                 static_cast<long long>(split_stride), N, bias, gelu, out, row_skip));
     count_launch();
     return 0;
 }
 
 int splitk_reduce_resid_ln(const float* partial, int splits, int64_t split_stride, int M, int N, const float* bias,
-                           float* x, const float* gamma, const float* beta, __nv_bfloat16* xn, cudaStream_t stream) {
+                           float* x, const float* gamma, const float* beta, __nv_bfloat16* xn,
+                           const unsigned char* row_skip, cudaStream_t stream) {
     WSB_REQUIRE(N % 4 == 0 && N <= kRedLnVec * kRedThreads * 4 && split_stride % 4 == 0 && splits <= kRedMaxSplits,
                 "split-K reduce shape (row width <= 1536)");
     if (M <= 0) return 0;
     WSB_CHECK_CUDA(launch_kernel(splitk_reduce_resid_ln_kernel, dim3(M), dim3(kRedThreads), 0, stream, partial, splits,
-                                 static_cast<long long>(split_stride), N, bias, x, gamma, beta, xn));
+                                 static_cast<long long>(split_stride), N, bias, x, gamma, beta, xn, row_skip));
     count_launch();
     return 0;
 }

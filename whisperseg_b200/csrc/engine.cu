@@ -351,7 +351,7 @@ static int encode(Model* m, const float* feats, int B, float* hidden_f32, cudaSt
 //   mode 0: out_bf16 = act(sum + bias)         mode 1: x += sum + bias; xn = LayerNorm(x) (if gamma)
 static int skinny_linear(Model* m, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, int B, int N, int K,
                          int gelu, __nv_bfloat16* out_bf16, float* x, const float* gamma, const float* beta,
-                         __nv_bfloat16* xn, cudaStream_t s, SplitkInput* planes_only = nullptr) {
+                         __nv_bfloat16* xn, cudaStream_t s, const unsigned char* row_skip, SplitkInput* planes_only = nullptr) {
     int bn = 128, splits = 1;
     gemm_pick_skinny(B, N, K, &bn, &splits);
     const int64_t plane = static_cast<int64_t>(B) * N;
@@ -371,6 +371,7 @@ static int skinny_linear(Model* m, const __nv_bfloat16* A, const __nv_bfloat16* 
         g.block_n = bn;
         g.splits = splits;
         g.split_stride = plane;
+        g.row_skip = row_skip;
         WSB_RUN(gemm_bf16(g, s));
     }
     const int eff = gemm_effective_splits(K, splits);
@@ -382,8 +383,8 @@ static int skinny_linear(Model* m, const __nv_bfloat16* A, const __nv_bfloat16* 
         return 0;
     }
     ProfScope ps(PROF_DEC_LN, 4.0 * B * N * (splits + 1), s);
-    if (out_bf16) return splitk_reduce_bf16(m->dpart, eff, plane, B, N, bias, gelu, out_bf16, s);
-    return splitk_reduce_resid_ln(m->dpart, eff, plane, B, N, bias, x, gamma, beta, xn, s);
+    if (out_bf16) return splitk_reduce_bf16(m->dpart, eff, plane, B, N, bias, gelu, out_bf16, row_skip, s);
+    return splitk_reduce_resid_ln(m->dpart, eff, plane, B, N, bias, x, gamma, beta, xn, row_skip, s);
 }
 
 // one decoder position for all rows.  with_logits: project + arg-max + finalize; else prefill advance.
@@ -409,21 +410,21 @@ static int decode_step(Model* m, int B, bool with_logits, bool first_generated, 
         const float* next_g = (l + 1 < L) ? m->dec[l + 1].ln1_g : m->dec_ln_g;
         const float* next_b = (l + 1 < L) ? m->dec[l + 1].ln1_b : m->dec_ln_b;
         SplitkInput part;
-        WSB_RUN(skinny_linear(m, m->dxn, e.sqkv_w, e.sqkv_b, B, 3 * d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, &part));
+        WSB_RUN(skinny_linear(m, m->dxn, e.sqkv_w, e.sqkv_b, B, 3 * d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, fin, &part));
         {
             ProfScope ps(PROF_DEC_SELF_ATTN, 0.0, s);
             WSB_RUN(decode_self_attention(nullptr, &part, d, m->k_cache + l * cache_l, m->v_cache + l * cache_l, tmax, m->step, 0,
                                           fin, m->datt, B, H, s));
         }
-        WSB_RUN(skinny_linear(m, m->datt, e.so_w, e.so_b, B, d, d, 0, nullptr, m->dx, e.ln2_g, e.ln2_b, m->dxn, s));
-        WSB_RUN(skinny_linear(m, m->dxn, e.cq_w, e.cq_b, B, d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, &part));
+        WSB_RUN(skinny_linear(m, m->datt, e.so_w, e.so_b, B, d, d, 0, nullptr, m->dx, e.ln2_g, e.ln2_b, m->dxn, s, fin));
+        WSB_RUN(skinny_linear(m, m->dxn, e.cq_w, e.cq_b, B, d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, fin, &part));
         {
             ProfScope ps(PROF_DEC_CROSS_ATTN, 4.0 * B * H * T * 64.0, s);   // bytes: K and V blocks, bf16
             WSB_RUN(decode_cross_attention(nullptr, &part, d, m->cross_kv, l, L, T, fin, m->datt, B, H, s));
         }
-        WSB_RUN(skinny_linear(m, m->datt, e.co_w, e.co_b, B, d, d, 0, nullptr, m->dx, e.ln3_g, e.ln3_b, m->dxn, s));
-        WSB_RUN(skinny_linear(m, m->dxn, e.fc1_w, e.fc1_b, B, F, d, 1, m->dff, nullptr, nullptr, nullptr, nullptr, s));
-        WSB_RUN(skinny_linear(m, m->dff, e.fc2_w, e.fc2_b, B, d, F, 0, nullptr, m->dx, next_g, next_b, m->dxn, s));
+        WSB_RUN(skinny_linear(m, m->datt, e.co_w, e.co_b, B, d, d, 0, nullptr, m->dx, e.ln3_g, e.ln3_b, m->dxn, s, fin));
+        WSB_RUN(skinny_linear(m, m->dxn, e.fc1_w, e.fc1_b, B, F, d, 1, m->dff, nullptr, nullptr, nullptr, nullptr, s, fin));
+        WSB_RUN(skinny_linear(m, m->dff, e.fc2_w, e.fc2_b, B, d, F, 0, nullptr, m->dx, next_g, next_b, m->dxn, s, fin));
     }
     if (!with_logits) return prefill_advance(m->next_token, forced, forced_ld, m->prompt_dev, m->step, B, s);
     GemmArgs g;

@@ -48,6 +48,7 @@ struct GemmDev {
     int m_tiles, n_tiles;
     int splits, kb_per_split;      // split-K: tile space is m_tiles x n_tiles x splits, fp32 partial planes
     long long split_stride;        // elements between partial planes of the output
+    const unsigned char* row_skip; // optional [M]: rows flagged non-zero are not stored (finished decode rows)
 };
 
 template <int BN>
@@ -265,6 +266,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     } else if constexpr (EPI == EPI_F32 || EPI == EPI_F32_GELU_ROWVEC) {
                         float* o = reinterpret_cast<float*>(p.out) + sp * p.split_stride + grow0 * p.ldc + col;
+                        // finished decode rows: skip the partial-plane stores (lane rr holds row rr's flag)
+                        unsigned skip_mask = 0;
+                        if constexpr (EPI == EPI_F32) {
+                            if (p.row_skip)
+                                skip_mask = __ballot_sync(0xffffffffu, lane < nvalid && p.row_skip[grow0 + lane] != 0);
+                        }
                         int brow = 0;
                         if constexpr (EPI == EPI_F32_GELU_ROWVEC) brow = static_cast<int>(grow0 % p.rows_per_batch);
 #pragma unroll 8
@@ -276,7 +283,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 if (cvalid) v += __ldg(p.rowvec + static_cast<long long>(brow) * p.N + col);
                                 if (++brow == p.rows_per_batch) brow = 0;
                             }
-                            if (cvalid) o[static_cast<long long>(rr) * p.ldc] = v;
+                            if (cvalid && !((skip_mask >> rr) & 1u)) o[static_cast<long long>(rr) * p.ldc] = v;
                         }
                     } else {   // bf16 outputs: EPI_BF16, EPI_BF16_GELU, EPI_HEADMAJOR
                         long long hm_b = 0;
@@ -455,6 +462,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.kb_per_split = ceil_div(a.K / kBK, p.splits);
     p.splits = ceil_div(a.K / kBK, p.kb_per_split);          // drop empty trailing splits
     p.split_stride = a.split_stride;
+    p.row_skip = a.row_skip;
     const int total = p.m_tiles * p.n_tiles * p.splits;
     const int grid = std::min(total, num_sms);
     WSB_CHECK_CUDA(launch_kernel(gemm_kernel<BN, EPI>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmB, p));

@@ -24,7 +24,8 @@ namespace cg = cooperative_groups;
 
 namespace wsb {
 
-constexpr int kLogmelThreads = 256;
+constexpr int kLogmelThreads = 512;
+constexpr int kMaxBfly = 8;          // radix-4 butterflies a thread may hold per pass
 constexpr int kMels = 80;
 constexpr int kMaxCluster = 8;
 
@@ -33,8 +34,9 @@ struct LogmelPlan {
     int cluster, frames_per_cta, group_threads, n_groups;
     int span_floats, tile_stride;
     size_t smem_bytes;
+    bool smem_tables = false;
     float* hann = nullptr;          // [n_fft]
-    float2* tw = nullptr;           // [n_fft/2]  exp(-2 pi i j / n_fft)
+    float2* tw = nullptr;           // [3 n_fft/4]  exp(-2 pi i j / n_fft)
     int* mel_start = nullptr;       // [80]
     int* mel_cnt = nullptr;         // [80]
     int* mel_off = nullptr;         // [80]
@@ -54,42 +56,80 @@ struct LogmelParams {
     const float* mel_w;
     int n_fft, hop, clip_len, n_frames, n_cols, log2m;
     int frames_per_cta, group_threads, n_groups, span_floats, tile_stride;
+    int mel_nnz;
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-// exp(-2 pi i idx / n_fft) for idx in [0, n_fft) from the half table
-__device__ __forceinline__ float2 twiddle(const float2* __restrict__ tw, int idx, int m) {
-    float2 t = tw[idx >= m ? idx - m : idx];
-    return idx >= m ? make_float2(-t.x, -t.y) : t;
-}
+
+// Compile-time shape of the per-frame FFT: M = n_fft/2 complex points handled by a group of G threads
+// (a warp up to n_fft 1024; larger groups beyond), NB radix-4 butterflies per thread and pass.
+template <int LOG2M>
+struct FftCfg {
+    static constexpr int M = 1 << LOG2M;
+    static constexpr int G = LOG2M <= 9 ? 32 : (32 << (LOG2M - 9));
+    static constexpr int NB = M / (4 * G);
+    static constexpr int NGROUPS = kLogmelThreads / G;
+    static constexpr int GROUP_FLOATS = 3 * M + 4;          // M complex points + (M+4) floats of power spectrum
+    static constexpr int TW = 3 * M / 2;                    // twiddle table entries: exp(-2 pi i j / n_fft), j < 3 n_fft / 4
+};
 
 // barrier among the G threads that cooperate on one frame (a warp, or a named barrier per group), so
 // the frame groups of a CTA run their FFT passes independently of each other
-__device__ __forceinline__ void group_sync(int g, int G) {
-    if (G == 32) {
+template <int G>
+__device__ __forceinline__ void group_sync(int g) {
+    if constexpr (G == 32) {
         __syncwarp();
     } else {
-        asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(G) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(G) : "memory");
     }
 }
 
+// kSmemTables: Hann window, twiddles and the CSR mel bank are staged in shared memory (fits up to
+// n_fft 2048 for the usual hops); otherwise they are read through L1 from global memory.
+template <int LOG2M, bool kSmemTables>
 __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelParams p) {
+    using C = FftCfg<LOG2M>;
+    constexpr int M = C::M, G = C::G, NB = C::NB, N_FFT = 2 * C::M;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = static_cast<int>(cluster.block_rank());
     const int csize = static_cast<int>(cluster.num_blocks());
     const int w = blockIdx.x / csize;
     const int tid = threadIdx.x;
-    const int M = p.n_fft >> 1;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_samples = reinterpret_cast<float*>(smem_raw);                       // span_floats
-    float* s_tile = s_samples + p.span_floats;                                   // 80 * tile_stride
-    float2* s_tw = reinterpret_cast<float2*>(s_tile + kMels * p.tile_stride);    // M
-    float2* s_fft = s_tw + M;                                                    // n_groups * 2 * M
+    float* s_tile = s_samples + p.span_floats;                                   // 80 * tile_stride (+ pad to 4)
+    float* s_fft = s_tile + ((kMels * p.tile_stride + 3) & ~3);                  // NGROUPS * GROUP_FLOATS
+    float* s_tab = s_fft + C::NGROUPS * C::GROUP_FLOATS;                         // optional tables
     __shared__ float s_red[2][kLogmelThreads / 32];
     __shared__ float s_cluster_red[2];                                           // this CTA's {max, min}, read by peers
+    __shared__ int s_mel[3][kMels];                                              // CSR: first bin, count, weight offset
+
+    const float2* tw;
+    const float* hann;
+    const float* mel_w;
+    if constexpr (kSmemTables) {
+        float2* t = reinterpret_cast<float2*>(s_tab);
+        float* h = s_tab + 2 * C::TW;
+        float* mw = h + N_FFT;
+        for (int i = tid; i < C::TW; i += kLogmelThreads) t[i] = p.tw[i];
+        for (int i = tid; i < N_FFT; i += kLogmelThreads) h[i] = p.hann[i];
+        for (int i = tid; i < p.mel_nnz; i += kLogmelThreads) mw[i] = p.mel_w[i];
+        tw = t;
+        hann = h;
+        mel_w = mw;
+    } else {
+        tw = p.tw;
+        hann = p.hann;
+        mel_w = p.mel_w;
+    }
+    if (tid < kMels) {
+        s_mel[0][tid] = p.mel_start[tid];
+        s_mel[1][tid] = p.mel_cnt[tid];
+        s_mel[2][tid] = p.mel_off[tid];
+    }
 
     const int f0 = rank * p.frames_per_cta;
     const int f1 = min(p.n_frames, f0 + p.frames_per_cta);
@@ -99,10 +139,9 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
     const long long lo = p.win[3 * w + 1];
     const long long hi = p.win[3 * w + 2];
 
-    // ---- stage twiddles and this CTA's sample span -------------------------------------------
-    for (int i = tid; i < M; i += kLogmelThreads) s_tw[i] = p.tw[i];
+    // ---- stage this CTA's sample span ---------------------------------------------------------
     if (nf > 0) {
-        const int span = (nf - 1) * p.hop + p.n_fft;
+        const int span = (nf - 1) * p.hop + N_FFT;
         const int p0 = f0 * p.hop - M;                    // padded-clip coordinate of s_samples[0]
         const int jlo = max(0, -p0);                      // first j with clip index >= 0
         const int jhi = min(span, p.clip_len - p0);       // first j with clip index >= clip_len
@@ -119,7 +158,7 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
         const long long abase = start + p0;
         const long long a_first = abase + jlo, a_last = abase + jhi;            // [a_first, a_last)
         const long long v_lo = max(a_first, lo), v_hi = min(a_last, hi);        // fully-valid range
-        long long a4 = (a_first >= 0 ? (a_first & ~3LL) : -((-a_first + 3) & ~3LL)) + 4LL * tid;
+        long long a4 = (a_first & ~3LL) + 4LL * tid;
         for (; a4 < a_last; a4 += 4LL * kLogmelThreads) {
             if (a4 >= v_lo && a4 + 4 <= v_hi) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(p.audio + a4));
@@ -141,108 +180,129 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
     __syncthreads();
 
     // ---- per-frame FFT + mel + log ---------------------------------------------------------------
-    const int G = p.group_threads;
     const int g = tid / G;
     const int gt = tid - g * G;
-    float2* bufA = s_fft + static_cast<size_t>(g) * 2 * M;
-    float2* bufB = bufA + M;
+    float2* buf = reinterpret_cast<float2*>(s_fft + g * C::GROUP_FLOATS);
+    float* power = reinterpret_cast<float*>(buf + M);
     float vmax = -INFINITY, vmin = INFINITY;
-    const int iters = (nf + p.n_groups - 1) / p.n_groups;
+    const int iters = (nf + C::NGROUPS - 1) / C::NGROUPS;
+    constexpr int Q = M / 4;
 
+#pragma unroll 1
     for (int it = 0; it < iters; ++it) {
-        const int fl = it * p.n_groups + g;              // frame index local to this CTA
+        const int fl = it * C::NGROUPS + g;              // frame index local to this CTA
         const bool active = fl < nf;
         // window + pack: z[j] = x[2j] w[2j] + i x[2j+1] w[2j+1]
         if (active) {
             const float* x = s_samples + fl * p.hop;
-            for (int j = gt; j < M; j += G) {
-                const float2 h = __ldg(reinterpret_cast<const float2*>(p.hann) + j);
-                bufA[j] = make_float2(x[2 * j] * h.x, x[2 * j + 1] * h.y);
+#pragma unroll
+            for (int i = 0; i < M / G; ++i) {
+                const int j = gt + i * G;
+                const float2 h = reinterpret_cast<const float2*>(hann)[j];
+                buf[j] = make_float2(x[2 * j] * h.x, x[2 * j + 1] * h.y);
             }
         }
-        group_sync(g, G);
-        float2* src = bufA;
-        float2* dst = bufB;
-        int ns = 1, lg = 0;
-        if (p.log2m & 1) {                               // one radix-2 pass first when log2(M) is odd
+        group_sync<G>(g);
+        // In-place Stockham passes: every thread pulls the inputs of all its butterflies into registers,
+        // the group synchronises, then the outputs are scattered -- one M-point buffer per frame group.
+        if constexpr (LOG2M & 1) {                       // one radix-2 pass first when log2(M) is odd
+            float2 u[2 * NB][2];
             if (active) {
-                const int half = M >> 1;
-                for (int j = gt; j < half; j += G) {
-                    const float2 u0 = src[j], u1 = src[j + half];
-                    dst[2 * j] = make_float2(u0.x + u1.x, u0.y + u1.y);
-                    dst[2 * j + 1] = make_float2(u0.x - u1.x, u0.y - u1.y);
+#pragma unroll
+                for (int i = 0; i < 2 * NB; ++i) {
+                    const int j = gt + i * G;
+                    u[i][0] = buf[j];
+                    u[i][1] = buf[j + M / 2];
                 }
             }
-            group_sync(g, G);
-            float2* t = src; src = dst; dst = t;
-            ns = 2; lg = 1;
-        }
-        for (; lg < p.log2m; lg += 2, ns <<= 2) {        // radix-4 Stockham passes
+            group_sync<G>(g);
             if (active) {
-                const int quarter = M >> 2;
-                const int tw_stride = p.n_fft / (ns * 4);
-                for (int j = gt; j < quarter; j += G) {
+#pragma unroll
+                for (int i = 0; i < 2 * NB; ++i) {
+                    const int j = gt + i * G;
+                    buf[2 * j] = make_float2(u[i][0].x + u[i][1].x, u[i][0].y + u[i][1].y);
+                    buf[2 * j + 1] = make_float2(u[i][0].x - u[i][1].x, u[i][0].y - u[i][1].y);
+                }
+            }
+            group_sync<G>(g);
+        }
+#pragma unroll
+        for (int lg = (LOG2M & 1); lg < LOG2M; lg += 2) {      // radix-4 passes, ns = 2^lg
+            const int ns = 1 << lg;
+            const int tw_stride = N_FFT / (ns * 4);
+            float2 v[NB][4];
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int j = gt + i * G;
+                    v[i][0] = buf[j];
+                    v[i][1] = buf[j + Q];
+                    v[i][2] = buf[j + 2 * Q];
+                    v[i][3] = buf[j + 3 * Q];
+                }
+            }
+            group_sync<G>(g);
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int j = gt + i * G;
                     const int k = j & (ns - 1);
-                    float2 v0 = src[j];
-                    float2 v1 = src[j + quarter];
-                    float2 v2 = src[j + 2 * quarter];
-                    float2 v3 = src[j + 3 * quarter];
-                    if (k != 0) {
-                        v1 = cmul(v1, twiddle(s_tw, k * tw_stride, M));
-                        v2 = cmul(v2, twiddle(s_tw, 2 * k * tw_stride, M));
-                        v3 = cmul(v3, twiddle(s_tw, 3 * k * tw_stride, M));
+                    float2 v1 = v[i][1], v2 = v[i][2], v3 = v[i][3];
+                    if (lg > 0) {                              // ns == 1: all twiddles are 1
+                        v1 = cmul(v1, tw[k * tw_stride]);
+                        v2 = cmul(v2, tw[2 * k * tw_stride]);
+                        v3 = cmul(v3, tw[3 * k * tw_stride]);
                     }
+                    const float2 v0 = v[i][0];
                     const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
                     const float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
                     const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
                     const float2 a3 = make_float2(v1.y - v3.y, v3.x - v1.x);       // (v1 - v3) * (-i)
                     const int j0 = ((j - k) << 2) + k;
-                    dst[j0] = make_float2(a0.x + a2.x, a0.y + a2.y);
-                    dst[j0 + ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
-                    dst[j0 + 2 * ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
-                    dst[j0 + 3 * ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
+                    buf[j0] = make_float2(a0.x + a2.x, a0.y + a2.y);
+                    buf[j0 + ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
+                    buf[j0 + 2 * ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
+                    buf[j0 + 3 * ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
                 }
             }
-            group_sync(g, G);
-            float2* t = src; src = dst; dst = t;
+            group_sync<G>(g);
         }
-        // real-FFT untangle + power spectrum: P[k], k = 0..M, into dst (as floats)
-        float* power = reinterpret_cast<float*>(dst);
+        // real-FFT untangle + power spectrum: P[k], k = 0..M
         if (active) {
-            for (int k = gt; k <= M; k += G) {
-                const float2 zk = src[k & (M - 1)];
-                const float2 zm = src[(M - k) & (M - 1)];
-                const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-                const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));   // (zk - conj zm)/(2i)
-                const float2 t = cmul(o, twiddle(s_tw, k, M));
-                const float re = e.x + t.x, im = e.y + t.y;
-                power[k] = re * re + im * im;
+#pragma unroll
+            for (int i = 0; i <= M / G; ++i) {
+                const int k = gt + i * G;
+                if (i < M / G || k == M) {
+                    const float2 zk = buf[k & (M - 1)];
+                    const float2 zm = buf[(M - k) & (M - 1)];
+                    const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                    const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));   // (zk - conj zm)/(2i)
+                    const float2 t = cmul(o, tw[k]);
+                    const float re = e.x + t.x, im = e.y + t.y;
+                    power[k] = re * re + im * im;
+                }
             }
         }
-        group_sync(g, G);
-        // sparse mel: 8 lanes cooperate on one filter
+        group_sync<G>(g);
+        // sparse mel: each thread owns filters gt, gt+G, ... (<= 2 triangles per FFT bin, CSR rows)
         if (active) {
-            const int sub = gt >> 3, sl = gt & 7, nsub = G >> 3;
-            for (int m0 = 0; m0 < kMels; m0 += nsub) {
-                const int m = m0 + sub;
-                float acc = 0.0f;
-                if (m < kMels) {
-                    const int b0 = __ldg(p.mel_start + m), cnt = __ldg(p.mel_cnt + m);
-                    const float* wt = p.mel_w + __ldg(p.mel_off + m);
-                    for (int i = sl; i < cnt; i += 8) acc = fmaf(__ldg(wt + i), power[b0 + i], acc);
+            for (int m = gt; m < kMels; m += G) {
+                const int b0 = s_mel[0][m], cnt = s_mel[1][m];
+                const float* wt = mel_w + s_mel[2][m];
+                float acc0 = 0.0f, acc1 = 0.0f;
+                int i = 0;
+                for (; i + 1 < cnt; i += 2) {
+                    acc0 = fmaf(wt[i], power[b0 + i], acc0);
+                    acc1 = fmaf(wt[i + 1], power[b0 + i + 1], acc1);
                 }
-                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                if (m < kMels && sl == 0) {
-                    const float v = log10f(fmaxf(acc, 1e-10f));
-                    s_tile[m * p.tile_stride + fl] = v;
-                    vmax = fmaxf(vmax, v);
-                    if (f0 + fl < p.n_cols) vmin = fminf(vmin, v);
-                }
+                if (i < cnt) acc0 = fmaf(wt[i], power[b0 + i], acc0);
+                const float v = log10f(fmaxf(acc0 + acc1, 1e-10f));
+                s_tile[m * p.tile_stride + fl] = v;
+                vmax = fmaxf(vmax, v);
+                if (f0 + fl < p.n_cols) vmin = fminf(vmin, v);
             }
         }
-        group_sync(g, G);
+        group_sync<G>(g);
     }
 
     // ---- window-global max / min across the cluster ---------------------------------------------
@@ -295,6 +355,20 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
     }
 }
 
+typedef void (*LogmelKernelFn)(const LogmelParams);
+static LogmelKernelFn pick_logmel_kernel(int log2m, bool smem_tables) {
+    switch (log2m) {
+        case 7: return smem_tables ? logmel_kernel<7, true> : logmel_kernel<7, false>;
+        case 8: return smem_tables ? logmel_kernel<8, true> : logmel_kernel<8, false>;
+        case 9: return smem_tables ? logmel_kernel<9, true> : logmel_kernel<9, false>;
+        case 10: return smem_tables ? logmel_kernel<10, true> : logmel_kernel<10, false>;
+        case 11: return smem_tables ? logmel_kernel<11, true> : logmel_kernel<11, false>;
+        case 12: return smem_tables ? logmel_kernel<12, true> : logmel_kernel<12, false>;
+        default: return nullptr;
+    }
+}
+static int fft_group_threads(int log2m) { return log2m <= 9 ? 32 : (32 << (log2m - 9)); }
+
 // ------------------------------------------------------------------------------------------- host
 static int ilog2(int v) {
     int l = 0;
@@ -304,7 +378,7 @@ static int ilog2(int v) {
 
 int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float* mel_filters_host, int n_freq,
                        LogmelPlan** out) {
-    WSB_REQUIRE(n_fft >= 64 && (n_fft & (n_fft - 1)) == 0 && n_fft <= 8192, "n_fft must be a power of two in [64, 8192]");
+    WSB_REQUIRE(n_fft >= 256 && (n_fft & (n_fft - 1)) == 0 && n_fft <= 8192, "n_fft must be a power of two in [256, 8192]");
     WSB_REQUIRE(n_freq == n_fft / 2 + 1, "mel filter bank must have n_fft/2+1 rows");
     WSB_REQUIRE(hop >= 1 && clip_len > n_fft / 2 && n_cols >= 1, "bad hop / clip_len / n_cols");
     LogmelPlan* pl = new LogmelPlan();
@@ -324,29 +398,12 @@ int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float
     pl->frames_per_cta = std::max(1, ceil_div(std::max(pl->n_frames, 1), pl->cluster));
     pl->span_floats = ((pl->frames_per_cta - 1) * hop + n_fft + 3) & ~3;
     pl->tile_stride = pl->frames_per_cta | 1;
-    // as many independent frame groups as shared memory allows (a warp per frame when possible): the
-    // FFT passes of different frames then overlap instead of serialising on block-wide barriers
-    const size_t fixed_bytes = sizeof(float) * (static_cast<size_t>(pl->span_floats) + kMels * pl->tile_stride) +
-                               sizeof(float2) * static_cast<size_t>(M) + 2048;
-    pl->group_threads = 32;
-    while (pl->group_threads < kLogmelThreads &&
-           fixed_bytes + sizeof(float2) * 2 * M * (kLogmelThreads / pl->group_threads) > static_cast<size_t>(max_smem))
-        pl->group_threads *= 2;
-    pl->n_groups = kLogmelThreads / pl->group_threads;
-    pl->smem_bytes = sizeof(float) * (static_cast<size_t>(pl->span_floats) + kMels * pl->tile_stride) +
-                     sizeof(float2) * (static_cast<size_t>(M) + static_cast<size_t>(pl->n_groups) * 2 * M);
-    if (pl->smem_bytes + 1024 > static_cast<size_t>(max_smem)) {
-        set_last_error("log-mel plan needs " + std::to_string(pl->smem_bytes) + " B shared memory per CTA (limit " +
-                       std::to_string(max_smem) + "): hop/n_fft combination too large for an 8-CTA cluster");
-        delete pl;
-        return 3;
-    }
-
     std::vector<float> hann(n_fft);
-    std::vector<float2> tw(M);
+    const int n_tw = 3 * n_fft / 4;
+    std::vector<float2> tw(n_tw);
     const double two_pi = 6.283185307179586476925286766559;
     for (int i = 0; i < n_fft; ++i) hann[i] = static_cast<float>(0.5 - 0.5 * cos(two_pi * i / n_fft));
-    for (int i = 0; i < M; ++i)
+    for (int i = 0; i < n_tw; ++i)
         tw[i] = make_float2(static_cast<float>(cos(two_pi * i / n_fft)), static_cast<float>(-sin(two_pi * i / n_fft)));
     std::vector<int> st(kMels), cnt(kMels), off(kMels);
     std::vector<float> wts;
@@ -365,21 +422,37 @@ int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float
     pl->nnz = static_cast<int>(wts.size());
     if (wts.empty()) wts.push_back(0.0f);
     WSB_CHECK_CUDA(cudaMalloc(&pl->hann, sizeof(float) * n_fft));
-    WSB_CHECK_CUDA(cudaMalloc(&pl->tw, sizeof(float2) * M));
+    WSB_CHECK_CUDA(cudaMalloc(&pl->tw, sizeof(float2) * n_tw));
     WSB_CHECK_CUDA(cudaMalloc(&pl->mel_start, sizeof(int) * kMels));
     WSB_CHECK_CUDA(cudaMalloc(&pl->mel_cnt, sizeof(int) * kMels));
     WSB_CHECK_CUDA(cudaMalloc(&pl->mel_off, sizeof(int) * kMels));
     WSB_CHECK_CUDA(cudaMalloc(&pl->mel_w, sizeof(float) * wts.size()));
     WSB_CHECK_CUDA(cudaMemcpy(pl->hann, hann.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
-    WSB_CHECK_CUDA(cudaMemcpy(pl->tw, tw.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+    WSB_CHECK_CUDA(cudaMemcpy(pl->tw, tw.data(), sizeof(float2) * n_tw, cudaMemcpyHostToDevice));
     WSB_CHECK_CUDA(cudaMemcpy(pl->mel_start, st.data(), sizeof(int) * kMels, cudaMemcpyHostToDevice));
     WSB_CHECK_CUDA(cudaMemcpy(pl->mel_cnt, cnt.data(), sizeof(int) * kMels, cudaMemcpyHostToDevice));
     WSB_CHECK_CUDA(cudaMemcpy(pl->mel_off, off.data(), sizeof(int) * kMels, cudaMemcpyHostToDevice));
     WSB_CHECK_CUDA(cudaMemcpy(pl->mel_w, wts.data(), sizeof(float) * wts.size(), cudaMemcpyHostToDevice));
-    // plans with different shapes share the kernel: always opt in to the device maximum
+    // shared-memory budget: samples + tile + per-group FFT buffers (+ tables when they fit)
+    pl->group_threads = fft_group_threads(pl->log2m);
+    pl->n_groups = kLogmelThreads / pl->group_threads;
+    const size_t base_bytes = sizeof(float) * (static_cast<size_t>(pl->span_floats) + ((kMels * pl->tile_stride + 3) & ~3) +
+                                               static_cast<size_t>(pl->n_groups) * (3 * M + 4));
+    const size_t table_bytes = sizeof(float) * (2 * static_cast<size_t>(n_tw) + n_fft + ((wts.size() + 3) & ~size_t(3)));
+    const size_t static_bytes = 2048;                   // s_red, s_cluster_red, s_mel + margin
+    pl->smem_tables = base_bytes + table_bytes + static_bytes <= static_cast<size_t>(max_smem);
+    pl->smem_bytes = base_bytes + (pl->smem_tables ? table_bytes : 0);
+    if (pl->smem_bytes + static_bytes > static_cast<size_t>(max_smem)) {
+        set_last_error("log-mel plan needs " + std::to_string(pl->smem_bytes) + " B shared memory per CTA (limit " +
+                       std::to_string(max_smem) + "): hop/n_fft combination too large for an 8-CTA cluster");
+        logmel_plan_destroy(pl);
+        return 3;
+    }
+    LogmelKernelFn fn = pick_logmel_kernel(pl->log2m, pl->smem_tables);
+    WSB_REQUIRE(fn != nullptr, "unsupported n_fft");
     cudaFuncAttributes fa;
-    WSB_CHECK_CUDA(cudaFuncGetAttributes(&fa, logmel_kernel));
-    WSB_CHECK_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    WSB_CHECK_CUDA(cudaFuncGetAttributes(&fa, fn));
+    WSB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         max_smem - static_cast<int>(fa.sharedSizeBytes)));
     *out = pl;
     return 0;
@@ -421,6 +494,7 @@ int logmel_run(const LogmelPlan* pl, const float* audio_dev, const long long* wi
     p.n_groups = pl->n_groups;
     p.span_floats = pl->span_floats;
     p.tile_stride = pl->tile_stride;
+    p.mel_nnz = pl->nnz;
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(n_win) * pl->cluster);
@@ -434,7 +508,7 @@ int logmel_run(const LogmelPlan* pl, const float* audio_dev, const long long* wi
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    WSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, logmel_kernel, p));
+    WSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pick_logmel_kernel(pl->log2m, pl->smem_tables), p));
     count_launch();
     return 0;
 }

@@ -49,6 +49,7 @@ struct GemmArgs {
     int block_n = 0;                    // 0 = choose
     int splits = 1;                     // split-K factor (GEMM_OUT_F32 without bias only): partial plane s is
     int64_t split_stride = 0;           //   written at out + s * split_stride; see splitk_reduce_* below
+    const unsigned char* row_skip = nullptr;   // optional [M] flags: flagged rows are not stored (GEMM_OUT_F32)
 };
 // effective number of partial planes gemm_bf16 will write for (K, splits)
 int gemm_effective_splits(int K, int splits);
@@ -67,9 +68,10 @@ int conv1_gelu(const float* feats, const float* w /*[d][80][3]*/, const float* b
 //   bf16 variant : out_bf16[M][N] = act(sum + bias)
 //   resid+LN     : x[M][N] += sum + bias (fp32, in place); if gamma: xn_bf16 = LayerNorm(x) (N <= 1536)
 int splitk_reduce_bf16(const float* partial, int splits, int64_t split_stride, int M, int N, const float* bias, int gelu,
-                       __nv_bfloat16* out, cudaStream_t stream);
+                       __nv_bfloat16* out, const unsigned char* row_skip, cudaStream_t stream);
 int splitk_reduce_resid_ln(const float* partial, int splits, int64_t split_stride, int M, int N, const float* bias,
-                           float* x, const float* gamma, const float* beta, __nv_bfloat16* xn, cudaStream_t stream);
+                           float* x, const float* gamma, const float* beta, __nv_bfloat16* xn,
+                           const unsigned char* row_skip, cudaStream_t stream);
 int embed_tokens(const int* tokens, const int* positions, const __nv_bfloat16* emb, const float* pos_emb, float* x,
                  int B, int d, cudaStream_t stream);
 
