@@ -330,8 +330,11 @@ def run_ours(args):
                                    launches=dg_cnt, algorithmic_bytes_per_launch=dec_weight_bytes / (6 * L),
                                    note="weight streaming at batch %d" % n_win)
     shares = {k: v[0] for k, v in prof.items() if v[1]}
+    # DRAM traffic of one representative launch of the class (the qkv projection: exactly the class-average
+    # FLOPs per launch) from `ncu --set full`: profiles/r1_ncu_full_gemm_qkv2.txt (read 318 MB + write 876 MB;
+    # algorithmic: A 307 MB + W 10 MB + C 922 MB)
     roofline = dict(bound="tensor", achieved=roof["achieved"], peak=roof["peak"], unit="TFLOP/s", frac=roof["frac"],
-                    traffic=None, kernel="gemm_kernel<BN> (encoder GEMM class: conv2, qkv, out-proj, fc1, fc2)",
+                    traffic=1.194e9 if args.arch == "large" else None, kernel="gemm_kernel<BN> (encoder GEMM class: conv2, qkv, out-proj, fc1, fc2)",
                     ms_per_launch=roof["ms_per_launch"], launches=roof["launches"],
                     algorithmic_flops_per_launch=roof["algorithmic_flops_per_launch"],
                     peak_source="%s cuBLAS bf16, sustained figure (kernel timed inside a long step)" % pk["source"])
@@ -359,6 +362,27 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     t_e2e = float(te.item())
     e2e_value = world * SECONDS_PER_GPU * e2e_steps / t_e2e
+
+    # ---- secondary figure: the same workload with a decode budget sized to real label statistics --------
+    # (data/example_subset/Marmoset: 7.6 segments = ~24 tokens per 2.5 s window, max 15 segments = 46 tokens;
+    # a trained model stops there, the random-init one mostly does not.)  Device-resident, like `value`.
+    short_len = 64
+    def short_step():
+        feats = eng.features_device(plan, audio_dev, desc_dev, n_win)
+        eng.encode(feats)
+        return eng.generate(n_win, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, short_len)
+    short_step()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(2):
+        short_step()
+    s1.record()
+    barrier()
+    ts = torch.tensor([s0.elapsed_time(s1) / 2], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    short_ms = float(ts.item())
     h2d = len(piece) * 4 + n_win * 24
     d2h = n_win * max_new * 4
 
@@ -376,6 +400,9 @@ def run_ours(args):
                     e2e=dict(value=e2e_value, unit="audio-s/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              steps=e2e_steps, segments=len(res["onset"])),
                     gpu_launches=launches, clocks=clocks, roofline=roofline, kernels=kernels, cpu_baseline=cpu,
+                    secondary=dict(note="same workload, decode budget max_length=%d (covers the longest labelled marmoset "
+                                        "window: 46 tokens)" % short_len, max_length=short_len, ms_per_step=short_ms,
+                                   value=world * SECONDS_PER_GPU / (short_ms / 1000.0), unit="audio-s/s"),
                     decode_positions_per_step=float(np.mean(steps_done)),
                     decode_row_lengths=dict(mean=float(row_len.mean()), median=float(np.median(row_len)),
                                             p95=float(np.percentile(row_len, 95)), max=int(row_len.max()),

@@ -83,7 +83,8 @@ int wsb_encode(wsb_model* model, const float* features_dev, int batch, float* hi
  * forced_dev: NULL, or device int32 [batch][max_length] decoder inputs for teacher forcing (the
  * per-position arg-max is still what is written to tokens_dev).  n_steps (host, may be NULL)
  * receives the number of generated positions actually computed.  flags: bit0 = replay the decode
- * step from a CUDA graph; bit1 = launch decode kernels with programmatic dependent launch.       */
+ * step from a CUDA graph; bit1 = launch decode kernels with programmatic dependent launch; bit2 =
+ * disable batch compaction (gathering the still-active rows into a smaller batch as rows finish).  */
 int wsb_generate(wsb_model* model, int batch, const int32_t* prompt, int prompt_len, int eos_id, int pad_id,
                  int max_length, const int32_t* forced_dev, int32_t* tokens_dev, int* n_steps, int flags,
                  void* stream);

@@ -136,3 +136,31 @@ def test_segment_multi_trial_and_empty(setup):
     assert res["onset"] == sorted(res["onset"])
     empty = seg.segment(np.zeros(0, np.float32), 16000, num_trials=1, num_beams=1, max_length=16)
     assert set(empty) == {"onset", "offset", "cluster"}
+
+
+def test_batch_compaction_equals_uncompacted(tiny_checkpoint, monkeypatch):
+    """Gathering the still-active rows into a smaller batch (decode.cu: batch compaction) must not change
+    a single token: 96 windows, most of which stop early, decoded with and without compaction."""
+    import torch
+    from oracle import synth
+    from whisperseg_b200.frontend import FrontendPlan
+    from whisperseg_b200.segmenter import WhisperSegmenter
+    seg = WhisperSegmenter(tiny_checkpoint[0], device="cuda", device_ids=[0], max_batch=96)
+    eng, tok = seg.engines[0], seg.tokenizer
+    sr, sts = 16000, 0.001
+    audio = synth.synth_audio(96.0, sr, seed=21)
+    plan = FrontendPlan(sr, sts, 0)
+    wins = plan.windows(len(audio), 1)
+    assert len(wins) == 96
+    feats = eng.features(plan, audio, wins)
+    outs = {}
+    for mode in ("compact", "plain"):
+        if mode == "plain":
+            monkeypatch.setenv("WSB_NO_COMPACT", "1")
+        eng.encode(feats)
+        ids, n_steps = eng.generate(96, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, 160)
+        outs[mode] = (ids.cpu(), n_steps)
+    lens = (outs["plain"][0] != tok.eos_token_id).sum(dim=1)
+    print("row lengths: min %d median %d max %d; steps %d" % (lens.min(), lens.median(), lens.max(), outs["plain"][1]))
+    assert torch.equal(outs["compact"][0], outs["plain"][0])
+    assert outs["compact"][1] == outs["plain"][1]

@@ -249,7 +249,8 @@ __global__ void argmax_finalize_kernel(const float* __restrict__ val, const int*
                                        int* __restrict__ tokens_out, int max_new, int out_offset,
                                        int* __restrict__ next_token, const int* __restrict__ forced, int forced_ld,
                                        unsigned char* __restrict__ finished, const int* __restrict__ step_ptr,
-                                       int* __restrict__ n_active, int eos_id, int pad_id, int B) {
+                                       int* __restrict__ n_active, int eos_id, int pad_id, int B,
+                                       const int* __restrict__ row_map) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     pdl_wait();
     pdl_launch_dependents();
@@ -282,7 +283,9 @@ __global__ void argmax_finalize_kernel(const float* __restrict__ val, const int*
             } else {
                 const bool was_finished = finished[warp] != 0;
                 const int tok = was_finished ? pad_id : best_i;
-                if (slot >= 0 && slot < max_new) tokens_out[static_cast<long long>(warp) * max_new + slot] = tok;
+                const int orow = row_map ? row_map[warp] : warp;       // slot -> original window after compaction
+                if (slot >= 0 && slot < max_new && !was_finished)
+                    tokens_out[static_cast<long long>(orow) * max_new + slot] = tok;
                 next_token[warp] = tok;
                 if (!was_finished && tok == eos_id) {
                     finished[warp] = 1;
@@ -300,11 +303,11 @@ __global__ void step_increment_kernel(int* step_ptr) {
 
 int argmax_finalize(const float* val, const int* idx, int n_tiles, int* tokens_out, int max_new, int out_offset,
                     int* next_token, const int* forced, int forced_ld, unsigned char* finished, int* step_ptr,
-                    int* n_active, int eos_id, int pad_id, int B, cudaStream_t stream) {
+                    int* n_active, int eos_id, int pad_id, int B, const int* row_map, cudaStream_t stream) {
     if (B <= 0) return 0;
     WSB_CHECK_CUDA(launch_kernel(argmax_finalize_kernel, dim3(ceil_div(B * 32, 256)), dim3(256), 0, stream, val, idx, n_tiles,
                                  tokens_out, max_new, out_offset, next_token, forced, forced_ld, finished,
-                                 static_cast<const int*>(step_ptr), n_active, eos_id, pad_id, B));
+                                 static_cast<const int*>(step_ptr), n_active, eos_id, pad_id, B, row_map));
     WSB_CHECK_CUDA(launch_kernel(step_increment_kernel, dim3(1), dim3(1), 0, stream, step_ptr));
     count_launch(2);
     return 0;
@@ -327,6 +330,82 @@ int prefill_advance(int* next_token, const int* forced, int forced_ld, const int
     WSB_CHECK_CUDA(launch_kernel(prefill_advance_kernel, dim3(1), dim3(256), 0, stream, next_token, forced, forced_ld, prompt_dev,
                                  step_ptr, B));
     count_launch();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- batch compaction
+// When most windows have emitted EOS the per-position cost is dominated by work that scales with the
+// batch dimension of the launch (split-K planes, reduce CTAs, GEMM m-tiles).  The still-active rows are
+// then gathered into a small dense batch: their K/V caches and cross-attention K/V blocks are copied
+// once (tens of MB per row) and the remaining hundreds of positions run on the compact batch.
+__global__ void compact_plan_kernel(const unsigned char* __restrict__ fin_src, int b_src, const int* __restrict__ map_src,
+                                    const int* __restrict__ tok_src, int b_dst, int* __restrict__ active_idx,
+                                    int* __restrict__ map_dst, int* __restrict__ tok_dst,
+                                    unsigned char* __restrict__ fin_dst) {
+    if (threadIdx.x != 0) return;
+    int n = 0;
+    for (int r = 0; r < b_src && n < b_dst; ++r) {
+        if (!fin_src[r]) {
+            active_idx[n] = r;
+            map_dst[n] = map_src ? map_src[r] : r;
+            tok_dst[n] = tok_src[r];
+            fin_dst[n] = 0;
+            ++n;
+        }
+    }
+    for (int i = n; i < b_dst; ++i) {
+        active_idx[i] = -1;
+        map_dst[i] = 0;
+        tok_dst[i] = 0;
+        fin_dst[i] = 1;                                  // padding slots are skipped by every kernel
+    }
+}
+
+// grid (H, b_dst, L): copy positions [0, *step_ptr) of one (layer, slot, head) K and V block
+__global__ void gather_self_cache_kernel(const __nv_bfloat16* __restrict__ k_src, const __nv_bfloat16* __restrict__ v_src,
+                                         __nv_bfloat16* __restrict__ k_dst, __nv_bfloat16* __restrict__ v_dst,
+                                         const int* __restrict__ active_idx, const int* __restrict__ step_ptr, int b_src,
+                                         int b_dst, int n_heads, int t_max) {
+    const int h = blockIdx.x, slot = blockIdx.y, l = blockIdx.z;
+    const int r = active_idx[slot];
+    if (r < 0) return;
+    const int n_vec = *step_ptr * 8;                     // uint4 = 8 bf16; 64 dims = 8 vectors per position
+    const long long so = ((static_cast<long long>(l) * b_src + r) * n_heads + h) * t_max * 64;
+    const long long dofs = ((static_cast<long long>(l) * b_dst + slot) * n_heads + h) * t_max * 64;
+    const uint4* ks = reinterpret_cast<const uint4*>(k_src + so);
+    const uint4* vs = reinterpret_cast<const uint4*>(v_src + so);
+    uint4* kd = reinterpret_cast<uint4*>(k_dst + dofs);
+    uint4* vd = reinterpret_cast<uint4*>(v_dst + dofs);
+    for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
+        kd[i] = ks[i];
+        vd[i] = vs[i];
+    }
+}
+
+// grid (chunks, b_dst): copy one window's contiguous cross-attention K/V block [L][2][H][T][64]
+__global__ void gather_cross_kv_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                       const int* __restrict__ active_idx, long long row_elems) {
+    const int slot = blockIdx.y;
+    const int r = active_idx[slot];
+    if (r < 0) return;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + static_cast<long long>(r) * row_elems);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + static_cast<long long>(slot) * row_elems);
+    const long long n_vec = row_elems / 8;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        d4[i] = s4[i];
+}
+
+int compact_decode_state(const CompactArgs& a, cudaStream_t stream) {
+    compact_plan_kernel<<<1, 32, 0, stream>>>(a.fin_src, a.b_src, a.map_src, a.tok_src, a.b_dst, a.active_idx, a.map_dst,
+                                              a.tok_dst, a.fin_dst);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    gather_self_cache_kernel<<<dim3(a.n_heads, a.b_dst, a.n_layers), 256, 0, stream>>>(
+        a.k_src, a.v_src, a.k_dst, a.v_dst, a.active_idx, a.step_ptr, a.b_src, a.b_dst, a.n_heads, a.t_max);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    gather_cross_kv_kernel<<<dim3(256, a.b_dst), 256, 0, stream>>>(a.cross_src, a.cross_dst, a.active_idx, a.cross_row_elems);
+    WSB_CHECK_CUDA(cudaGetLastError());
+    count_launch(3);
     return 0;
 }
 

@@ -10,6 +10,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <tuple>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -122,12 +124,31 @@ struct Model {
     unsigned char* finished;
     int am_tiles = 0, logits_bn = 0;
     int last_batch = 0;
-    // CUDA graph of one steady-state decode step, keyed by batch
-    cudaGraphExec_t graph_exec = nullptr;
-    int graph_batch = -1;
-    int graph_kernels = 0;
+    // compact decode state (see decode.cu: batch compaction): alternate K/V buffers for kCompactRows rows
+    __nv_bfloat16 *cross_kv_alt, *k_cache_alt, *v_cache_alt;
+    int *next_token_alt, *row_map_main, *row_map_alt, *active_idx;
+    unsigned char* finished_alt;
+    // CUDA graphs of one steady-state decode step, keyed by everything that is baked into the launches
+    struct GraphEntry {
+        cudaGraphExec_t exec;
+        int kernels;
+    };
+    std::map<std::tuple<int, int, int, int, int, int, int>, GraphEntry> graphs;
     bool use_pdl = false;
     int* pinned_active = nullptr;
+};
+
+constexpr int kCompactRows = 64;        // first compaction level; the second level (16 rows) reuses the main buffers
+constexpr int kCompactRows2 = 16;
+
+// the per-row decode state a step works on (main buffers, or a compacted copy)
+struct DecState {
+    int B;
+    int buffer_id;                      // 0 = main buffers, 1 = alternate buffers
+    __nv_bfloat16 *k_cache, *v_cache, *cross_kv;
+    int* next_token;
+    unsigned char* finished;
+    const int* row_map;                 // slot -> window index of this generate() call (null = identity)
 };
 
 template <typename T>
@@ -170,6 +191,17 @@ static int model_layout(Model* m, bool assign) {
     m->n_active = carve<int>(p, 4);
     m->prompt_dev = carve<int>(p, 16);
     m->finished = carve<unsigned char>(p, B);
+    {
+        const size_t Ba = std::min<size_t>(B, kCompactRows);
+        m->cross_kv_alt = carve<__nv_bfloat16>(p, Ba * L * 2 * H * T * 64);
+        m->k_cache_alt = carve<__nv_bfloat16>(p, L * Ba * H * c.max_target_positions * 64);
+        m->v_cache_alt = carve<__nv_bfloat16>(p, L * Ba * H * c.max_target_positions * 64);
+        m->next_token_alt = carve<int>(p, B);
+        m->row_map_main = carve<int>(p, B);
+        m->row_map_alt = carve<int>(p, B);
+        m->active_idx = carve<int>(p, B);
+        m->finished_alt = carve<unsigned char>(p, B);
+    }
     m->ws_bytes = static_cast<size_t>(p - p0);
     return 0;
 }
@@ -260,7 +292,7 @@ static int model_create(const wsb_model_config* cfg, const char* const* names, c
 
 static void model_destroy(Model* m) {
     if (!m) return;
-    if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+    for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
     cudaFree(m->ws);
     cudaFreeHost(m->pinned_active);
     delete m;
@@ -388,17 +420,18 @@ static int skinny_linear(Model* m, const __nv_bfloat16* A, const __nv_bfloat16* 
 }
 
 // one decoder position for all rows.  with_logits: project + arg-max + finalize; else prefill advance.
-static int decode_step(Model* m, int B, bool with_logits, bool first_generated, int prompt_len, int max_new,
+static int decode_step(Model* m, const DecState& st, bool with_logits, bool first_generated, int prompt_len, int max_new,
                        const int* forced, int forced_ld, int eos_id, int pad_id, cudaStream_t s) {
     const wsb_model_config& c = m->cfg;
+    const int B = st.B;
     const int d = c.d_model, F = c.ffn_dim, L = c.n_layers, H = c.n_heads, T = m->T, tmax = c.max_target_positions;
-    const unsigned char* fin = forced ? nullptr : m->finished;
+    const unsigned char* fin = forced ? nullptr : st.finished;
     struct PdlScope {
         bool prev;
         explicit PdlScope(bool on) : prev(g_use_pdl) { g_use_pdl = on; }
         ~PdlScope() { g_use_pdl = prev; }
     } pdl_scope(m->use_pdl);
-    WSB_RUN(embed_tokens_step(m->next_token, m->step, 0, m->dec_emb, m->dec_pos, m->dx, B, d, s));
+    WSB_RUN(embed_tokens_step(st.next_token, m->step, 0, m->dec_emb, m->dec_pos, m->dx, B, d, s));
     const long long cache_l = static_cast<long long>(B) * H * tmax * 64;
     {
         ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
@@ -413,20 +446,20 @@ static int decode_step(Model* m, int B, bool with_logits, bool first_generated, 
         WSB_RUN(skinny_linear(m, m->dxn, e.sqkv_w, e.sqkv_b, B, 3 * d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, fin, &part));
         {
             ProfScope ps(PROF_DEC_SELF_ATTN, 0.0, s);
-            WSB_RUN(decode_self_attention(nullptr, &part, d, m->k_cache + l * cache_l, m->v_cache + l * cache_l, tmax, m->step, 0,
+            WSB_RUN(decode_self_attention(nullptr, &part, d, st.k_cache + l * cache_l, st.v_cache + l * cache_l, tmax, m->step, 0,
                                           fin, m->datt, B, H, s));
         }
         WSB_RUN(skinny_linear(m, m->datt, e.so_w, e.so_b, B, d, d, 0, nullptr, m->dx, e.ln2_g, e.ln2_b, m->dxn, s, fin));
         WSB_RUN(skinny_linear(m, m->dxn, e.cq_w, e.cq_b, B, d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, fin, &part));
         {
             ProfScope ps(PROF_DEC_CROSS_ATTN, 4.0 * B * H * T * 64.0, s);   // bytes: K and V blocks, bf16
-            WSB_RUN(decode_cross_attention(nullptr, &part, d, m->cross_kv, l, L, T, fin, m->datt, B, H, s));
+            WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s));
         }
         WSB_RUN(skinny_linear(m, m->datt, e.co_w, e.co_b, B, d, d, 0, nullptr, m->dx, e.ln3_g, e.ln3_b, m->dxn, s, fin));
         WSB_RUN(skinny_linear(m, m->dxn, e.fc1_w, e.fc1_b, B, F, d, 1, m->dff, nullptr, nullptr, nullptr, nullptr, s, fin));
         WSB_RUN(skinny_linear(m, m->dff, e.fc2_w, e.fc2_b, B, d, F, 0, nullptr, m->dx, next_g, next_b, m->dxn, s, fin));
     }
-    if (!with_logits) return prefill_advance(m->next_token, forced, forced_ld, m->prompt_dev, m->step, B, s);
+    if (!with_logits) return prefill_advance(st.next_token, forced, forced_ld, m->prompt_dev, m->step, B, s);
     GemmArgs g;
     g.A = m->dxn;
     g.lda = d;
@@ -444,8 +477,8 @@ static int decode_step(Model* m, int B, bool with_logits, bool first_generated, 
         ProfScope ps(PROF_DEC_LOGITS, 2.0 * B * c.vocab_size * d, s);
         WSB_RUN(gemm_bf16(g, s));
     }
-    return argmax_finalize(m->am_val, m->am_idx, m->am_tiles, m->tokens, max_new, prompt_len - 1, m->next_token, forced,
-                           forced_ld, m->finished, m->step, m->n_active, eos_id, pad_id, B, s);
+    return argmax_finalize(m->am_val, m->am_idx, m->am_tiles, m->tokens, max_new, prompt_len - 1, st.next_token, forced,
+                           forced_ld, st.finished, m->step, m->n_active, eos_id, pad_id, B, st.row_map, s);
 }
 
 static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_id, int pad_id, int max_length,
@@ -492,45 +525,108 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
         WSB_CHECK_CUDA(cudaMemcpyAsync(m->tokens, pad.data(), sizeof(int) * pad.size(), cudaMemcpyHostToDevice, s));
         WSB_CHECK_CUDA(cudaStreamSynchronize(s));
     }
+    DecState st;
+    st.B = B;
+    st.buffer_id = 0;
+    st.k_cache = m->k_cache;
+    st.v_cache = m->v_cache;
+    st.cross_kv = m->cross_kv;
+    st.next_token = m->next_token;
+    st.finished = m->finished;
+    st.row_map = nullptr;
     for (int pos = 0; pos + 1 < prompt_len; ++pos)
-        WSB_RUN(decode_step(m, B, false, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
+        WSB_RUN(decode_step(m, st, false, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
     // first generated token (begin-suppress mask active)
-    WSB_RUN(decode_step(m, B, true, true, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
+    WSB_RUN(decode_step(m, st, true, true, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
     int steps_done = 1;
-    const bool use_graph = (flags & 1) != 0 && max_new > 2;
-    if (use_graph && (m->graph_exec == nullptr || m->graph_batch != B * 2 + (forced ? 1 : 0))) {
-        if (m->graph_exec) {
-            cudaGraphExecDestroy(m->graph_exec);
-            m->graph_exec = nullptr;
+    // teacher forcing bakes a caller-owned pointer into the launches: never replay those from a cached graph
+    const bool use_graph = (flags & 1) != 0 && max_new > 2 && forced == nullptr;
+    const bool allow_compaction = (flags & 4) == 0 && forced == nullptr;
+    Model::GraphEntry* graph = nullptr;
+    auto get_graph = [&](const DecState& cur, Model::GraphEntry** out) -> int {
+        const auto key = std::make_tuple(cur.B, cur.buffer_id, cur.row_map != nullptr ? 1 : 0, max_new, prompt_len, eos_id, pad_id);
+        auto it = m->graphs.find(key);
+        if (it == m->graphs.end()) {
+            cudaGraph_t g = nullptr;
+            WSB_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            g_capturing = true;
+            const long long before = g_launches.load();
+            int rc = decode_step(m, cur, true, false, prompt_len, max_new, nullptr, max_length, eos_id, pad_id, s);
+            const int kernels = static_cast<int>(g_launches.load() - before);
+            g_launches.store(before);                   // captured, not executed
+            g_capturing = false;
+            cudaError_t ce = cudaStreamEndCapture(s, &g);
+            if (rc) return rc;
+            WSB_CHECK_CUDA(ce);
+            Model::GraphEntry entry;
+            entry.kernels = kernels;
+            WSB_CHECK_CUDA(cudaGraphInstantiate(&entry.exec, g, 0));
+            cudaGraphDestroy(g);
+            it = m->graphs.emplace(key, entry).first;
         }
-        cudaGraph_t graph = nullptr;
-        WSB_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        g_capturing = true;
-        const long long before = g_launches.load();
-        int rc = decode_step(m, B, true, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s);
-        m->graph_kernels = static_cast<int>(g_launches.load() - before);
-        g_launches.store(before);                       // captured, not executed
-        g_capturing = false;
-        cudaError_t ce = cudaStreamEndCapture(s, &graph);
-        if (rc) return rc;
-        WSB_CHECK_CUDA(ce);
-        WSB_CHECK_CUDA(cudaGraphInstantiate(&m->graph_exec, graph, 0));
-        cudaGraphDestroy(graph);
-        m->graph_batch = B * 2 + (forced ? 1 : 0);
-    }
+        *out = &it->second;
+        return 0;
+    };
+    if (use_graph) WSB_RUN(get_graph(st, &graph));
     const int check_every = 8;
     while (steps_done < max_new) {
         if (use_graph) {
-            WSB_CHECK_CUDA(cudaGraphLaunch(m->graph_exec, s));
-            count_launch(m->graph_kernels);
+            WSB_CHECK_CUDA(cudaGraphLaunch(graph->exec, s));
+            count_launch(graph->kernels);
         } else {
-            WSB_RUN(decode_step(m, B, true, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
+            WSB_RUN(decode_step(m, st, true, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
         }
         ++steps_done;
         if (!forced && (steps_done % check_every) == 0 && steps_done < max_new) {
             WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active, m->n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
             WSB_CHECK_CUDA(cudaStreamSynchronize(s));
-            if (m->pinned_active[0] <= 0) break;
+            const int active = m->pinned_active[0];
+            if (active <= 0) break;
+            // batch compaction: main (B) -> alternate (64 or 16) -> main (16)
+            int target = 0;
+            if (allow_compaction && max_new - steps_done >= 16) {
+                if (st.buffer_id == 0 && st.B > kCompactRows && active <= kCompactRows)
+                    target = active <= kCompactRows2 ? kCompactRows2 : kCompactRows;
+                else if (st.buffer_id == 1 && st.B > kCompactRows2 && active <= kCompactRows2)
+                    target = kCompactRows2;
+            }
+            if (target > 0) {
+                DecState nx;
+                nx.B = target;
+                nx.buffer_id = 1 - st.buffer_id;
+                const bool to_alt = nx.buffer_id == 1;
+                nx.k_cache = to_alt ? m->k_cache_alt : m->k_cache;
+                nx.v_cache = to_alt ? m->v_cache_alt : m->v_cache;
+                nx.cross_kv = to_alt ? m->cross_kv_alt : m->cross_kv;
+                nx.next_token = to_alt ? m->next_token_alt : m->next_token;
+                nx.finished = to_alt ? m->finished_alt : m->finished;
+                int* map_dst = to_alt ? m->row_map_alt : m->row_map_main;
+                nx.row_map = map_dst;
+                CompactArgs ca;
+                ca.fin_src = st.finished;
+                ca.b_src = st.B;
+                ca.map_src = st.row_map;
+                ca.tok_src = st.next_token;
+                ca.b_dst = target;
+                ca.active_idx = m->active_idx;
+                ca.map_dst = map_dst;
+                ca.tok_dst = nx.next_token;
+                ca.fin_dst = nx.finished;
+                ca.k_src = st.k_cache;
+                ca.v_src = st.v_cache;
+                ca.cross_src = st.cross_kv;
+                ca.k_dst = nx.k_cache;
+                ca.v_dst = nx.v_cache;
+                ca.cross_dst = nx.cross_kv;
+                ca.step_ptr = m->step;
+                ca.n_heads = c.n_heads;
+                ca.n_layers = L;
+                ca.t_max = c.max_target_positions;
+                ca.cross_row_elems = static_cast<long long>(L) * 2 * c.n_heads * T * 64;
+                WSB_RUN(compact_decode_state(ca, s));
+                st = nx;
+                if (use_graph) WSB_RUN(get_graph(st, &graph));
+            }
         }
     }
     WSB_CHECK_CUDA(cudaMemcpyAsync(tokens_out, m->tokens, sizeof(int) * static_cast<size_t>(B) * max_new,
