@@ -26,8 +26,9 @@ namespace wsb {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 384;           // 4 control warps + 8 epilogue warps
-constexpr int kEpiWarps = 8;
+// epilogue warps: a multiple of 4 (one set per TMEM lane quarter).  16 warps hide the epilogue of short-K
+// tiles (K=1280: 20 k-blocks) at the price of one pipeline stage; long-K tiles keep 8 warps and 4 stages.
+constexpr int kMaxEpiWarps = 16;
 constexpr int kABytes = kBM * kBK * 2;
 
 struct GemmDev {
@@ -51,11 +52,14 @@ struct GemmDev {
     const unsigned char* row_skip; // optional [M]: rows flagged non-zero are not stored (finished decode rows)
 };
 
-template <int BN>
+template <int BN, int EPIW>
 struct GemmCfg {
+    static constexpr int kEpiWarps = EPIW;
+    static constexpr int kEpiGroups = EPIW / 4;          // column groups
+    static constexpr int kThreads = 128 + 32 * EPIW;     // 4 control warps + epilogue warps
     static constexpr int kBBytes = BN * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+    static constexpr int kStages = (BN == 256) ? (EPIW > 8 ? 3 : 4) : (BN == 128) ? (EPIW > 8 ? 4 : 6) : (EPIW > 8 ? 6 : 8);
     static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
     static constexpr int kEpiBytes = kEpiWarps * 32 * 33 * 4;
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -65,10 +69,11 @@ struct GemmCfg {
 // the instruction cache (runtime mode flags made the epilogue fetch- and branch-bound)
 enum Epi : int { EPI_BF16 = 0, EPI_BF16_GELU, EPI_F32, EPI_F32_RESID, EPI_F32_GELU_ROWVEC, EPI_HEADMAJOR, EPI_ARGMAX };
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, int EPI, int EPIW>
+__global__ void __launch_bounds__(128 + 32 * EPIW, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, EPIW>;
+    constexpr int kEpiWarps = Cfg::kEpiWarps, kEpiGroups = Cfg::kEpiGroups;
     constexpr int S = Cfg::kStages;
     extern __shared__ unsigned char smem_raw[];
     // align inside the shared window with pointer arithmetic (an integer round-trip would demote every
@@ -178,7 +183,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // ---- epilogue: 8 warps; warp (4 + e) owns TMEM lanes 32*(e%4).. (hardware restriction: a warp
         // may only touch the lane quarter warp_id % 4) and the 32-column chunks c with c % 2 == e / 4.
         const int e = warp - 4;
-        const int q = e & 3, half = e >> 2;
+        const int q = e & 3, half = e >> 2;        // half = column group index
         float* tbuf = epi_buf + e * (32 * 33);            // per-warp 32x32 transpose tile (padded)
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
@@ -233,7 +238,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
             } else {
 #pragma unroll 1
-                for (int c = half; c < BN / 32; c += 2) {
+                for (int c = half; c < BN / 32; c += kEpiGroups) {
                     uint32_t r[32];
                     tmem_ld_32x32(t_base + c * 32, r);
                     tmem_ld_wait();
@@ -399,13 +404,13 @@ int gemm_pick_block_n(int M, int N) {
 }
 int gemm_n_tiles(int N, int block_n) { return ceil_div(N, block_n); }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int EPIW>
 static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, EPIW>;
     static bool attr_set = false;
     static int num_sms = 0;
     if (!attr_set) {
-        WSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        WSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, EPIW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         int dev = 0;
         WSB_CHECK_CUDA(cudaGetDevice(&dev));
         WSB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -465,7 +470,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.row_skip = a.row_skip;
     const int total = p.m_tiles * p.n_tiles * p.splits;
     const int grid = std::min(total, num_sms);
-    WSB_CHECK_CUDA(launch_kernel(gemm_kernel<BN, EPI>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmB, p));
+    WSB_CHECK_CUDA(launch_kernel(gemm_kernel<BN, EPI, EPIW>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, tmA, tmB, p));
     count_launch();
     return 0;
 }
@@ -498,16 +503,19 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
     if (a.splits > 1) WSB_REQUIRE(epi == EPI_F32 && !a.bias && a.split_stride >= static_cast<int64_t>(a.M) * a.ldc,
                                   "split-K writes raw fp32 partial planes (no bias / activation)");
     if (a.rows_per_batch > 0) WSB_REQUIRE(a.rows_per_batch >= 32, "rows_per_batch must be >= 32");
-#define WSB_GEMM_CASE(BN_)                                                                     \
-    case BN_:                                                                                  \
-        switch (epi) {                                                                         \
-            case EPI_BF16: return launch_gemm<BN_, EPI_BF16>(a, stream);                       \
-            case EPI_BF16_GELU: return launch_gemm<BN_, EPI_BF16_GELU>(a, stream);             \
-            case EPI_F32: return launch_gemm<BN_, EPI_F32>(a, stream);                         \
-            case EPI_F32_RESID: return launch_gemm<BN_, EPI_F32_RESID>(a, stream);             \
-            case EPI_F32_GELU_ROWVEC: return launch_gemm<BN_, EPI_F32_GELU_ROWVEC>(a, stream); \
-            case EPI_HEADMAJOR: return launch_gemm<BN_, EPI_HEADMAJOR>(a, stream);             \
-            default: return launch_gemm<BN_, EPI_ARGMAX>(a, stream);                           \
+    // short-K tiles are epilogue-bound: give them 16 epilogue warps; long-K and skinny GEMMs keep 8
+    const bool wide_epi = (a.K / kBK) / (a.splits > 1 ? a.splits : 1) <= 40 && a.M > 512 && epi != EPI_ARGMAX;
+#define WSB_GEMM_EPI(BN_, EPI_) (wide_epi ? launch_gemm<BN_, EPI_, 16>(a, stream) : launch_gemm<BN_, EPI_, 8>(a, stream))
+#define WSB_GEMM_CASE(BN_)                                                           \
+    case BN_:                                                                        \
+        switch (epi) {                                                               \
+            case EPI_BF16: return WSB_GEMM_EPI(BN_, EPI_BF16);                       \
+            case EPI_BF16_GELU: return WSB_GEMM_EPI(BN_, EPI_BF16_GELU);             \
+            case EPI_F32: return WSB_GEMM_EPI(BN_, EPI_F32);                         \
+            case EPI_F32_RESID: return WSB_GEMM_EPI(BN_, EPI_F32_RESID);             \
+            case EPI_F32_GELU_ROWVEC: return WSB_GEMM_EPI(BN_, EPI_F32_GELU_ROWVEC); \
+            case EPI_HEADMAJOR: return WSB_GEMM_EPI(BN_, EPI_HEADMAJOR);             \
+            default: return launch_gemm<BN_, EPI_ARGMAX, 8>(a, stream);              \
         }
     switch (bn) {
         WSB_GEMM_CASE(256)
@@ -516,6 +524,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
         WSB_GEMM_CASE(32)
         default: set_last_error("unsupported block_n"); return 2;
     }
+#undef WSB_GEMM_EPI
 #undef WSB_GEMM_CASE
 }
 
