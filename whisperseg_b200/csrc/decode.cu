@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaPa
     if (p.finished && p.finished[b]) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     __shared__ float s_q[64];
-    __shared__ float s_p[kDaMaxKeys];
+    __shared__ float s_p[kDaThreads / 32];
     __shared__ float s_red[kDaThreads / 32];
     __shared__ float s_out[kDaThreads / 32][64];
 
@@ -88,75 +88,77 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaPa
     if (tid < 64) s_q[tid] = __bfloat162float(__float2bfloat16(proj(h * 64 + tid, p.q)));
     __syncthreads();                                   // also orders the cache append before the reads below
 
-    // scores: a warp covers 4 keys per iteration; lane = (key % 4) * 8 + 16-byte chunk
+    // Single pass over the keys with an online softmax: a warp covers 4 keys per step (lane = (key % 4) * 8 +
+    // 16-byte chunk, so every load instruction reads 512 contiguous bytes), K and V rows of two steps are in
+    // flight together, and each 8-lane group keeps its own running (max, sum, 8-dim accumulator).
     const int sub = lane >> 3, ch = lane & 7;
     float qv[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) qv[i] = s_q[ch * 8 + i];
-    float lmax = -INFINITY;
-    for (int j0 = warp * 4; j0 < n_keys; j0 += (kDaThreads / 32) * 4) {
-        const int j = j0 + sub;
-        float dot = 0.0f;
-        if (j < n_keys) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(K + static_cast<long long>(j) * 64 + ch * 8);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __bfloat1622float2(h2[i]);
-                dot = fmaf(f.x, qv[2 * i], dot);
-                dot = fmaf(f.y, qv[2 * i + 1], dot);
-            }
-        }
-        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        if (j < n_keys) {
-            if (ch == 0) s_p[j] = dot;
-            lmax = fmaxf(lmax, dot);
-        }
-    }
-    lmax = warp_max(lmax);
-    if (lane == 0) s_red[warp] = lmax;
-    __syncthreads();
-    float gmax = s_red[0];
-#pragma unroll
-    for (int i = 1; i < kDaThreads / 32; ++i) gmax = fmaxf(gmax, s_red[i]);
-    __syncthreads();
-    float lsum = 0.0f;
-    for (int j = tid; j < n_keys; j += kDaThreads) {
-        const float e = __expf(s_p[j] - gmax);
-        s_p[j] = e;
-        lsum += e;
-    }
-    lsum = warp_sum(lsum);
-    if (lane == 0) s_red[warp] = lsum;
-    __syncthreads();
-    float gsum = 0.0f;
-#pragma unroll
-    for (int i = 0; i < kDaThreads / 32; ++i) gsum += s_red[i];
-
-    // out = sum_j p_j V_j : same 4-keys-per-warp streaming pattern, 8 dims per lane
+    float m_run = -INFINITY, l_run = 0.0f;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-    for (int j0 = warp * 4; j0 < n_keys; j0 += (kDaThreads / 32) * 4) {
-        const int j = j0 + sub;
-        if (j < n_keys) {
-            const float pj = s_p[j];
-            const uint4 raw = *reinterpret_cast<const uint4*>(V + static_cast<long long>(j) * 64 + ch * 8);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    constexpr int kStep = (kDaThreads / 32) * 4;           // keys per CTA step
+    for (int j0 = warp * 4; j0 < n_keys; j0 += 2 * kStep) {
+        uint4 kraw[2], vraw[2];
+        bool ok[2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __bfloat1622float2(h2[i]);
-                acc[2 * i] = fmaf(pj, f.x, acc[2 * i]);
-                acc[2 * i + 1] = fmaf(pj, f.y, acc[2 * i + 1]);
+        for (int u = 0; u < 2; ++u) {
+            const int j = j0 + u * kStep + sub;
+            ok[u] = j < n_keys;
+            if (ok[u]) {
+                kraw[u] = *reinterpret_cast<const uint4*>(K + static_cast<long long>(j) * 64 + ch * 8);
+                vraw[u] = *reinterpret_cast<const uint4*>(V + static_cast<long long>(j) * 64 + ch * 8);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float dot = 0.0f;
+            if (ok[u]) {
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kraw[u]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __bfloat1622float2(h2[i]);
+                    dot = fmaf(f.x, qv[2 * i], dot);
+                    dot = fmaf(f.y, qv[2 * i + 1], dot);
+                }
+            }
+            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            if (ok[u]) {
+                const float m_new = fmaxf(m_run, dot);
+                const float scale = __expf(m_run - m_new);      // exp(-inf) = 0 on the first key
+                const float pj = __expf(dot - m_new);
+                l_run = fmaf(l_run, scale, pj);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vraw[u]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __bfloat1622float2(h2[i]);
+                    acc[2 * i] = fmaf(acc[2 * i], scale, pj * f.x);
+                    acc[2 * i + 1] = fmaf(acc[2 * i + 1], scale, pj * f.y);
+                }
+                m_run = m_new;
             }
         }
     }
+    // merge the 4 key sub-groups of the warp, then the warps
+    float m_w = fmaxf(m_run, __shfl_xor_sync(0xffffffffu, m_run, 8));
+    m_w = fmaxf(m_w, __shfl_xor_sync(0xffffffffu, m_w, 16));
+    const float sc = (m_run == -INFINITY) ? 0.0f : __expf(m_run - m_w);
+    l_run *= sc;
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 8);
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 16);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+        acc[i] *= sc;
         acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
         acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    }
+    if (lane == 0) {
+        s_red[warp] = m_w;
+        s_p[warp] = l_run;
     }
     if (sub == 0) {
 #pragma unroll
@@ -164,9 +166,16 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaPa
     }
     __syncthreads();
     if (tid < 64) {
-        float o = 0.0f;
+        float gmax = s_red[0];
 #pragma unroll
-        for (int wi = 0; wi < kDaThreads / 32; ++wi) o += s_out[wi][tid];
+        for (int wi = 1; wi < kDaThreads / 32; ++wi) gmax = fmaxf(gmax, s_red[wi]);
+        float o = 0.0f, gsum = 0.0f;
+#pragma unroll
+        for (int wi = 0; wi < kDaThreads / 32; ++wi) {
+            const float f = (s_red[wi] == -INFINITY) ? 0.0f : __expf(s_red[wi] - gmax);
+            o = fmaf(s_out[wi][tid], f, o);
+            gsum = fmaf(s_p[wi], f, gsum);
+        }
         p.out[static_cast<long long>(b) * p.d + h * 64 + tid] = __float2bfloat16(o / gsum);
     }
 }

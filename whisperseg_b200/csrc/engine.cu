@@ -123,6 +123,7 @@ struct Model {
     int *am_idx, *tokens, *next_token, *step, *n_active, *prompt_dev;
     unsigned char* finished;
     int am_tiles = 0, logits_bn = 0;
+    int* logit_tiles = nullptr;          // n-tiles of the output projection that contain a non-suppressed token
     int last_batch = 0;
     // compact decode state (see decode.cu: batch compaction): alternate K/V buffers for kCompactRows rows
     __nv_bfloat16 *cross_kv_alt, *k_cache_alt, *v_cache_alt;
@@ -281,7 +282,23 @@ static int model_create(const wsb_model_config* cfg, const char* const* names, c
         WSB_GET(e.fc2_w, p + "fc2.w"); WSB_GET(e.fc2_b, p + "fc2.b");
     }
     m->logits_bn = gemm_pick_block_n(cfg->max_batch, cfg->vocab_size);
-    m->am_tiles = gemm_n_tiles(cfg->vocab_size, m->logits_bn);
+    {   // vocabulary tiles in which every token is suppressed (additive -inf mask) can never win the arg-max:
+        // only the others are computed
+        std::vector<float> mask(cfg->vocab_size);
+        WSB_CHECK_CUDA(cudaMemcpy(mask.data(), m->suppress, sizeof(float) * cfg->vocab_size, cudaMemcpyDeviceToHost));
+        std::vector<int> tiles;
+        const int nt = gemm_n_tiles(cfg->vocab_size, m->logits_bn);
+        for (int t = 0; t < nt; ++t) {
+            bool any = false;
+            for (int v = t * m->logits_bn; v < std::min(cfg->vocab_size, (t + 1) * m->logits_bn) && !any; ++v)
+                any = !(mask[v] < -1e30f);
+            if (any) tiles.push_back(t);
+        }
+        if (tiles.empty()) tiles.push_back(0);
+        m->am_tiles = static_cast<int>(tiles.size());
+        WSB_CHECK_CUDA(cudaMalloc(&m->logit_tiles, sizeof(int) * tiles.size()));
+        WSB_CHECK_CUDA(cudaMemcpy(m->logit_tiles, tiles.data(), sizeof(int) * tiles.size(), cudaMemcpyHostToDevice));
+    }
     model_layout(m, false);
     WSB_CHECK_CUDA(cudaMalloc(&m->ws, m->ws_bytes));
     model_layout(m, true);
@@ -294,6 +311,7 @@ static void model_destroy(Model* m) {
     if (!m) return;
     for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
     cudaFree(m->ws);
+    cudaFree(m->logit_tiles);
     cudaFreeHost(m->pinned_active);
     delete m;
 }
@@ -473,6 +491,8 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
     g.argmax_val = m->am_val;
     g.argmax_idx = m->am_idx;
     g.block_n = m->logits_bn;
+    g.n_tile_list = m->logit_tiles;
+    g.n_tile_count = m->am_tiles;
     {
         ProfScope ps(PROF_DEC_LOGITS, 2.0 * B * c.vocab_size * d, s);
         WSB_RUN(gemm_bf16(g, s));

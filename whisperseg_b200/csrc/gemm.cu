@@ -50,6 +50,7 @@ struct GemmDev {
     int splits, kb_per_split;      // split-K: tile space is m_tiles x n_tiles x splits, fp32 partial planes
     long long split_stride;        // elements between partial planes of the output
     const unsigned char* row_skip; // optional [M]: rows flagged non-zero are not stored (finished decode rows)
+    const int* n_tile_list;        // optional: only these n-tiles are computed (n_tiles = length of the list)
 };
 
 template <int BN, int EPIW>
@@ -124,7 +125,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int sp = tile % p.splits, mn = tile / p.splits;
-                const int mt = mn / p.n_tiles, nt = mn - mt * p.n_tiles;
+                const int mt = mn / p.n_tiles, nti = mn - mt * p.n_tiles;
+                const int nt = p.n_tile_list ? p.n_tile_list[nti] : nti;
                 const int kb0 = sp * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
                 int a_row, a_batch;
                 if (tiles_per_batch > 0) {
@@ -188,7 +190,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             const int sp = tile % p.splits, mn = tile / p.splits;
-            const int mt = mn / p.n_tiles, nt = mn - mt * p.n_tiles;
+            const int mt = mn / p.n_tiles, nti = mn - mt * p.n_tiles;
+            const int nt = p.n_tile_list ? p.n_tile_list[nti] : nti;       // nti: dense slot of the arg-max partials
             const int as = local & 1;
             const uint32_t aphase = (local >> 1) & 1;
             long long grow0;                            // global row of this warp's first lane
@@ -232,8 +235,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     }
                     if (valid) {
-                        p.argmax_val[(grow0 + lane) * p.n_tiles + nt] = best;
-                        p.argmax_idx[(grow0 + lane) * p.n_tiles + nt] = best_idx;
+                        p.argmax_val[(grow0 + lane) * p.n_tiles + nti] = best;
+                        p.argmax_idx[(grow0 + lane) * p.n_tiles + nti] = best_idx;
                     }
                 }
             } else {
@@ -462,7 +465,8 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
         p.m_tiles = (a.M / a.a_rows_per_batch) * ceil_div(a.a_rows_per_batch, kBM);
     else
         p.m_tiles = ceil_div(a.M, kBM);
-    p.n_tiles = ceil_div(a.N, BN);
+    p.n_tiles = a.n_tile_list ? a.n_tile_count : ceil_div(a.N, BN);
+    p.n_tile_list = a.n_tile_list;
     p.splits = a.splits > 1 ? a.splits : 1;
     p.kb_per_split = ceil_div(a.K / kBK, p.splits);
     p.splits = ceil_div(a.K / kBK, p.kb_per_split);          // drop empty trailing splits

@@ -50,6 +50,8 @@ struct GemmArgs {
     int splits = 1;                     // split-K factor (GEMM_OUT_F32 without bias only): partial plane s is
     int64_t split_stride = 0;           //   written at out + s * split_stride; see splitk_reduce_* below
     const unsigned char* row_skip = nullptr;   // optional [M] flags: flagged rows are not stored (GEMM_OUT_F32)
+    const int* n_tile_list = nullptr;   // optional device list of the n-tiles (of width block_n) to compute; the
+    int n_tile_count = 0;               //   arg-max partials are then [M][n_tile_count]
 };
 // effective number of partial planes gemm_bf16 will write for (K, splits)
 int gemm_effective_splits(int K, int splits);
