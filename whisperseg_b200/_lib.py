@@ -5,7 +5,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwsb.so")
+LIB_PATH = os.environ.get("WSB_LIB") or os.path.join(HERE, "libwsb.so")
 
 _lib = None
 _lock = threading.Lock()
