@@ -132,3 +132,19 @@ def test_cfg5_folder_mode_ragged_clips(tiny_checkpoint):
     many3 = seg.segment_many(clips[:5], sr, min_frequency=0, spec_time_step=sts, max_length=48, num_trials=3)
     for clip, got in zip(clips[:5], many3):
         assert got == seg.segment(clip, sr, min_frequency=0, spec_time_step=sts, num_trials=3, num_beams=1, max_length=48)
+
+
+def test_in_process_multi_device_fanout(tiny_checkpoint):
+    """device_ids=[0, 1]: the reference's thread-per-device fan-out inside one process (model.py:169-189).
+    Results must equal the single-device run (windows are independent)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import synth
+    from whisperseg_b200.segmenter import WhisperSegmenter
+    audio = synth.synth_audio(83.0, 16000, seed=31)
+    one = WhisperSegmenter(tiny_checkpoint[0], device="cuda", device_ids=[0], max_batch=8)
+    two = WhisperSegmenter(tiny_checkpoint[0], device="cuda", device_ids=[0, 1], max_batch=8)
+    a = one.segment(audio, 16000, min_frequency=0, spec_time_step=0.01, num_trials=2, num_beams=1, max_length=64)
+    b = two.segment(audio, 16000, min_frequency=0, spec_time_step=0.01, num_trials=2, num_beams=1, max_length=64)
+    assert a == b and len(a["onset"]) == len(a["cluster"])

@@ -222,10 +222,11 @@ int encoder_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T
     WSB_REQUIRE(T <= kAttKeys && T > 0, "encoder attention supports up to 512 positions");
     if (B <= 0) return 0;
     const int d = n_heads * kHd;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    int dev = 0;
+    if (once.need(&dev)) {
         WSB_CHECK_CUDA(cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
-        attr_set = true;
+        once.mark(dev);
     }
     CUtensorMap tm_q, tm_kv;
     uint64_t dims[3] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};

@@ -40,6 +40,21 @@ void count_launch(int n = 1);
 // of the previous one; every such kernel calls pdl_wait() before touching its inputs.
 extern thread_local bool g_use_pdl;
 
+// Per-device one-time kernel setup (cudaFuncSetAttribute is per device; a process may drive several GPUs
+// from different threads -- reference model.py:169-184 fans out one thread per device).
+struct PerDeviceOnce {
+    unsigned long long done = 0;      // bit d set: device d is configured (benign race: setting twice is harmless)
+    bool need(int* dev_out) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        *dev_out = dev;
+        return dev >= 64 || !((done >> dev) & 1ull);
+    }
+    void mark(int dev) {
+        if (dev < 64) done |= (1ull << dev);
+    }
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

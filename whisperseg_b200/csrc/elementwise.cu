@@ -297,11 +297,12 @@ int conv1_gelu(const float* feats, const float* wt, const float* b, __nv_bfloat1
                int64_t out_batch_stride, cudaStream_t stream) {
     WSB_REQUIRE(d % kC1TileC == 0, "d_model must be a multiple of 64");
     if (B <= 0) return 0;
-    static bool attr_set = false;
+    static PerDeviceOnce once;
+    int dev = 0;
     const size_t smem = sizeof(float) * (kC1In * (kC1TileT + 4) + kC1In * 3 * kC1TileC);
-    if (!attr_set) {
+    if (once.need(&dev)) {
         WSB_CHECK_CUDA(cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_set = true;
+        once.mark(dev);
     }
     dim3 grid(ceil_div(n_cols, kC1TileT), d / kC1TileC, B);
     conv1_kernel<<<grid, kC1Threads, smem, stream>>>(feats, wt, b, out, n_cols, d, out_batch_stride);

@@ -410,14 +410,13 @@ int gemm_n_tiles(int N, int block_n) { return ceil_div(N, block_n); }
 template <int BN, int EPI, int EPIW>
 static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, EPIW>;
-    static bool attr_set = false;
+    static PerDeviceOnce once;
     static int num_sms = 0;
-    if (!attr_set) {
+    int dev = 0;
+    if (once.need(&dev)) {
         WSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, EPI, EPIW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        int dev = 0;
-        WSB_CHECK_CUDA(cudaGetDevice(&dev));
         WSB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
+        once.mark(dev);
     }
     CUtensorMap tmA, tmB;
     {
