@@ -59,6 +59,10 @@ struct LogmelParams {
     int mel_nnz;
 };
 
+// padded index into a frame group's FFT buffer: the strided scatters of the early Stockham passes (stride 4,
+// 8, 16 complex elements) would otherwise hit the same banks 8-way
+__device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -68,10 +72,11 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 template <int LOG2M>
 struct FftCfg {
     static constexpr int M = 1 << LOG2M;
-    static constexpr int G = LOG2M <= 9 ? 32 : (32 << (LOG2M - 9));
+    static constexpr int G = LOG2M <= 9 ? 32 : LOG2M == 10 ? 64 : LOG2M == 11 ? 256 : 512;   // large FFTs: fewer, wider groups (smem)
     static constexpr int NB = M / (4 * G);
     static constexpr int NGROUPS = kLogmelThreads / G;
-    static constexpr int GROUP_FLOATS = 3 * M + 4;          // M complex points + (M+4) floats of power spectrum
+    static constexpr int MPAD = M + M / 16;                 // FFT buffer with one pad element per 16 (bank conflicts)
+    static constexpr int GROUP_FLOATS = 2 * MPAD + M + 4;   // padded complex points + (M+4) floats of power spectrum
     static constexpr int TW = 3 * M / 2;                    // twiddle table entries: exp(-2 pi i j / n_fft), j < 3 n_fft / 4
 };
 
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
     const int g = tid / G;
     const int gt = tid - g * G;
     float2* buf = reinterpret_cast<float2*>(s_fft + g * C::GROUP_FLOATS);
-    float* power = reinterpret_cast<float*>(buf + M);
+    float* power = reinterpret_cast<float*>(buf + C::MPAD);
     float vmax = -INFINITY, vmin = INFINITY;
     const int iters = (nf + C::NGROUPS - 1) / C::NGROUPS;
     constexpr int Q = M / 4;
@@ -195,11 +200,18 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
         // window + pack: z[j] = x[2j] w[2j] + i x[2j+1] w[2j+1]
         if (active) {
             const float* x = s_samples + fl * p.hop;
+            const bool x_aligned = ((fl * p.hop) & 1) == 0;       // warp-uniform
 #pragma unroll
             for (int i = 0; i < M / G; ++i) {
                 const int j = gt + i * G;
                 const float2 h = reinterpret_cast<const float2*>(hann)[j];
-                buf[j] = make_float2(x[2 * j] * h.x, x[2 * j + 1] * h.y);
+                float2 xv;
+                if (x_aligned) {
+                    xv = reinterpret_cast<const float2*>(x)[j];
+                } else {
+                    xv = make_float2(x[2 * j], x[2 * j + 1]);
+                }
+                buf[fpad(j)] = make_float2(xv.x * h.x, xv.y * h.y);
             }
         }
         group_sync<G>(g);
@@ -211,8 +223,8 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
 #pragma unroll
                 for (int i = 0; i < 2 * NB; ++i) {
                     const int j = gt + i * G;
-                    u[i][0] = buf[j];
-                    u[i][1] = buf[j + M / 2];
+                    u[i][0] = buf[fpad(j)];
+                    u[i][1] = buf[fpad(j + M / 2)];
                 }
             }
             group_sync<G>(g);
@@ -220,8 +232,8 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
 #pragma unroll
                 for (int i = 0; i < 2 * NB; ++i) {
                     const int j = gt + i * G;
-                    buf[2 * j] = make_float2(u[i][0].x + u[i][1].x, u[i][0].y + u[i][1].y);
-                    buf[2 * j + 1] = make_float2(u[i][0].x - u[i][1].x, u[i][0].y - u[i][1].y);
+                    buf[fpad(2 * j)] = make_float2(u[i][0].x + u[i][1].x, u[i][0].y + u[i][1].y);
+                    buf[fpad(2 * j + 1)] = make_float2(u[i][0].x - u[i][1].x, u[i][0].y - u[i][1].y);
                 }
             }
             group_sync<G>(g);
@@ -235,10 +247,10 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     const int j = gt + i * G;
-                    v[i][0] = buf[j];
-                    v[i][1] = buf[j + Q];
-                    v[i][2] = buf[j + 2 * Q];
-                    v[i][3] = buf[j + 3 * Q];
+                    v[i][0] = buf[fpad(j)];
+                    v[i][1] = buf[fpad(j + Q)];
+                    v[i][2] = buf[fpad(j + 2 * Q)];
+                    v[i][3] = buf[fpad(j + 3 * Q)];
                 }
             }
             group_sync<G>(g);
@@ -259,10 +271,10 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
                     const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
                     const float2 a3 = make_float2(v1.y - v3.y, v3.x - v1.x);       // (v1 - v3) * (-i)
                     const int j0 = ((j - k) << 2) + k;
-                    buf[j0] = make_float2(a0.x + a2.x, a0.y + a2.y);
-                    buf[j0 + ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
-                    buf[j0 + 2 * ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
-                    buf[j0 + 3 * ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
+                    buf[fpad(j0)] = make_float2(a0.x + a2.x, a0.y + a2.y);
+                    buf[fpad(j0 + ns)] = make_float2(a1.x + a3.x, a1.y + a3.y);
+                    buf[fpad(j0 + 2 * ns)] = make_float2(a0.x - a2.x, a0.y - a2.y);
+                    buf[fpad(j0 + 3 * ns)] = make_float2(a1.x - a3.x, a1.y - a3.y);
                 }
             }
             group_sync<G>(g);
@@ -273,8 +285,8 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
             for (int i = 0; i <= M / G; ++i) {
                 const int k = gt + i * G;
                 if (i < M / G || k == M) {
-                    const float2 zk = buf[k & (M - 1)];
-                    const float2 zm = buf[(M - k) & (M - 1)];
+                    const float2 zk = buf[fpad(k & (M - 1))];
+                    const float2 zm = buf[fpad((M - k) & (M - 1))];
                     const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
                     const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));   // (zk - conj zm)/(2i)
                     const float2 t = cmul(o, tw[k]);
@@ -367,7 +379,7 @@ static LogmelKernelFn pick_logmel_kernel(int log2m, bool smem_tables) {
         default: return nullptr;
     }
 }
-static int fft_group_threads(int log2m) { return log2m <= 9 ? 32 : (32 << (log2m - 9)); }
+static int fft_group_threads(int log2m) { return log2m <= 9 ? 32 : log2m == 10 ? 64 : log2m == 11 ? 256 : 512; }
 
 // ------------------------------------------------------------------------------------------- host
 static int ilog2(int v) {
@@ -437,7 +449,7 @@ int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float
     pl->group_threads = fft_group_threads(pl->log2m);
     pl->n_groups = kLogmelThreads / pl->group_threads;
     const size_t base_bytes = sizeof(float) * (static_cast<size_t>(pl->span_floats) + ((kMels * pl->tile_stride + 3) & ~3) +
-                                               static_cast<size_t>(pl->n_groups) * (3 * M + 4));
+                                               static_cast<size_t>(pl->n_groups) * (2 * (M + M / 16) + M + 4));
     const size_t table_bytes = sizeof(float) * (2 * static_cast<size_t>(n_tw) + n_fft + ((wts.size() + 3) & ~size_t(3)));
     const size_t static_bytes = 2048;                   // s_red, s_cluster_red, s_mel + margin
     pl->smem_tables = base_bytes + table_bytes + static_bytes <= static_cast<size_t>(max_smem);
