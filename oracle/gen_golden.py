@@ -23,7 +23,7 @@ ROOT = os.path.dirname(HERE)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 sys.path.insert(0, ROOT)
 
-from oracle import synth  # noqa: E402
+from tools import synth  # noqa: E402
 from oracle.ref_shim import GenerateAdapter, import_reference  # noqa: E402
 
 FRONTEND_CASES = [

@@ -20,7 +20,7 @@ def golden_dir():
 @pytest.fixture(scope="session")
 def tiny_checkpoint(tmp_path_factory):
     """Seeded shaped whisper-tiny-architecture checkpoint directory (HF layout) + the HF model."""
-    from oracle import synth
+    from tools import synth
     path = str(tmp_path_factory.mktemp("ckpt_tiny"))
     hf = synth.make_hf_model("tiny", seed=0, default_segmentation_config=dict(
         sr=16000, min_frequency=0, spec_time_step=0.01, species="human"))

@@ -13,7 +13,7 @@ BF16_MARGIN = 0.15
 
 
 def _segmenter(arch, max_batch, **kw):
-    from oracle import synth
+    from tools import synth
     from whisperseg_b200.segmenter import WhisperSegmenter
     state = synth.make_state(arch, seed=0, **kw)
     tokdir = tempfile.mkdtemp()
@@ -55,7 +55,7 @@ def test_cfg1_whisper_base_60s_16k():
     import torch
     from oracle import frontend_np as FO
     from oracle import postprocess_ref as PR
-    from oracle import synth
+    from tools import synth
     from whisperseg_b200.frontend import FrontendPlan, get_n_fft_given_sr
     seg, state = _segmenter("base", 8)
     audio = synth.synth_audio(60.0, 16000, seed=1)
@@ -80,7 +80,7 @@ def test_cfg1_whisper_base_60s_16k():
 def test_cfg2_whisper_large_two_windows():
     import torch
     from oracle import frontend_np as FO
-    from oracle import synth
+    from tools import synth
     seg, state = _segmenter("large", 4)
     audio = synth.synth_audio(5.0, 48000, seed=2)
     ref_feats = FO.sliced_audio_features(audio, 48000, 0, 0.0025, 1, dtype=np.float32)
@@ -95,7 +95,7 @@ def test_cfg2_whisper_large_two_windows():
 def test_cfg3_zebra_finch_three_trials(tiny_checkpoint):
     from oracle import frontend_np as FO
     from oracle import postprocess_ref as PR
-    from oracle import synth
+    from tools import synth
     from whisperseg_b200.frontend import FrontendPlan, get_n_fft_given_sr
     from whisperseg_b200.segmenter import WhisperSegmenter
     seg = WhisperSegmenter(tiny_checkpoint[0], device="cuda", device_ids=[0], max_batch=16)
@@ -116,7 +116,7 @@ def test_cfg3_zebra_finch_three_trials(tiny_checkpoint):
 
 
 def test_cfg5_folder_mode_ragged_clips(tiny_checkpoint):
-    from oracle import synth
+    from tools import synth
     from whisperseg_b200.segmenter import WhisperSegmenter
     seg = WhisperSegmenter(tiny_checkpoint[0], device="cuda", device_ids=[0], max_batch=8)
     sr, sts = 32000, 0.0025
@@ -140,7 +140,7 @@ def test_in_process_multi_device_fanout(tiny_checkpoint):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    from oracle import synth
+    from tools import synth
     from whisperseg_b200.segmenter import WhisperSegmenter
     audio = synth.synth_audio(83.0, 16000, seed=31)
     one = WhisperSegmenter(tiny_checkpoint[0], device="cuda", device_ids=[0], max_batch=8)

@@ -23,7 +23,7 @@ BF16_MARGIN = 0.15
 @pytest.fixture(scope="module")
 def setup(tiny_checkpoint):
     import torch
-    from oracle import synth
+    from tools import synth
     from oracle import frontend_np as FO
     from oracle.whisper_torch import oracle_from_hf
     from whisperseg_b200.segmenter import WhisperSegmenter
@@ -60,7 +60,7 @@ def test_encoder_matches_golden_probe(setup, golden_dir):
 
 def test_decoder_teacher_forced(setup):
     import torch
-    from oracle import synth
+    from tools import synth
     seg, orc, hf, x = setup["seg"], setup["orc"], setup["hf"], setup["x"]
     eng = seg.engines[0]
     tok = seg.tokenizer
@@ -142,7 +142,7 @@ def test_batch_compaction_equals_uncompacted(tiny_checkpoint, monkeypatch):
     """Gathering the still-active rows into a smaller batch (decode.cu: batch compaction) must not change
     a single token: 96 windows, most of which stop early, decoded with and without compaction."""
     import torch
-    from oracle import synth
+    from tools import synth
     from whisperseg_b200.frontend import FrontendPlan
     from whisperseg_b200.segmenter import WhisperSegmenter
     seg = WhisperSegmenter(tiny_checkpoint[0], device="cuda", device_ids=[0], max_batch=96)

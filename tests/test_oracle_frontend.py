@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import frontend_np as FO
-from oracle import synth
+from tools import synth
 from oracle.ref_shim import reference_available
 
 

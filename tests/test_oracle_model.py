@@ -11,7 +11,7 @@ import torch
 
 from oracle import frontend_np as FO
 from oracle import postprocess_ref as PR
-from oracle import synth
+from tools import synth
 from oracle.whisper_torch import WhisperOracle, oracle_from_hf
 
 

@@ -6,7 +6,7 @@ import tempfile
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import synth  # noqa: E402
+from tools import synth  # noqa: E402
 from whisperseg_b200.frontend import FrontendPlan  # noqa: E402
 from whisperseg_b200.segmenter import WhisperSegmenter  # noqa: E402
 

@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY -- seeded synthetic checkpoints, tokenizer and audio.
+"""BENCH / TEST DATA -- seeded synthetic checkpoints, tokenizer and audio (not part of the product,
+not part of the oracle: nothing here restates the reference's algorithm).
 
 There is no network, so neither the trained WhisperSeg checkpoints nor the Whisper tokenizer
 files exist here.  This module builds, deterministically from a seed:
@@ -247,12 +248,14 @@ def sinusoids(length, channels, max_timescale=10000):
 
 # per-architecture EOS boost: deeper networks need a larger one for rows to terminate (tuned on the GPU
 # with tools/tune_large.py: large/3.0 -> median 16, mean ~110 generated tokens, ~5 % of rows never stop)
+ARCH_EOS_RAMP = {"large": 0.1}
 ARCH_EOS_SCALE = {"tiny": 1.3, "base": 1.3, "small": 1.3, "large": 3.0}
 
 
 def make_state(arch="large", seed=0, n_digits=2, eos_scale=None, qk_cross=3.0, qk_self=2.0, emb_std=0.05,
                digit_scale=1.0, conv_gain=2.0, ts_step=25, n_allowed_digits=4, bias_std=0.02,
-               cancel_gelu_mean=True, dec_pos_std=2.0, cross_out_gain=2.0, calibrate=True, dtype=None):
+               cancel_gelu_mean=True, dec_pos_std=2.0, cross_out_gain=2.0, calibrate="auto", dtype=None,
+               eos_ramp=None, eos_ramp_start=10):
     """(config dict, state dict, generation dict) of a shaped random checkpoint -- same recipe as
     shape_weights_, HF parameter names, drawn tensor by tensor from one seeded CPU generator."""
     import torch
@@ -320,19 +323,52 @@ def make_state(arch="large", seed=0, n_digits=2, eos_scale=None, qk_cross=3.0, q
     ln("model.decoder.layer_norm")
     allowed = set(allowed_token_ids(ts_step, n_allowed_digits))
     gen = dict(suppress_tokens=[i for i in range(VOCAB_SIZE) if i not in allowed], begin_suppress_tokens=None)
+    # calibrate: "file" = committed vector under tools/calibration/ only (bench.py's GPU arm: no oracle
+    # code runs there); "auto" = that file when present, else one fp32 forward pass through the oracle
+    # network (tests); False = skip
     if calibrate:
-        calibrate_output_bias_(sd, H, L, sorted(allowed), seed)
+        path = calibration_path(arch, seed)
+        if os.path.isfile(path):
+            import torch
+            mean = torch.from_numpy(np.load(path))
+            sd["model.decoder.layer_norm.bias"] = sd["model.decoder.layer_norm.bias"].float() - mean
+        elif calibrate == "file":
+            raise FileNotFoundError("no committed calibration vector for (%s, seed %d): %s" % (arch, seed, path))
+        else:
+            calibrate_output_bias_(sd, H, L, sorted(allowed), seed)
+    if eos_ramp is None:
+        eos_ramp = ARCH_EOS_RAMP.get(arch, 0.0)
+    if eos_ramp:
+        sd["model.decoder.embed_positions.weight"] = sd["model.decoder.embed_positions.weight"] + eos_ramp_vectors(
+            sd["model.decoder.embed_tokens.weight"], eos_ramp, eos_ramp_start)
     return hf_config_dict(arch), sd, gen
 
 
-def calibrate_output_bias_(sd, n_heads, n_layers, allowed, seed, n_windows=2, n_positions=24):
+def eos_ramp_vectors(emb, eos_ramp, start=10):
+    """[448, d] term added to the decoder position table: eos_ramp * max(0, p - start) along the unit
+    EOS embedding.  It rides the residual stream into the tied output projection, so the EOS logit grows
+    linearly with the position and every row of a RANDOM checkpoint ends after a bounded number of
+    tokens -- as a trained segmenter's do (2.5 s windows hold ~8 segments = ~24 tokens).
+    Without it ~5 % of the rows never emit EOS and run to max_length."""
+    import torch
+    u = emb[ID_EOT].float()
+    u = u / u.norm()
+    ramp = torch.clamp(torch.arange(448, dtype=torch.float32) - float(start), min=0.0)
+    return eos_ramp * ramp[:, None] * u[None, :]
+
+
+def calibration_path(arch, seed):
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "calibration", "%s_seed%d.npy" % (arch, seed))
+
+
+def calibrate_output_bias_(sd, n_heads, n_layers, allowed, seed, n_windows=2, n_positions=24, return_mean=False):
     """Remove the position- and window-independent component of the decoder's final hidden state by
     folding its negative mean into `decoder.layer_norm.bias`.  A random deep network otherwise carries
     a large constant vector to the output projection and the same 3-4 tokens win every arg-max; with
     the bias calibrated the emitted tokens follow the audio (cross-attention) and the position."""
     import torch
-    from . import frontend_np as FO
-    from .whisper_torch import WhisperOracle
+    from oracle import frontend_np as FO
+    from oracle.whisper_torch import WhisperOracle
     audio = synth_audio(n_windows * 2.5, 32000, seed=9000 + seed)
     feats = FO.sliced_audio_features(audio, 32000, 0, 0.0025, 1, dtype=np.float32)
     x = torch.from_numpy(np.asarray([f[2] for f in feats]))
@@ -344,6 +380,7 @@ def calibrate_output_bias_(sd, n_heads, n_layers, allowed, seed, n_windows=2, n_
     hidden = orc.decode_logits(ids, enc=enc, return_hidden=True)
     mean = hidden[:, 3:].reshape(-1, hidden.shape[-1]).mean(dim=0)
     sd["model.decoder.layer_norm.bias"] = sd["model.decoder.layer_norm.bias"].float() - mean
+    return mean
 
 
 def token_table_files(path):

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import synth  # noqa: E402
+from tools import synth  # noqa: E402
 from whisperseg_b200 import postprocess as pp  # noqa: E402
 from whisperseg_b200.frontend import FrontendPlan  # noqa: E402
 from whisperseg_b200.segmenter import WhisperSegmenter  # noqa: E402
@@ -16,7 +16,7 @@ from whisperseg_b200.segmenter import WhisperSegmenter  # noqa: E402
 arch = sys.argv[1] if len(sys.argv) > 1 else "large"
 SR, STS = 48000, 0.0025
 n_win = 240
-state = synth.make_state(arch, seed=0, eos_scale=1.0)
+state = synth.make_state(arch, seed=0)
 tokdir = tempfile.mkdtemp()
 synth.token_table_files(tokdir)
 seg = WhisperSegmenter.from_state(state, tokdir, device="cuda", device_ids=[0], max_batch=n_win)
@@ -26,21 +26,21 @@ plan = FrontendPlan(SR, STS, 0)
 wins = plan.windows(len(audio), 1)
 feats = eng.features(plan, audio, wins)
 emb = eng.tensors["dec.emb"]
-base_eos = emb[synth.ID_EOT].clone()
-base_dig = emb[synth.ID_DIGIT0:synth.ID_DIGIT0 + 10].clone()
+pos = eng.tensors["dec.pos"]
+base_pos = pos.clone()
+u_eos = emb[synth.ID_EOT].float()
+u_eos = u_eos / u_eos.norm()
+ramp_pos = torch.clamp(torch.arange(pos.shape[0], device=pos.device, dtype=torch.float32) - 10.0, min=0.0)
 inv = {v: k for k, v in seg.cluster_codebook.items()}
-for eos_scale, digit_scale, n_digits in [(3.0, 1.0, 2), (4.0, 1.0, 2), (5.0, 1.0, 2), (6.0, 1.0, 2), (8.0, 1.0, 2)]:
-    emb[synth.ID_EOT] = (base_eos.float() * eos_scale).to(emb.dtype)
-    emb[synth.ID_DIGIT0:synth.ID_DIGIT0 + 10] = base_dig
-    emb[synth.ID_DIGIT0:synth.ID_DIGIT0 + n_digits] = (base_dig[:n_digits].float() * digit_scale).to(emb.dtype)
+for ramp in [0.0, 0.02, 0.05, 0.1, 0.2, 0.4]:
+    pos.copy_(base_pos + ramp * ramp_pos[:, None] * u_eos[None, :])
     eng.encode(feats)
     ids, n_steps = eng.generate(n_win, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, 448)
     ids = ids.cpu().numpy()
     lens = np.array([(row != tok.eos_token_id).sum() for row in ids])
     texts = tok.batch_decode(ids.tolist())
     nseg = sum(len(pp.segments_from_text(t, STS, inv)) for t in texts)
-    ndig = int(((ids >= synth.ID_DIGIT0) & (ids < synth.ID_DIGIT0 + 10)).sum())
     uniq = len({tuple(r[:8]) for r in ids.tolist()})
-    print("eos %.1f digit %.1f x%d: steps %3d  len mean %.1f median %.0f p95 %.0f max %d  zero-len %d  segments %d digits %d  distinct prefixes %d"
-          % (eos_scale, digit_scale, n_digits, n_steps, lens.mean(), np.median(lens), np.percentile(lens, 95), lens.max(),
-             int((lens == 0).sum()), nseg, ndig, uniq), flush=True)
+    print("eos ramp %.2f: steps %3d  len mean %.1f median %.0f p95 %.0f max %d  zero-len %d  segments %d  distinct prefixes %d"
+          % (ramp, n_steps, lens.mean(), np.median(lens), np.percentile(lens, 95), lens.max(), int((lens == 0).sum()), nseg, uniq),
+          flush=True)
