@@ -165,6 +165,27 @@ class WhisperOracle:
         return res
 
 
+def beam_search(orc, enc, prompt, eos_id, pad_id, max_length=448, num_beams=4, length_penalty=1.0,
+                suppress_tokens=None, begin_suppress_tokens=None, return_state=False):
+    """HF-equivalent beam search (oracle/beam_np.py) over the oracle network; int64 [B, n] (prompt stripped)."""
+    import numpy as np
+    from .beam_np import BeamState
+    B = enc.shape[0]
+    with torch.no_grad():
+        cross = [(k.repeat_interleave(num_beams, dim=0), v.repeat_interleave(num_beams, dim=0))
+                 for k, v in orc.cross_kv(enc)]
+        cache = [None] * orc.L
+        st = BeamState(B, num_beams, list(prompt), eos_id, pad_id, max_length, length_penalty)
+        cur = torch.tensor([list(prompt)] * (B * num_beams), dtype=torch.long)
+        while not st.finished:
+            logits = orc.decode_logits(cur, cross=cross, cache=cache)[:, -1, :].numpy()
+            parents = torch.from_numpy(st.step(logits, suppress_tokens, begin_suppress_tokens))
+            cache = [(k.index_select(0, parents), v.index_select(0, parents)) for k, v in cache]
+            cur = torch.from_numpy(st.rows_tokens()).view(-1, 1)
+    out = torch.from_numpy(st.result())
+    return (out, st) if return_state else out
+
+
 def oracle_from_hf(hf_model):
     cfg = hf_model.config
     return WhisperOracle(hf_model.state_dict(), cfg.encoder_attention_heads, cfg.encoder_layers)

@@ -115,3 +115,27 @@ def test_weight_preparation_layouts(tiny):
     L = cfg["encoder_layers"]
     assert t["dec.crosskv.w"].shape == (2 * L * d, d)
     assert (t["dec.suppress"] == 0).sum().item() == len(synth.allowed_token_ids())
+
+
+@pytest.mark.parametrize("eos_scale,length_penalty,max_length", [(1.0, 1.0, 48), (1.15, 1.0, 40), (1.15, 0.6, 40), (1.3, 2.0, 24)])
+def test_beam_oracle_matches_hf_generate(eos_scale, length_penalty, max_length):
+    """oracle/beam_np.py (HF beam search restated) against HF `generate(num_beams=4)` -- the reference's
+    default decode mode (model.py:409, 614).  HF strips the all-EOS tail column; tokens must be identical."""
+    from oracle.whisper_torch import beam_search
+    hf = synth.make_hf_model("tiny", seed=3, eos_scale=eos_scale)
+    orc = oracle_from_hf(hf)
+    audio = synth.synth_audio(15.0, 32000, seed=5)
+    feats = FO.sliced_audio_features(audio, 32000, 0, 0.0025, 1, dtype=np.float32)
+    x = torch.from_numpy(np.asarray([f[2] for f in feats]))
+    prompt = [synth.ID_SOT, synth.ID_EN, synth.ID_NOTIMESTAMPS]
+    with torch.no_grad():
+        out_hf = hf.generate(input_features=x, decoder_input_ids=torch.tensor([prompt] * x.shape[0]),
+                             pad_token_id=synth.ID_EOT, eos_token_id=synth.ID_EOT, max_length=max_length,
+                             num_beams=4, do_sample=False, length_penalty=length_penalty)
+    out, st = beam_search(orc, orc.encode(x), prompt, synth.ID_EOT, synth.ID_EOT, max_length, 4, length_penalty,
+                          hf.generation_config.suppress_tokens, hf.generation_config.begin_suppress_tokens,
+                          return_state=True)
+    n = min(out.shape[1], out_hf.shape[1])
+    assert n >= out.shape[1] - 1
+    assert torch.equal(out[:, :n], out_hf[:, :n])
+    assert (out[:, n:] == synth.ID_EOT).all()
