@@ -350,7 +350,7 @@ def run_ours(args):
 
     def e2e_step():
         if world > 1:
-            return segment_sharded(seg, full_audio, SR, MIN_FREQ, STS, max_length=args.max_length, num_trials=1)
+            return segment_sharded(seg, full_audio, SR, MIN_FREQ, STS, max_length=args.max_length, num_trials=1, num_beams=1)
         return seg.segment(piece, SR, MIN_FREQ, STS, max_length=args.max_length, num_trials=1, num_beams=1)
 
     e2e_step()

@@ -89,6 +89,26 @@ int wsb_generate(wsb_model* model, int batch, const int32_t* prompt, int prompt_
                  int max_length, const int32_t* forced_dev, int32_t* tokens_dev, int* n_steps, int flags,
                  void* stream);
 
+/* Beam search over the windows of the last wsb_encode call; replaces model.generate(..., num_beams=4,
+ * length_penalty=1.0) -- the reference's DEFAULT decode mode (reference model.py:409, 614, 662, 724) --
+ * with HF semantics (transformers generation/utils.py `_beam_search`, early_stopping=False): fp32
+ * log-softmax over the full vocabulary, then the suppression masks; 2*num_beams continuations per step;
+ * finished hypotheses scored sum_logprob / generated_len**length_penalty; the best one is returned.
+ * batch*num_beams <= max_batch, num_beams in [1,4].  tokens_dev: device int32 [batch][max_length -
+ * prompt_len] (EOS included, then pad_id); scores_dev: optional device float32 [batch] (score of the
+ * returned hypothesis).  flags: bit0 = replay the decode step from a CUDA graph.                      */
+int wsb_generate_beam(wsb_model* model, int batch, int num_beams, const int32_t* prompt, int prompt_len, int eos_id,
+                      int pad_id, int max_length, float length_penalty, int32_t* tokens_dev, float* scores_dev,
+                      int* n_steps, int flags, void* stream);
+
+/* The beam bookkeeping kernels alone, driven by caller-provided logits (parity tests): logits_dev float32
+ * [n_steps][batch*num_beams][vocab], suppress_dev float32 [vocab] additive mask.  Outputs as
+ * wsb_generate_beam plus, per step, the parent row of every surviving beam (parents_dev int32
+ * [n_steps][batch*num_beams]) and its token (next_tokens_dev, same shape); both optional.           */
+int wsb_beam_selftest(int batch, int num_beams, int vocab, int n_steps, const float* logits_dev, const float* suppress_dev,
+                      const int32_t* prompt, int prompt_len, int eos_id, int pad_id, int max_length, float length_penalty,
+                      int32_t* tokens_dev, float* scores_dev, int32_t* parents_dev, int32_t* next_tokens_dev, void* stream);
+
 /* ---- CUDA-event profiling of kernel classes (bench.py's roofline numbers) -----------------------
  * While enabled, every eagerly launched kernel is bracketed by CUDA events on its own stream.
  * categories: 0 conv1, 1 encoder GEMMs (conv2, qkv, out, fc1, fc2), 2 encoder attention,

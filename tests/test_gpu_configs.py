@@ -124,12 +124,12 @@ def test_cfg5_folder_mode_ragged_clips(tiny_checkpoint):
     clips = [synth.synth_audio(float(rng.uniform(0.5, 6.0)), sr, seed=50 + i) for i in range(12)]
     clips.append(np.zeros(0, np.float32))
     clips.append(synth.synth_audio(0.013, sr, seed=99))
-    many = seg.segment_many(clips, sr, min_frequency=0, spec_time_step=sts, max_length=48)
+    many = seg.segment_many(clips, sr, min_frequency=0, spec_time_step=sts, max_length=48, num_beams=1)
     assert len(many) == len(clips)
     for clip, got in zip(clips, many):
         one = seg.segment(clip, sr, min_frequency=0, spec_time_step=sts, num_trials=1, num_beams=1, max_length=48)
         assert got == one
-    many3 = seg.segment_many(clips[:5], sr, min_frequency=0, spec_time_step=sts, max_length=48, num_trials=3)
+    many3 = seg.segment_many(clips[:5], sr, min_frequency=0, spec_time_step=sts, max_length=48, num_trials=3, num_beams=1)
     for clip, got in zip(clips[:5], many3):
         assert got == seg.segment(clip, sr, min_frequency=0, spec_time_step=sts, num_trials=3, num_beams=1, max_length=48)
 

@@ -45,8 +45,14 @@ struct DaParams {
     long long split_stride;
     int part_ld;
     const float* bias;            // [part_ld]
+    // beam search: rows sharing a cross K/V block; self-attention ancestry tables [2][B][anc_ld]
+    int kv_div;
+    const int* anc;
+    int anc_ld;
+    long long anc_buf_stride;
 };
 
+template <bool kAnc>
 __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaParams p) {
     const int h = blockIdx.x, b = blockIdx.y;
     pdl_wait();
@@ -54,11 +60,12 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaPa
     if (p.finished && p.finished[b]) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     __shared__ float s_q[64];
+    __shared__ int s_src[kAnc ? kDaMaxKeys : 1];
     __shared__ float s_p[kDaThreads / 32];
     __shared__ float s_red[kDaThreads / 32];
     __shared__ float s_out[kDaThreads / 32][64];
 
-    const long long blk = static_cast<long long>(b) * p.b_stride + static_cast<long long>(h) * p.bh_stride;
+    const long long blk = static_cast<long long>(p.self_mode ? b : b / p.kv_div) * p.b_stride + static_cast<long long>(h) * p.bh_stride;
     const __nv_bfloat16* K = p.k_base + blk;
     const __nv_bfloat16* V = p.v_base + blk;
     int n_keys;
@@ -73,6 +80,10 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaPa
     if (p.self_mode) {
         const int pos = p.pos_offset + *p.step_ptr;
         n_keys = pos + 1;
+        if constexpr (kAnc) {
+            const int* a = p.anc + (pos & 1) * p.anc_buf_stride + static_cast<long long>(b) * p.anc_ld;
+            for (int j = tid; j <= pos; j += kDaThreads) s_src[j] = (j == pos) ? b : a[j];
+        }
         if (tid < 64) {
             const float kv = proj(p.d + h * 64 + tid, p.new_k);
             p.k_cache[blk + static_cast<long long>(pos) * 64 + tid] = __float2bfloat16(kv);
@@ -108,8 +119,10 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaPa
             const int j = j0 + u * kStep + sub;
             ok[u] = j < n_keys;
             if (ok[u]) {
-                kraw[u] = *reinterpret_cast<const uint4*>(K + static_cast<long long>(j) * 64 + ch * 8);
-                vraw[u] = *reinterpret_cast<const uint4*>(V + static_cast<long long>(j) * 64 + ch * 8);
+                long long off = static_cast<long long>(j) * 64 + ch * 8;
+                if constexpr (kAnc) off += static_cast<long long>(s_src[j] - b) * p.b_stride;
+                kraw[u] = *reinterpret_cast<const uint4*>(K + off);
+                vraw[u] = *reinterpret_cast<const uint4*>(V + off);
             }
         }
 #pragma unroll
@@ -182,7 +195,8 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaPa
 
 int decode_self_attention(const __nv_bfloat16* qkv, const SplitkInput* part, int d, __nv_bfloat16* k_cache,
                           __nv_bfloat16* v_cache, int t_max, const int* step_ptr, int pos_offset,
-                          const unsigned char* finished, __nv_bfloat16* out, int B, int n_heads, cudaStream_t stream) {
+                          const unsigned char* finished, __nv_bfloat16* out, int B, int n_heads, cudaStream_t stream,
+                          const int* anc, int anc_ld) {
     WSB_REQUIRE(t_max <= kDaMaxKeys, "self-attention cache longer than 512 positions");
     if (B <= 0) return 0;
     DaParams p;
@@ -208,14 +222,23 @@ int decode_self_attention(const __nv_bfloat16* qkv, const SplitkInput* part, int
     p.split_stride = part ? part->split_stride : 0;
     p.part_ld = 3 * d;
     p.bias = part ? part->bias : nullptr;
-    WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel, dim3(n_heads, B), dim3(kDaThreads), 0, stream, p));
+    p.kv_div = 1;
+    p.anc = anc;
+    p.anc_ld = anc_ld;
+    p.anc_buf_stride = static_cast<long long>(B) * anc_ld;
+    if (anc) {
+        WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel<true>, dim3(n_heads, B), dim3(kDaThreads), 0, stream, p));
+        count_launch();
+        return 0;
+    }
+    WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel<false>, dim3(n_heads, B), dim3(kDaThreads), 0, stream, p));
     count_launch();
     return 0;
 }
 
 int decode_cross_attention(const __nv_bfloat16* q, const SplitkInput* part, int d, const __nv_bfloat16* cross_kv, int layer,
                            int n_layers, int T, const unsigned char* finished, __nv_bfloat16* out, int B, int n_heads,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, int kv_div) {
     WSB_REQUIRE(T <= kDaMaxKeys, "cross-attention over more than 512 encoder positions");
     if (B <= 0) return 0;
     // cross_kv layout (written by the head-major GEMM epilogue): [b][layer][k|v][head][T][64]
@@ -243,7 +266,11 @@ int decode_cross_attention(const __nv_bfloat16* q, const SplitkInput* part, int 
     p.split_stride = part ? part->split_stride : 0;
     p.part_ld = d;
     p.bias = part ? part->bias : nullptr;
-    WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel, dim3(n_heads, B), dim3(kDaThreads), 0, stream, p));
+    p.kv_div = kv_div < 1 ? 1 : kv_div;
+    p.anc = nullptr;
+    p.anc_ld = 0;
+    p.anc_buf_stride = 0;
+    WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel<false>, dim3(n_heads, B), dim3(kDaThreads), 0, stream, p));
     count_launch();
     return 0;
 }
@@ -308,6 +335,12 @@ __global__ void step_increment_kernel(int* step_ptr) {
     pdl_wait();
     pdl_launch_dependents();
     *step_ptr += 1;
+}
+
+int step_increment(int* step_ptr, cudaStream_t stream) {
+    WSB_CHECK_CUDA(launch_kernel(step_increment_kernel, dim3(1), dim3(1), 0, stream, step_ptr));
+    count_launch();
+    return 0;
 }
 
 int argmax_finalize(const float* val, const int* idx, int n_tiles, int* tokens_out, int max_new, int out_offset,

@@ -9,6 +9,7 @@
 #include "../../include/wsb.h"
 
 #include <algorithm>
+#include <cstring>
 #include <atomic>
 #include <map>
 #include <tuple>
@@ -137,6 +138,12 @@ struct Model {
     std::map<std::tuple<int, int, int, int, int, int, int>, GraphEntry> graphs;
     bool use_pdl = false;
     int* pinned_active = nullptr;
+    // beam search workspace (allocated on first use): raw logits [max_batch][ldv] + BeamState arrays
+    char* beam_ws = nullptr;
+    float* beam_logits = nullptr;
+    long long beam_ldv = 0;
+    BeamState beam;
+    std::map<std::tuple<int, int, int, int, int, int, int>, GraphEntry> beam_graphs;
 };
 
 constexpr int kCompactRows = 64;        // first compaction level; the second level (16 rows) reuses the main buffers
@@ -150,6 +157,9 @@ struct DecState {
     int* next_token;
     unsigned char* finished;
     const int* row_map;                 // slot -> window index of this generate() call (null = identity)
+    int kv_div = 1;                     // beam search: rows per window (shared cross-attention K/V block)
+    const int* anc = nullptr;           // beam search: K/V-cache ancestry tables
+    int anc_ld = 0;
 };
 
 template <typename T>
@@ -310,6 +320,8 @@ static int model_create(const wsb_model_config* cfg, const char* const* names, c
 static void model_destroy(Model* m) {
     if (!m) return;
     for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
+    for (auto& kv : m->beam_graphs) cudaGraphExecDestroy(kv.second.exec);
+    cudaFree(m->beam_ws);
     cudaFree(m->ws);
     cudaFree(m->logit_tiles);
     cudaFreeHost(m->pinned_active);
@@ -437,9 +449,11 @@ static int skinny_linear(Model* m, const __nv_bfloat16* A, const __nv_bfloat16* 
     return splitk_reduce_resid_ln(m->dpart, eff, plane, B, N, bias, x, gamma, beta, xn, row_skip, s);
 }
 
-// one decoder position for all rows.  with_logits: project + arg-max + finalize; else prefill advance.
+// one decoder position for all rows.  with_logits: project + arg-max + finalize (or, with `beam`, raw logits +
+// beam bookkeeping); else prefill advance.
 static int decode_step(Model* m, const DecState& st, bool with_logits, bool first_generated, int prompt_len, int max_new,
-                       const int* forced, int forced_ld, int eos_id, int pad_id, cudaStream_t s) {
+                       const int* forced, int forced_ld, int eos_id, int pad_id, cudaStream_t s,
+                       const BeamState* beam = nullptr) {
     const wsb_model_config& c = m->cfg;
     const int B = st.B;
     const int d = c.d_model, F = c.ffn_dim, L = c.n_layers, H = c.n_heads, T = m->T, tmax = c.max_target_positions;
@@ -465,19 +479,39 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
         {
             ProfScope ps(PROF_DEC_SELF_ATTN, 0.0, s);
             WSB_RUN(decode_self_attention(nullptr, &part, d, st.k_cache + l * cache_l, st.v_cache + l * cache_l, tmax, m->step, 0,
-                                          fin, m->datt, B, H, s));
+                                          fin, m->datt, B, H, s, st.anc, st.anc_ld));
         }
         WSB_RUN(skinny_linear(m, m->datt, e.so_w, e.so_b, B, d, d, 0, nullptr, m->dx, e.ln2_g, e.ln2_b, m->dxn, s, fin));
         WSB_RUN(skinny_linear(m, m->dxn, e.cq_w, e.cq_b, B, d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, fin, &part));
         {
             ProfScope ps(PROF_DEC_CROSS_ATTN, 4.0 * B * H * T * 64.0, s);   // bytes: K and V blocks, bf16
-            WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s));
+            WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s, st.kv_div));
         }
         WSB_RUN(skinny_linear(m, m->datt, e.co_w, e.co_b, B, d, d, 0, nullptr, m->dx, e.ln3_g, e.ln3_b, m->dxn, s, fin));
         WSB_RUN(skinny_linear(m, m->dxn, e.fc1_w, e.fc1_b, B, F, d, 1, m->dff, nullptr, nullptr, nullptr, nullptr, s, fin));
         WSB_RUN(skinny_linear(m, m->dff, e.fc2_w, e.fc2_b, B, d, F, 0, nullptr, m->dx, next_g, next_b, m->dxn, s, fin));
     }
     if (!with_logits) return prefill_advance(st.next_token, forced, forced_ld, m->prompt_dev, m->step, B, s);
+    if (beam) {
+        // raw logits of every row (the log-softmax runs over the full vocabulary, before the suppression masks)
+        GemmArgs g;
+        g.A = m->dxn;
+        g.lda = d;
+        g.W = m->dec_emb;
+        g.M = B;
+        g.N = c.vocab_size;
+        g.K = d;
+        g.out = m->beam_logits;
+        g.ldc = m->beam_ldv;
+        g.out_mode = GEMM_OUT_F32;
+        g.row_skip = fin;
+        {
+            ProfScope ps(PROF_DEC_LOGITS, 2.0 * B * c.vocab_size * d, s);
+            WSB_RUN(gemm_bf16(g, s));
+        }
+        WSB_RUN(beam_step(*beam, s));
+        return step_increment(m->step, s);
+    }
     GemmArgs g;
     g.A = m->dxn;
     g.lda = d;
@@ -655,6 +689,128 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     return 0;
 }
 
+// Beam search over `B` windows x `nb` beams (rows = B*nb <= max_batch): the reference's default decode mode
+// (HF generate(num_beams=4, length_penalty), reference model.py:409, 614, 662).  See beam.cu.
+static int generate_beam(Model* m, int B, int nb, const int* prompt, int prompt_len, int eos_id, int pad_id, int max_length,
+                         float length_penalty, int* tokens_out, float* scores_out, int* n_steps, int flags, cudaStream_t s) {
+    const wsb_model_config& c = m->cfg;
+    WSB_REQUIRE(nb >= 1 && nb <= 4, "num_beams in [1,4]");
+    const int R = B * nb;
+    WSB_REQUIRE(B >= 1 && R <= c.max_batch && B == m->last_batch, "wsb_generate_beam must follow wsb_encode with batch*num_beams <= max_batch");
+    WSB_REQUIRE(prompt_len >= 1 && prompt_len <= 16, "prompt length in [1,16]");
+    WSB_REQUIRE(max_length > prompt_len && max_length <= c.max_target_positions, "max_length in (prompt_len, max_target_positions]");
+    const int d = c.d_model, L = c.n_layers, T = m->T, rows = B * T;
+    const int max_new = max_length - prompt_len;
+    m->use_pdl = false;
+    if (!m->beam_ws) {
+        m->beam_ldv = (c.vocab_size + 7) & ~7;
+        const size_t logits_bytes = (static_cast<size_t>(c.max_batch) * m->beam_ldv * sizeof(float) + 255) & ~size_t(255);
+        WSB_CHECK_CUDA(cudaMalloc(&m->beam_ws, logits_bytes + beam_state_bytes(c.max_batch, c.max_target_positions)));
+        m->beam_logits = reinterpret_cast<float*>(m->beam_ws);
+        beam_state_carve(&m->beam, m->beam_ws + logits_bytes, c.max_batch, c.max_target_positions);
+    }
+    {   // cross-attention K/V once per window (shared by its beams)
+        GemmArgs g;
+        g.A = m->enc_out;
+        g.lda = d;
+        g.W = m->crosskv_w;
+        g.M = rows;
+        g.N = 2 * L * d;
+        g.K = d;
+        g.bias = m->crosskv_b;
+        g.out = m->cross_kv;
+        g.out_mode = GEMM_OUT_HEADMAJOR;
+        g.rows_per_batch = T;
+        ProfScope ps(PROF_CROSSKV_GEMM, 2.0 * rows * 2.0 * L * d * d, s);
+        WSB_RUN(gemm_bf16(g, s));
+    }
+    BeamState& bs = m->beam;
+    bs.B = B;
+    bs.nb = nb;
+    bs.K = 2 * nb;
+    bs.V = c.vocab_size;
+    bs.ldv = m->beam_ldv;
+    bs.max_length = max_length;
+    bs.prompt_len = prompt_len;
+    bs.eos_id = eos_id;
+    bs.pad_id = pad_id;
+    bs.logits = m->beam_logits;
+    bs.suppress = m->suppress;
+    bs.begin_suppress = m->begin_suppress;
+    bs.next_token = m->next_token;
+    bs.finished = m->finished;
+    bs.step_ptr = m->step;
+    bs.n_active = m->n_active;
+    WSB_CHECK_CUDA(cudaMemcpyAsync(m->prompt_dev, prompt, sizeof(int) * prompt_len, cudaMemcpyHostToDevice, s));
+    WSB_CHECK_CUDA(cudaMemsetAsync(m->step, 0, sizeof(int) * 4, s));
+    WSB_CHECK_CUDA(cudaMemcpyAsync(m->n_active, &B, sizeof(int), cudaMemcpyHostToDevice, s));
+    WSB_RUN(beam_set_length_penalty(bs, length_penalty, max_length, s));      // synchronises: prompt / B are temporaries
+    WSB_RUN(beam_init(bs, m->prompt_dev, s));
+    DecState st;
+    st.B = R;
+    st.buffer_id = 0;
+    st.k_cache = m->k_cache;
+    st.v_cache = m->v_cache;
+    st.cross_kv = m->cross_kv;
+    st.next_token = m->next_token;
+    st.finished = m->finished;
+    st.row_map = nullptr;
+    st.kv_div = nb;
+    st.anc = bs.anc;
+    st.anc_ld = bs.seq_ld;
+    for (int pos = 0; pos + 1 < prompt_len; ++pos)
+        WSB_RUN(decode_step(m, st, false, false, prompt_len, max_new, nullptr, max_length, eos_id, pad_id, s));
+    WSB_RUN(decode_step(m, st, true, true, prompt_len, max_new, nullptr, max_length, eos_id, pad_id, s, &bs));
+    int steps_done = 1;
+    const bool use_graph = (flags & 1) != 0 && max_new > 2;
+    Model::GraphEntry* graph = nullptr;
+    if (use_graph) {
+        int lp_bits;
+        static_assert(sizeof(int) == sizeof(float), "float bits");
+        memcpy(&lp_bits, &length_penalty, sizeof(int));
+        (void)lp_bits;                                      // the penalty lives in a device table, not in the launches
+        const auto key = std::make_tuple(B, nb, max_length, prompt_len, eos_id, pad_id, 0);
+        auto it = m->beam_graphs.find(key);
+        if (it == m->beam_graphs.end()) {
+            cudaGraph_t g = nullptr;
+            WSB_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            g_capturing = true;
+            const long long before = g_launches.load();
+            int rc = decode_step(m, st, true, false, prompt_len, max_new, nullptr, max_length, eos_id, pad_id, s, &bs);
+            const int kernels = static_cast<int>(g_launches.load() - before);
+            g_launches.store(before);
+            g_capturing = false;
+            cudaError_t ce = cudaStreamEndCapture(s, &g);
+            if (rc) return rc;
+            WSB_CHECK_CUDA(ce);
+            Model::GraphEntry entry;
+            entry.kernels = kernels;
+            WSB_CHECK_CUDA(cudaGraphInstantiate(&entry.exec, g, 0));
+            cudaGraphDestroy(g);
+            it = m->beam_graphs.emplace(key, entry).first;
+        }
+        graph = &it->second;
+    }
+    const int check_every = 8;
+    while (steps_done < max_new) {
+        if (use_graph) {
+            WSB_CHECK_CUDA(cudaGraphLaunch(graph->exec, s));
+            count_launch(graph->kernels);
+        } else {
+            WSB_RUN(decode_step(m, st, true, false, prompt_len, max_new, nullptr, max_length, eos_id, pad_id, s, &bs));
+        }
+        ++steps_done;
+        if ((steps_done % check_every) == 0 && steps_done < max_new) {
+            WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active, m->n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+            WSB_CHECK_CUDA(cudaStreamSynchronize(s));
+            if (m->pinned_active[0] <= 0) break;
+        }
+    }
+    WSB_RUN(beam_output(bs, tokens_out, scores_out, max_new, s));
+    if (n_steps) *n_steps = steps_done;
+    return 0;
+}
+
 }  // namespace wsb
 
 // =============================================================================================== C ABI
@@ -723,6 +879,73 @@ int wsb_generate(wsb_model* model, int batch, const int32_t* prompt, int prompt_
     WSB_REQUIRE(model != nullptr && prompt != nullptr && tokens_dev != nullptr, "null argument");
     return generate(model->impl, batch, prompt, prompt_len, eos_id, pad_id, max_length, forced_dev, tokens_dev, n_steps,
                     flags, static_cast<cudaStream_t>(stream));
+}
+
+int wsb_generate_beam(wsb_model* model, int batch, int num_beams, const int32_t* prompt, int prompt_len, int eos_id,
+                      int pad_id, int max_length, float length_penalty, int32_t* tokens_dev, float* scores_dev, int* n_steps,
+                      int flags, void* stream) {
+    WSB_REQUIRE(model != nullptr && prompt != nullptr && tokens_dev != nullptr, "null argument");
+    return generate_beam(model->impl, batch, num_beams, prompt, prompt_len, eos_id, pad_id, max_length, length_penalty,
+                         tokens_dev, scores_dev, n_steps, flags, static_cast<cudaStream_t>(stream));
+}
+
+int wsb_beam_selftest(int batch, int num_beams, int vocab, int n_steps, const float* logits_dev, const float* suppress_dev,
+                      const int32_t* prompt, int prompt_len, int eos_id, int pad_id, int max_length, float length_penalty,
+                      int32_t* tokens_dev, float* scores_dev, int32_t* parents_dev, int32_t* next_tokens_dev, void* stream) {
+    WSB_REQUIRE(logits_dev && suppress_dev && prompt && tokens_dev, "null argument");
+    WSB_REQUIRE(num_beams >= 1 && num_beams <= 4 && batch >= 1, "num_beams in [1,4]");
+    WSB_REQUIRE(prompt_len >= 1 && prompt_len <= 16 && max_length > prompt_len && max_length <= 512, "bad lengths");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int R = batch * num_beams, ld = max_length;
+    char* ws = nullptr;
+    const size_t extra = 4096 + static_cast<size_t>(R) * 8;
+    WSB_CHECK_CUDA(cudaMalloc(&ws, beam_state_bytes(R, ld) + extra));
+    struct Free {
+        char* p;
+        ~Free() { cudaFree(p); }
+    } guard{ws};
+    BeamState bs;
+    int* step = reinterpret_cast<int*>(ws);
+    int* n_active = step + 4;
+    int* prompt_dev = step + 8;
+    bs.next_token = reinterpret_cast<int*>(ws + 1024);
+    bs.finished = reinterpret_cast<unsigned char*>(ws + 1024 + static_cast<size_t>(R) * 4);
+    beam_state_carve(&bs, ws + ((extra + 255) & ~size_t(255)), R, ld);
+    bs.B = batch;
+    bs.nb = num_beams;
+    bs.K = 2 * num_beams;
+    bs.V = vocab;
+    bs.ldv = vocab;
+    bs.max_length = max_length;
+    bs.prompt_len = prompt_len;
+    bs.eos_id = eos_id;
+    bs.pad_id = pad_id;
+    bs.suppress = suppress_dev;
+    bs.begin_suppress = nullptr;
+    bs.step_ptr = step;
+    bs.n_active = n_active;
+    const int start = prompt_len - 1;
+    WSB_CHECK_CUDA(cudaMemcpyAsync(prompt_dev, prompt, sizeof(int) * prompt_len, cudaMemcpyHostToDevice, s));
+    WSB_CHECK_CUDA(cudaMemcpyAsync(step, &start, sizeof(int), cudaMemcpyHostToDevice, s));
+    WSB_CHECK_CUDA(cudaMemcpyAsync(n_active, &batch, sizeof(int), cudaMemcpyHostToDevice, s));
+    WSB_RUN(beam_set_length_penalty(bs, length_penalty, max_length, s));
+    WSB_RUN(beam_init(bs, prompt_dev, s));
+    for (int t = 0; t < n_steps && prompt_len + t < max_length; ++t) {
+        bs.logits = logits_dev + static_cast<size_t>(t) * R * vocab;
+        WSB_RUN(beam_step(bs, s));
+        const int pos = start + t, nbuf = (pos & 1) ^ 1;
+        if (parents_dev)
+            WSB_CHECK_CUDA(cudaMemcpy2DAsync(parents_dev + static_cast<size_t>(t) * R, sizeof(int),
+                                             bs.anc + static_cast<size_t>(nbuf) * R * ld + pos, sizeof(int) * ld, sizeof(int), R,
+                                             cudaMemcpyDeviceToDevice, s));
+        if (next_tokens_dev)
+            WSB_CHECK_CUDA(cudaMemcpyAsync(next_tokens_dev + static_cast<size_t>(t) * R, bs.next_token, sizeof(int) * R,
+                                           cudaMemcpyDeviceToDevice, s));
+        WSB_RUN(step_increment(step, s));
+    }
+    WSB_RUN(beam_output(bs, tokens_dev, scores_dev, max_length - prompt_len, s));
+    WSB_CHECK_CUDA(cudaStreamSynchronize(s));
+    return 0;
 }
 
 int wsb_profile_enable(int enable) {

@@ -47,7 +47,7 @@ def local_slice(audio, windows, clip_len):
 
 def segment_sharded(segmenter, audio, sr, min_frequency=None, spec_time_step=None, min_segment_length=None, eps=None,
                     time_per_frame_for_voting=None, consolidation_method="clustering", max_length=448, num_trials=1,
-                    group=None, generate_fn=None):
+                    group=None, generate_fn=None, num_beams=4, length_penalty=1.0):
     """Drop-in for `segmenter.segment(...)` under torch.distributed: same result on every rank.
 
     `generate_fn(windows, plan, audio_slice, slice_start) -> int32 tensor [n_local, max_new]` can be
@@ -74,7 +74,7 @@ def segment_sharded(segmenter, audio, sr, min_frequency=None, spec_time_step=Non
     max_new = max_length - len(tok.prompt_ids)
     s0, piece = local_slice(audio, mine, plan.clip_len)
     if generate_fn is None:
-        local_ids = _engine_generate(segmenter, plan, mine, piece, s0, len(audio), max_length)
+        local_ids = _engine_generate(segmenter, plan, mine, piece, s0, len(audio), max_length, num_beams, length_penalty)
     else:
         local_ids = generate_fn(mine, plan, piece, s0)
     gathered = all_gather_tokens(local_ids, per, max_new, tok.pad_token_id, group)
@@ -89,7 +89,7 @@ def segment_sharded(segmenter, audio, sr, min_frequency=None, spec_time_step=Non
     return pp.correct_fft_blur_and_dedupe(pred, sr, get_n_fft_given_sr(sr))
 
 
-def _engine_generate(segmenter, plan, windows, piece, slice_start, n_total, max_length):
+def _engine_generate(segmenter, plan, windows, piece, slice_start, n_total, max_length, num_beams=1, length_penalty=1.0):
     eng = segmenter.engines[0]
     tok = segmenter.tokenizer
     max_new = max_length - len(tok.prompt_ids)
@@ -97,9 +97,16 @@ def _engine_generate(segmenter, plan, windows, piece, slice_start, n_total, max_
         return torch.zeros((0, max_new), dtype=torch.int32, device=eng.device)
     feats = eng.features_sliced(plan, piece, windows, slice_start, n_total)
     outs = []
-    for pos in range(0, len(windows), eng.max_batch):
-        chunk = feats[pos:pos + eng.max_batch].contiguous()
+    if not 1 <= int(num_beams) <= 4:
+        raise ValueError("whisperseg_b200 supports num_beams in [1, 4], got %r" % (num_beams,))
+    per_call = eng.max_batch if num_beams == 1 else max(1, eng.max_batch // num_beams)
+    for pos in range(0, len(windows), per_call):
+        chunk = feats[pos:pos + per_call].contiguous()
         eng.encode(chunk)
-        ids, _ = eng.generate(chunk.shape[0], tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length)
+        if num_beams == 1:
+            ids, _ = eng.generate(chunk.shape[0], tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length)
+        else:
+            ids, _ = eng.generate_beam(chunk.shape[0], int(num_beams), tok.prompt_ids, tok.eos_token_id, tok.pad_token_id,
+                                       max_length, length_penalty)
         outs.append(ids)
     return torch.cat(outs, 0)

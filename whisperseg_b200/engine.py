@@ -122,6 +122,27 @@ class Engine:
             self._exit()
         return tokens, n_steps.value
 
+    def generate_beam(self, batch, num_beams, prompt_ids, eos_id, pad_id, max_length, length_penalty=1.0,
+                      use_graph=True, return_scores=False):
+        """HF-equivalent beam search (reference default num_beams=4, model.py:409/662): best hypothesis per
+        window, int32 [batch, max_length - len(prompt)] (device), and #positions computed.
+        batch * num_beams must not exceed the engine's max_batch."""
+        n_new = max_length - len(prompt_ids)
+        tokens = torch.empty((batch, n_new), dtype=torch.int32, device=self.device)
+        scores = torch.empty((batch,), dtype=torch.float32, device=self.device)
+        prompt = (ctypes.c_int32 * len(prompt_ids))(*prompt_ids)
+        n_steps = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            self._enter()
+            _lib.check(self.lib.wsb_generate_beam(self.handle, batch, num_beams, prompt, len(prompt_ids), eos_id, pad_id,
+                                                  max_length, ctypes.c_float(length_penalty), _ptr(tokens), _ptr(scores),
+                                                  ctypes.byref(n_steps), 1 if use_graph else 0,
+                                                  ctypes.c_void_p(self.stream.cuda_stream)), "wsb_generate_beam")
+            self._exit()
+        if return_scores:
+            return tokens, n_steps.value, scores
+        return tokens, n_steps.value
+
     def features(self, fp: FrontendPlan, audio, windows):
         """Host float32 audio + window list -> device features (H2D through pinned memory)."""
         return self.features_sliced(fp, audio, windows, 0, len(audio))

@@ -14,8 +14,9 @@ Design differences (B200-first):
     over windows on the CPU, model.py:146-165); features never leave HBM;
   * windows are independent, so `batch_size` only bounds memory: the engine decodes up to
     `max_batch` windows together whatever `batch_size` says (results do not depend on batching);
-  * decoding is greedy: `num_beams` is accepted for signature compatibility, values != 1 fall
-    back to greedy with a one-time warning (BASELINE.json north_star; beam search is row "next").
+  * `num_beams=1` decodes greedily (BASELINE.json north_star); `num_beams` 2..4 -- the reference default
+    is 4 -- runs HF-equivalent beam search on the device (csrc/beam.cu), `length_penalty` honoured;
+    `top_k` / `top_p` only matter for sampling and the reference always passes top_k=1.
 """
 import json
 import os
@@ -82,29 +83,35 @@ class SegmenterBase:
         feats = eng.features(plan, audio, wins)
         return [(w.trial_id, w.offset_time, feats[i], w.clip_seconds) for i, w in enumerate(wins)]
 
-    def _generate_on(self, eng, feats, max_length, status_monitor, texts_out, slot):
+    def _generate_on(self, eng, feats, max_length, status_monitor, texts_out, slot, num_beams=1, length_penalty=1.0):
         """feats: device tensor [n,80,cols] on eng.device -> list of decoded strings."""
         tok = self.tokenizer
         texts, n = [], feats.shape[0]
         steps = 0
-        for pos in range(0, n, eng.max_batch):
-            chunk = feats[pos:pos + eng.max_batch].contiguous()
+        per_call = eng.max_batch if num_beams == 1 else max(1, eng.max_batch // num_beams)
+        for pos in range(0, n, per_call):
+            chunk = feats[pos:pos + per_call].contiguous()
             eng.encode(chunk)
-            ids, n_steps = eng.generate(chunk.shape[0], tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length)
+            if num_beams == 1:
+                ids, n_steps = eng.generate(chunk.shape[0], tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length)
+            else:
+                ids, n_steps = eng.generate_beam(chunk.shape[0], num_beams, tok.prompt_ids, tok.eos_token_id,
+                                                 tok.pad_token_id, max_length, length_penalty)
             steps += n_steps
             texts += tok.batch_decode(ids.cpu().numpy().tolist())
             if status_monitor is not None:                                       # model.py:672-674
-                status_monitor["progress"] = int(100 * min(1, (pos + eng.max_batch) / max(n, 1)))
+                status_monitor["progress"] = int(100 * min(1, (pos + per_call) / max(n, 1)))
         texts_out[slot] = texts
         self.last_stats["decode_steps"] = self.last_stats.get("decode_steps", 0) + steps
 
     def generate_segment_text(self, sliced_audios_features, batch_size, max_length, num_beams, top_k=1, top_p=1.0,
                               length_penalty=1.0, status_monitor=None):
         """model.py:169-189: contiguous shards of the window list, one worker per device."""
-        global _warned_beams
-        if num_beams != 1 and not _warned_beams:
-            warnings.warn("whisperseg_b200 decodes greedily; num_beams=%d is treated as 1" % num_beams)
-            _warned_beams = True
+        num_beams = int(num_beams)
+        if not 1 <= num_beams <= 4:
+            raise ValueError("whisperseg_b200 supports num_beams in [1, 4] (reference default 4), got %d" % num_beams)
+        if num_beams > 1 and num_beams > min(e.max_batch for e in self.engines):
+            raise ValueError("num_beams exceeds the engine's max_batch")
         n = len(sliced_audios_features)
         if n == 0:
             return []
@@ -116,7 +123,7 @@ class SegmenterBase:
             eng = self.engines[slot]
             shard = feats_all[pos:pos + per]
             stacked = torch.stack([f if torch.is_tensor(f) else torch.from_numpy(np.asarray(f)) for f in shard]).to(eng.device)
-            args = (eng, stacked, max_length, status_monitor if slot == 0 else None, outs, slot)
+            args = (eng, stacked, max_length, status_monitor if slot == 0 else None, outs, slot, num_beams, length_penalty)
             if n_dev == 1:
                 self._generate_on(*args)
             else:
@@ -170,7 +177,7 @@ class SegmenterBase:
     @torch.no_grad()
     def segment_many(self, audios, sr, min_frequency=None, spec_time_step=None, min_segment_length=None, eps=None,
                      time_per_frame_for_voting=None, consolidation_method="clustering", max_length=448, num_trials=1,
-                     status_monitor=None):
+                     status_monitor=None, num_beams=4, length_penalty=1.0):
         """Folder mode (reference scripts/segment.py:39-56 loops over files and calls segment() on each, so a
         0.5 s clip runs at batch size 1).  Here the windows of ALL clips are flattened into one list: one H2D
         copy of the concatenated samples, one log-mel launch (per-window [lo, hi) bounds keep clips from
@@ -211,7 +218,9 @@ class SegmenterBase:
         feats = eng.features_device(plan, audio_dev, desc_dev, len(descs))
         self.last_stats = {"n_windows": len(descs)}
         outs = {}
-        self._generate_on(eng, feats, max_length, status_monitor, outs, 0)
+        if not 1 <= int(num_beams) <= 4:
+            raise ValueError("whisperseg_b200 supports num_beams in [1, 4], got %r" % (num_beams,))
+        self._generate_on(eng, feats, max_length, status_monitor, outs, 0, int(num_beams), length_penalty)
         texts = outs[0]
         results, pos = [], 0
         n_fft = get_n_fft_given_sr(sr)
