@@ -389,6 +389,33 @@ def run_ours(args):
             dist.all_reduce(ts, op=dist.ReduceOp.MAX)
         worst_ms = float(ts.item())
         pos_t.add_(ramp_dev[:pos_t.shape[0]].to(pos_t.dtype))
+    # ---- the reference's DEFAULT decode mode: beam search, num_beams=4 (model.py:409) -- same workload, windows
+    # decoded in chunks of max_batch/4 so that windows x beams fills the same 240 decode rows
+    beam_ms, beam_positions = None, 0
+    if not args.no_beam and n_win >= 4:
+        per = n_win // 4
+
+        def beam_pass():
+            feats = eng.features_device(plan, audio_dev, desc_dev, n_win)
+            total = 0
+            for pos in range(0, n_win, per):
+                chunk = feats[pos:pos + per].contiguous()
+                eng.encode(chunk)
+                _, st = eng.generate_beam(chunk.shape[0], 4, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id,
+                                          args.max_length, 1.0)
+                total += st
+            return total
+        beam_pass()
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        beam_positions = beam_pass()
+        b1.record()
+        barrier()
+        tb = torch.tensor([b0.elapsed_time(b1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        beam_ms = float(tb.item())
     h2d = len(piece) * 4 + n_win * 24
     d2h = n_win * max_new * 4
 
@@ -412,6 +439,11 @@ def run_ours(args):
                              "the rows never emit EOS and the batch decodes to max_length",
                         ms_per_step=worst_ms, decode_positions_per_step=int(worst_positions),
                         value=world * SECONDS_PER_GPU / (worst_ms / 1000.0), unit="audio-s/s"),
+                    beam4=None if beam_ms is None else dict(
+                        note="same workload decoded with the reference's default num_beams=4 (HF beam search on the "
+                             "device, length_penalty 1.0), 4 calls of %d windows x 4 beams" % (n_win // 4),
+                        ms_per_step=beam_ms, decode_positions_per_step=int(beam_positions),
+                        value=world * SECONDS_PER_GPU / (beam_ms / 1000.0), unit="audio-s/s"),
                     decode_positions_per_step=float(np.mean(steps_done)),
                     decode_row_lengths=dict(mean=float(row_len.mean()), median=float(np.median(row_len)),
                                             p95=float(np.percentile(row_len, 95)), max=int(row_len.max()),
@@ -433,6 +465,7 @@ def main():
     ap.add_argument("--ref-windows", type=int, default=4, dest="ref_windows")
     ap.add_argument("--ref-decode-steps", type=int, default=12, dest="ref_decode_steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-beam", action="store_true", dest="no_beam")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
