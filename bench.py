@@ -172,7 +172,7 @@ def run_reference(args):
                 config=workload_config(args, n_win),
                 cpu_baseline=dict(value=v, unit="audio-s/s", cores=last["cores"], kind="port", sample=last["sample"]),
                 e2e=dict(value=v, unit="audio-s/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, n_win):
@@ -449,12 +449,30 @@ def run_ours(args):
                                             p95=float(np.percentile(row_len, 95)), max=int(row_len.max()),
                                             mean_positions_per_batch_of_4=per_batch4),
                     step_share_ms={k: v / args.steps for k, v in shares.items()})
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints (NCCL's version banner,
+    torchrun notices) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
