@@ -95,3 +95,47 @@ def test_encoder_attention(lib, B, T, H):
     ref = (torch.softmax(q @ k.transpose(-1, -2), -1) @ v).transpose(1, 2).reshape(B * T, d)
     err = (out.float() - ref).abs().max().item()
     assert err < 2e-2, "attention max err %g" % err
+
+
+@pytest.mark.parametrize("M,N,K", [(16, 3840, 1280), (5, 1280, 1280), (16, 5120, 1280), (9, 1280, 5120), (1, 1152, 384),
+                                   (16, 1536, 384), (12, 384, 1536), (3, 52, 96)])
+@pytest.mark.parametrize("mode", ["ln_f32", "ln_gelu", "bf16_resid", "bf16_f32", "ln_resid", "bf16_gelu"])
+def test_gemv16(lib, M, N, K, mode):
+    """Skinny linear for <= 16 rows (fused LayerNorm / bias / GELU / residual) against torch fp32 on the
+    same bf16-rounded operands.  Tolerance: fp32 accumulation-order noise (2e-3 relative to the output scale),
+    bf16 output rounding for the GELU mode."""
+    import torch
+    from whisperseg_b200 import _lib
+    if mode.startswith("ln") and K > 1536:
+        pytest.skip("fused LayerNorm is for d_model-wide inputs")
+    torch.manual_seed(M * 31 + N + K)
+    dev = "cuda"
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    if mode.startswith("ln"):
+        x = torch.randn(M, K, device=dev) * 3.0 + 0.5
+        gamma, beta = torch.rand(K, device=dev) + 0.5, torch.randn(K, device=dev) * 0.1
+        a = torch.nn.functional.layer_norm(x, (K,), gamma, beta, 1e-5).to(torch.bfloat16)
+        args = (_p(x), _p(gamma), _p(beta), _p(None))
+    else:
+        a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        args = (_p(None), _p(None), _p(None), _p(a))
+    ref = a.float() @ w.float().t() + bias
+    scale = max(1.0, ref.abs().max().item())
+    if mode.endswith("f32"):
+        out = torch.full((M, N), float("nan"), device=dev)
+        _lib.check(lib.wsb_gemv16(*args, _p(w), _p(bias), M, N, K, 0, _p(out), None), "gemv16")
+        torch.cuda.synchronize()
+        assert (out - ref).abs().max().item() < 2e-3 * scale
+    elif mode.endswith("gelu"):
+        out = torch.zeros((M, N), device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.wsb_gemv16(*args, _p(w), _p(bias), M, N, K, 1, _p(out), None), "gemv16")
+        torch.cuda.synchronize()
+        refg = torch.nn.functional.gelu(ref)
+        assert (out.float() - refg).abs().max().item() < 1e-2 * scale
+    else:
+        resid = torch.randn(M, N, device=dev)
+        out = resid.clone()
+        _lib.check(lib.wsb_gemv16(*args, _p(w), _p(bias), M, N, K, 2, _p(out), None), "gemv16")
+        torch.cuda.synchronize()
+        assert (out - (resid + ref)).abs().max().item() < 2e-3 * scale

@@ -10,13 +10,13 @@ from tools import synth  # noqa: E402
 from whisperseg_b200.frontend import FrontendPlan  # noqa: E402
 from whisperseg_b200.segmenter import WhisperSegmenter  # noqa: E402
 
-n_win = 240
-state = synth.make_state("large", seed=0)
+n_win = int(sys.argv[1]) if len(sys.argv) > 1 else 240
+state = synth.make_state("large", seed=0, calibrate="file")
 tokdir = tempfile.mkdtemp()
 synth.token_table_files(tokdir)
 seg = WhisperSegmenter.from_state(state, tokdir, device="cuda", device_ids=[0], max_batch=n_win)
 eng, tok = seg.engines[0], seg.tokenizer
-audio = synth.synth_audio(600.0, 48000, seed=2)
+audio = synth.synth_audio(2.5 * n_win, 48000, seed=2)
 plan = FrontendPlan(48000, 0.0025, 0)
 feats = eng.features(plan, audio, plan.windows(len(audio), 1))
 eng.encode(feats)

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaPa
     // value of column `col` of this row's projection output: bf16 activation, or bias + split-K planes
     auto proj = [&](int col, const __nv_bfloat16* act) -> float {
         if (p.part == nullptr) return __bfloat162float(act[static_cast<long long>(b) * p.q_ld + h * 64 + (col & 63)]);
-        float acc = __ldg(p.bias + col);
+        float acc = p.bias ? __ldg(p.bias + col) : 0.0f;
         const float* src = p.part + static_cast<long long>(b) * p.part_ld + col;
         for (int sp = 0; sp < p.splits; ++sp) acc += src[sp * p.split_stride];
         return acc;

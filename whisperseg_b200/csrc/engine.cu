@@ -119,7 +119,7 @@ struct Model {
     char* ws = nullptr;
     size_t ws_bytes = 0;
     __nv_bfloat16 *h1p, *xn, *qkv, *att, *ff, *enc_out, *cross_kv, *k_cache, *v_cache, *dxn, *dqkv, *datt, *dq, *dff;
-    float *x, *dx, *am_val, *dpart;
+    float *x, *dx, *am_val, *dpart, *gv_stats;
     size_t dpart_floats = 0;
     int *am_idx, *tokens, *next_token, *step, *n_active, *prompt_dev;
     unsigned char* finished;
@@ -137,6 +137,7 @@ struct Model {
     };
     std::map<std::tuple<int, int, int, int, int, int, int>, GraphEntry> graphs;
     bool use_pdl = false;
+    bool use_gemv = true;               // <= 16 decode rows: fused LN + mma.sync linear layers (gemv.cu)
     int* pinned_active = nullptr;
     // beam search workspace (allocated on first use): raw logits [max_batch][ldv] + BeamState arrays
     char* beam_ws = nullptr;
@@ -194,6 +195,7 @@ static int model_layout(Model* m, bool assign) {
     m->dff = carve<__nv_bfloat16>(p, B * F);
     m->dpart_floats = 16 * B * std::max<size_t>(F, 3 * d);
     m->dpart = carve<float>(p, m->dpart_floats);
+    m->gv_stats = carve<float>(p, 160 * 32);
     m->am_val = carve<float>(p, B * m->am_tiles);
     m->am_idx = carve<int>(p, B * m->am_tiles);
     m->tokens = carve<int>(p, B * c.max_target_positions);
@@ -462,9 +464,75 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
         bool prev;
         explicit PdlScope(bool on) : prev(g_use_pdl) { g_use_pdl = on; }
         ~PdlScope() { g_use_pdl = prev; }
-    } pdl_scope(m->use_pdl);
+    } pdl_scope(m->use_pdl || (m->use_gemv && B <= 16 && c.d_model <= 1536));
+    // (programmatic dependent launch pays off on the <= 16-row path only: its kernels prefetch their weight
+    // tiles before the dependency wait and two of their CTAs fit on an SM; it measured slower on the tcgen05 path)
     WSB_RUN(embed_tokens_step(st.next_token, m->step, 0, m->dec_emb, m->dec_pos, m->dx, B, d, s));
     const long long cache_l = static_cast<long long>(B) * H * tmax * 64;
+    const bool small = m->use_gemv && B <= 16 && d <= 1536;
+    if (small) {
+        // <= 16 rows: one launch per linear layer (LayerNorm, bias, activation / residual fused), 8 per layer.
+        // The residual stream's row statistics travel with it: embed -> (exact) -> qkv; out-proj -> cq;
+        // cross-out -> fc1; fc2 -> next layer's qkv.
+        int parts = 1;
+        {
+            ProfScope ps(PROF_DEC_LN, 4.0 * B * d, s);
+            WSB_RUN(row_stats16(m->dx, B, d, m->gv_stats, s));
+        }
+        auto lin_ln = [&](const float* g_, const float* b_, const __nv_bfloat16* W, const float* bias, int N, float* out_f32,
+                          __nv_bfloat16* out_gelu) -> int {
+            Gemv16Args ga;
+            ga.x = m->dx;
+            ga.stats = m->gv_stats;
+            ga.stats_parts = parts;
+            ga.gamma = g_;
+            ga.beta = b_;
+            ga.W = W;
+            ga.bias = bias;
+            ga.out_f32 = out_f32;
+            ga.out_bf16_gelu = out_gelu;
+            ga.row_skip = fin;
+            ga.M = B;
+            ga.N = N;
+            ga.K = d;
+            ProfScope ps(PROF_DEC_GEMM, 2.0 * B * N * d, s);
+            return gemv16(ga, s);
+        };
+        auto lin_resid = [&](const __nv_bfloat16* a_, const __nv_bfloat16* W, const float* bias, int K) -> int {
+            Gemv16Args ga;
+            ga.a = a_;
+            ga.W = W;
+            ga.bias = bias;
+            ga.resid = m->dx;
+            ga.stats_out = m->gv_stats;
+            ga.row_skip = fin;
+            ga.M = B;
+            ga.N = d;
+            ga.K = K;
+            parts = gemv16_parts(d);
+            ProfScope ps(PROF_DEC_GEMM, 2.0 * B * d * K, s);
+            return gemv16(ga, s);
+        };
+        for (int l = 0; l < L; ++l) {
+            const DecLayer& e = m->dec[l];
+            SplitkInput part;
+            part.planes = m->dpart;
+            part.splits = 1;
+            part.bias = nullptr;
+            WSB_RUN(lin_ln(e.ln1_g, e.ln1_b, e.sqkv_w, e.sqkv_b, 3 * d, m->dpart, nullptr));
+            part.split_stride = static_cast<long long>(B) * 3 * d;
+            WSB_RUN(decode_self_attention(nullptr, &part, d, st.k_cache + l * cache_l, st.v_cache + l * cache_l, tmax, m->step, 0,
+                                          fin, m->datt, B, H, s, st.anc, st.anc_ld));
+            WSB_RUN(lin_resid(m->datt, e.so_w, e.so_b, d));
+            WSB_RUN(lin_ln(e.ln2_g, e.ln2_b, e.cq_w, e.cq_b, d, m->dpart, nullptr));
+            part.split_stride = static_cast<long long>(B) * d;
+            WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s, st.kv_div));
+            WSB_RUN(lin_resid(m->datt, e.co_w, e.co_b, d));
+            WSB_RUN(lin_ln(e.ln3_g, e.ln3_b, e.fc1_w, e.fc1_b, F, nullptr, m->dff));
+            WSB_RUN(lin_resid(m->dff, e.fc2_w, e.fc2_b, F));
+        }
+        if (with_logits) WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec_ln_g, m->dec_ln_b, m->dxn, nullptr, B, d, s));
+    } else {
     {
         ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
         WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec[0].ln1_g, m->dec[0].ln1_b, m->dxn, nullptr, B, d, s));
@@ -490,6 +558,7 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
         WSB_RUN(skinny_linear(m, m->datt, e.co_w, e.co_b, B, d, d, 0, nullptr, m->dx, e.ln3_g, e.ln3_b, m->dxn, s, fin));
         WSB_RUN(skinny_linear(m, m->dxn, e.fc1_w, e.fc1_b, B, F, d, 1, m->dff, nullptr, nullptr, nullptr, nullptr, s, fin));
         WSB_RUN(skinny_linear(m, m->dff, e.fc2_w, e.fc2_b, B, d, F, 0, nullptr, m->dx, next_g, next_b, m->dxn, s, fin));
+    }
     }
     if (!with_logits) return prefill_advance(st.next_token, forced, forced_ld, m->prompt_dev, m->step, B, s);
     if (beam) {
@@ -544,6 +613,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     const int d = c.d_model, L = c.n_layers, T = m->T, rows = B * T;
     const int max_new = max_length - prompt_len;
     m->use_pdl = (flags & 2) != 0;                      // bit1: programmatic dependent launch (measured slower: off)
+    m->use_gemv = (flags & 8) == 0;                     // bit3: keep the tcgen05 split-K path below 17 rows too
     // cross-attention K/V of every decoder layer in one GEMM, scattered head-major:
     // cross_kv[b][layer][k|v][head][t][64]   (HF modeling_whisper.py:326-336, computed once and cached)
     {
@@ -598,7 +668,8 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     const bool allow_compaction = (flags & 4) == 0 && forced == nullptr;
     Model::GraphEntry* graph = nullptr;
     auto get_graph = [&](const DecState& cur, Model::GraphEntry** out) -> int {
-        const auto key = std::make_tuple(cur.B, cur.buffer_id, cur.row_map != nullptr ? 1 : 0, max_new, prompt_len, eos_id, pad_id);
+        const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 0 : 16), cur.row_map != nullptr ? 1 : 0, max_new,
+                                         prompt_len, eos_id, pad_id);
         auto it = m->graphs.find(key);
         if (it == m->graphs.end()) {
             cudaGraph_t g = nullptr;
@@ -979,6 +1050,40 @@ int wsb_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_
                   float* out_f32_dev, int rows, int d, void* stream) {
     return layernorm_f32_to_bf16(x_dev, gamma_dev, beta_dev, static_cast<__nv_bfloat16*>(out_bf16_dev), out_f32_dev, rows,
                                  d, static_cast<cudaStream_t>(stream));
+}
+int wsb_gemv16(const float* x_f32_dev, const float* gamma_dev, const float* beta_dev, const void* a_bf16_dev, const void* w_dev,
+               const float* bias_dev, int M, int N, int K, int out_mode, void* out_dev, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Gemv16Args g;
+    float* stats = nullptr;
+    struct Free {
+        float*& p;
+        ~Free() { cudaFree(p); }
+    } guard{stats};
+    WSB_CHECK_CUDA(cudaMalloc(&stats, sizeof(float) * 160 * 32 * 2));
+    if (x_f32_dev) {                                      // stand-alone use: exact row statistics, one part
+        WSB_RUN(row_stats16(x_f32_dev, M, K, stats, s));
+        g.x = x_f32_dev;
+        g.stats = stats;
+        g.stats_parts = 1;
+    }
+    g.gamma = gamma_dev;
+    g.beta = beta_dev;
+    g.a = static_cast<const __nv_bfloat16*>(a_bf16_dev);
+    g.W = static_cast<const __nv_bfloat16*>(w_dev);
+    g.bias = bias_dev;
+    if (out_mode == 0) g.out_f32 = static_cast<float*>(out_dev);
+    else if (out_mode == 1) g.out_bf16_gelu = static_cast<__nv_bfloat16*>(out_dev);
+    else {
+        g.resid = static_cast<float*>(out_dev);
+        g.stats_out = stats + 160 * 32;
+    }
+    g.M = M;
+    g.N = N;
+    g.K = K;
+    WSB_RUN(gemv16(g, s));
+    WSB_CHECK_CUDA(cudaStreamSynchronize(s));
+    return 0;
 }
 int wsb_encoder_attention(const void* qkv_dev, void* out_dev, int batch, int T, int n_heads, void* stream) {
     return encoder_attention(static_cast<const __nv_bfloat16*>(qkv_dev), static_cast<__nv_bfloat16*>(out_dev), batch, T,
