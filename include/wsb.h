@@ -85,7 +85,7 @@ int wsb_encode(wsb_model* model, const float* features_dev, int batch, float* hi
  * receives the number of generated positions actually computed.  flags: bit0 = replay the decode
  * step from a CUDA graph; bit1 = launch decode kernels with programmatic dependent launch; bit2 =
  * disable batch compaction (gathering the still-active rows into a smaller batch as rows finish); bit3 =
- * keep the tcgen05 split-K linear layers for batches of <= 16 rows (default: fused LN + mma.sync kernels). */
+ * keep the tcgen05 split-K linear layers for batches of <= 64 rows (default: fused LN + mma.sync kernels). */
 int wsb_generate(wsb_model* model, int batch, const int32_t* prompt, int prompt_len, int eos_id, int pad_id,
                  int max_length, const int32_t* forced_dev, int32_t* tokens_dev, int* n_steps, int flags,
                  void* stream);
@@ -127,13 +127,17 @@ int wsb_gemm_bf16(const void* a_dev, const void* w_dev, int M, int N, int K, con
                   const float* resid_dev, void* c_dev, int out_f32, int block_n, void* stream);
 int wsb_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_dev, void* out_bf16_dev,
                   float* out_f32_dev, int rows, int d, void* stream);
-/* Skinny linear layer for decode batches of at most 16 rows (csrc/gemv.cu): out = epilogue(in * W^T + bias) in
+/* Skinny linear layer for decode batches of at most 64 rows (csrc/gemv.cu): out = epilogue(in * W^T + bias) in
  * one launch.  Input: fp32 rows x_f32_dev [M][K] with the LayerNorm (gamma, beta) fused in, or (x NULL) bf16
  * activations a_bf16_dev [M][K].  w_dev bf16 [N][K].  out_mode 0: float32 [M][N]; 1: bf16 [M][N] = GELU(.);
  * 2: float32 [M][N] += (in-place residual update).  Replaces nn.Linear (+ the preceding nn.LayerNorm) of
  * HF WhisperDecoderLayer (modeling_whisper.py:417-506) at small batch.                                       */
 int wsb_gemv16(const float* x_f32_dev, const float* gamma_dev, const float* beta_dev, const void* a_bf16_dev,
                const void* w_dev, const float* bias_dev, int M, int N, int K, int out_mode, void* out_dev, void* stream);
+
+/* Diagnostics: steady-state microseconds per wsb_gemv16-style launch (weights rotating through `weight_copies`
+ * buffers so that they stream from HBM).  mode 0: LayerNorm -> fp32, 1: LayerNorm -> GELU bf16, 2: bf16 -> residual. */
+int wsb_gemv16_bench(int M, int N, int K, int mode, int iters, int weight_copies, float* us_per_launch);
 
 /* qkv bf16 [batch*T][3*n_heads*64] (q pre-scaled) -> out bf16 [batch*T][n_heads*64] */
 int wsb_encoder_attention(const void* qkv_dev, void* out_dev, int batch, int T, int n_heads, void* stream);

@@ -98,10 +98,12 @@ def test_encoder_attention(lib, B, T, H):
 
 
 @pytest.mark.parametrize("M,N,K", [(16, 3840, 1280), (5, 1280, 1280), (16, 5120, 1280), (9, 1280, 5120), (1, 1152, 384),
-                                   (16, 1536, 384), (12, 384, 1536), (3, 52, 96)])
+                                   (16, 1536, 384), (12, 384, 1536), (3, 52, 96),
+                                   (17, 1280, 1280), (32, 3840, 1280), (40, 5120, 1280), (64, 1280, 5120), (64, 3840, 1280),
+                                   (50, 1152, 384), (33, 384, 1536), (64, 52, 96)])
 @pytest.mark.parametrize("mode", ["ln_f32", "ln_gelu", "bf16_resid", "bf16_f32", "ln_resid", "bf16_gelu"])
 def test_gemv16(lib, M, N, K, mode):
-    """Skinny linear for <= 16 rows (fused LayerNorm / bias / GELU / residual) against torch fp32 on the
+    """Skinny linear for <= 64 rows (1, 2 or 4 m-tiles of 16; fused LayerNorm / bias / GELU / residual) against torch fp32 on the
     same bf16-rounded operands.  Tolerance: fp32 accumulation-order noise (2e-3 relative to the output scale),
     bf16 output rounding for the GELU mode."""
     import torch

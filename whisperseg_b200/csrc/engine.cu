@@ -9,6 +9,7 @@
 #include "../../include/wsb.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <map>
@@ -137,7 +138,9 @@ struct Model {
     };
     std::map<std::tuple<int, int, int, int, int, int, int>, GraphEntry> graphs;
     bool use_pdl = false;
-    bool use_gemv = true;               // <= 16 decode rows: fused LN + mma.sync linear layers (gemv.cu)
+    bool use_gemv = true;               // few decode rows: fused LN + mma.sync linear layers (gemv.cu)
+    int gemv_rows = 64;                 // ... used up to this many rows (WSB_GEMV_ROWS, <= 64)
+    std::vector<int> ladder{64, 32, 16};   // compaction levels, descending, all <= kCompactRows (override: WSB_LADDER=64,16)
     int* pinned_active = nullptr;
     // beam search workspace (allocated on first use): raw logits [max_batch][ldv] + BeamState arrays
     char* beam_ws = nullptr;
@@ -148,7 +151,6 @@ struct Model {
 };
 
 constexpr int kCompactRows = 64;        // first compaction level; the second level (16 rows) reuses the main buffers
-constexpr int kCompactRows2 = 16;
 
 // the per-row decode state a step works on (main buffers, or a compacted copy)
 struct DecState {
@@ -195,7 +197,7 @@ static int model_layout(Model* m, bool assign) {
     m->dff = carve<__nv_bfloat16>(p, B * F);
     m->dpart_floats = 16 * B * std::max<size_t>(F, 3 * d);
     m->dpart = carve<float>(p, m->dpart_floats);
-    m->gv_stats = carve<float>(p, 160 * 32);
+    m->gv_stats = carve<float>(p, 160 * 64 * 2);
     m->am_val = carve<float>(p, B * m->am_tiles);
     m->am_idx = carve<int>(p, B * m->am_tiles);
     m->tokens = carve<int>(p, B * c.max_target_positions);
@@ -464,14 +466,13 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
         bool prev;
         explicit PdlScope(bool on) : prev(g_use_pdl) { g_use_pdl = on; }
         ~PdlScope() { g_use_pdl = prev; }
-    } pdl_scope(m->use_pdl || (m->use_gemv && B <= 16 && c.d_model <= 1536));
-    // (programmatic dependent launch pays off on the <= 16-row path only: its kernels prefetch their weight
-    // tiles before the dependency wait and two of their CTAs fit on an SM; it measured slower on the tcgen05 path)
+    } pdl_scope(m->use_pdl || (m->use_gemv && B <= m->gemv_rows && c.d_model <= 1536));
+    // (programmatic dependent launch: the linear-layer kernels fetch their weight tiles before the dependency wait)
     WSB_RUN(embed_tokens_step(st.next_token, m->step, 0, m->dec_emb, m->dec_pos, m->dx, B, d, s));
     const long long cache_l = static_cast<long long>(B) * H * tmax * 64;
-    const bool small = m->use_gemv && B <= 16 && d <= 1536;
+    const bool small = m->use_gemv && B <= m->gemv_rows && d <= 1536;
     if (small) {
-        // <= 16 rows: one launch per linear layer (LayerNorm, bias, activation / residual fused), 8 per layer.
+        // <= gemv_rows (64) rows: one launch per linear layer (LayerNorm, bias, activation / residual fused), 8 per layer.
         // The residual stream's row statistics travel with it: embed -> (exact) -> qkv; out-proj -> cq;
         // cross-out -> fc1; fc2 -> next layer's qkv.
         int parts = 1;
@@ -612,8 +613,20 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     WSB_REQUIRE(max_length > prompt_len && max_length <= c.max_target_positions, "max_length in (prompt_len, max_target_positions]");
     const int d = c.d_model, L = c.n_layers, T = m->T, rows = B * T;
     const int max_new = max_length - prompt_len;
-    m->use_pdl = (flags & 2) != 0;                      // bit1: programmatic dependent launch (measured slower: off)
-    m->use_gemv = (flags & 8) == 0;                     // bit3: keep the tcgen05 split-K path below 17 rows too
+    m->use_pdl = (flags & 2) != 0;                      // bit1: programmatic dependent launch (GEMM weight tiles and gemv weight rows
+                                                        // are fetched before the dependency wait)
+    m->use_gemv = (flags & 8) == 0;                     // bit3: keep the tcgen05 split-K path for small batches too
+    if (const char* e = std::getenv("WSB_GEMV_ROWS")) m->gemv_rows = std::max(0, std::min(64, std::atoi(e)));
+    if (const char* e = std::getenv("WSB_LADDER")) {
+        std::vector<int> lv;
+        for (const char* q = e; *q;) {
+            const int v = std::atoi(q);
+            if (v >= 1 && v <= kCompactRows && (lv.empty() || v < lv.back())) lv.push_back(v);
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        if (!lv.empty()) m->ladder = lv;
+    }
     // cross-attention K/V of every decoder layer in one GEMM, scattered head-major:
     // cross_kv[b][layer][k|v][head][t][64]   (HF modeling_whisper.py:326-336, computed once and cached)
     {
@@ -668,7 +681,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     const bool allow_compaction = (flags & 4) == 0 && forced == nullptr;
     Model::GraphEntry* graph = nullptr;
     auto get_graph = [&](const DecState& cur, Model::GraphEntry** out) -> int {
-        const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 0 : 16), cur.row_map != nullptr ? 1 : 0, max_new,
+        const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 32 * m->gemv_rows : 16), cur.row_map != nullptr ? 1 : 0, max_new,
                                          prompt_len, eos_id, pad_id);
         auto it = m->graphs.find(key);
         if (it == m->graphs.end()) {
@@ -693,7 +706,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
         return 0;
     };
     if (use_graph) WSB_RUN(get_graph(st, &graph));
-    const int check_every = 8;
+    const int check_every = 4;
     while (steps_done < max_new) {
         if (use_graph) {
             WSB_CHECK_CUDA(cudaGraphLaunch(graph->exec, s));
@@ -707,13 +720,12 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
             WSB_CHECK_CUDA(cudaStreamSynchronize(s));
             const int active = m->pinned_active[0];
             if (active <= 0) break;
-            // batch compaction: main (B) -> alternate (64 or 16) -> main (16)
+            // batch compaction ladder: every move goes to the other buffer set (main <-> alternate); the target is
+            // the smallest level that still holds the active rows
             int target = 0;
             if (allow_compaction && max_new - steps_done >= 16) {
-                if (st.buffer_id == 0 && st.B > kCompactRows && active <= kCompactRows)
-                    target = active <= kCompactRows2 ? kCompactRows2 : kCompactRows;
-                else if (st.buffer_id == 1 && st.B > kCompactRows2 && active <= kCompactRows2)
-                    target = kCompactRows2;
+                for (int lv : m->ladder)
+                    if (lv < st.B && active <= lv) target = lv;
             }
             if (target > 0) {
                 DecState nx;
@@ -862,7 +874,7 @@ static int generate_beam(Model* m, int B, int nb, const int* prompt, int prompt_
         }
         graph = &it->second;
     }
-    const int check_every = 8;
+    const int check_every = 4;
     while (steps_done < max_new) {
         if (use_graph) {
             WSB_CHECK_CUDA(cudaGraphLaunch(graph->exec, s));
@@ -1060,7 +1072,7 @@ int wsb_gemv16(const float* x_f32_dev, const float* gamma_dev, const float* beta
         float*& p;
         ~Free() { cudaFree(p); }
     } guard{stats};
-    WSB_CHECK_CUDA(cudaMalloc(&stats, sizeof(float) * 160 * 32 * 2));
+    WSB_CHECK_CUDA(cudaMalloc(&stats, sizeof(float) * 160 * 128 * 2));
     if (x_f32_dev) {                                      // stand-alone use: exact row statistics, one part
         WSB_RUN(row_stats16(x_f32_dev, M, K, stats, s));
         g.x = x_f32_dev;
@@ -1076,13 +1088,75 @@ int wsb_gemv16(const float* x_f32_dev, const float* gamma_dev, const float* beta
     else if (out_mode == 1) g.out_bf16_gelu = static_cast<__nv_bfloat16*>(out_dev);
     else {
         g.resid = static_cast<float*>(out_dev);
-        g.stats_out = stats + 160 * 32;
+        g.stats_out = stats + 160 * 128;
     }
     g.M = M;
     g.N = N;
     g.K = K;
     WSB_RUN(gemv16(g, s));
     WSB_CHECK_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+int wsb_gemv16_bench(int M, int N, int K, int mode, int iters, int weight_copies, float* us_per_launch) {
+    // diagnostics: steady-state time of one skinny-linear launch; the weights rotate through `weight_copies`
+    // buffers so that they come from HBM, not L2.  mode 0: LN -> fp32, 1: LN -> GELU bf16, 2: bf16 -> residual
+    WSB_REQUIRE(M >= 1 && M <= gemv16_max_rows() && iters >= 1 && weight_copies >= 1 && us_per_launch, "bad arguments");
+    const size_t wn = static_cast<size_t>(N) * K;
+    __nv_bfloat16 *w = nullptr, *a = nullptr;
+    float *x = nullptr, *gb = nullptr, *stats = nullptr, *out = nullptr;
+    struct Free {
+        void** p[6];
+        ~Free() { for (auto q : p) cudaFree(*q); }
+    } guard{{reinterpret_cast<void**>(&w), reinterpret_cast<void**>(&a), reinterpret_cast<void**>(&x), reinterpret_cast<void**>(&gb),
+             reinterpret_cast<void**>(&stats), reinterpret_cast<void**>(&out)}};
+    WSB_CHECK_CUDA(cudaMalloc(&w, wn * 2 * weight_copies));
+    WSB_CHECK_CUDA(cudaMalloc(&a, static_cast<size_t>(64) * K * 2));
+    WSB_CHECK_CUDA(cudaMalloc(&x, static_cast<size_t>(64) * K * 4));
+    WSB_CHECK_CUDA(cudaMalloc(&gb, static_cast<size_t>(K) * 8 + static_cast<size_t>(N) * 4));
+    WSB_CHECK_CUDA(cudaMalloc(&stats, sizeof(float) * 160 * 128 * 2));
+    WSB_CHECK_CUDA(cudaMalloc(&out, static_cast<size_t>(64) * N * 4));
+    WSB_CHECK_CUDA(cudaMemset(w, 0, wn * 2 * weight_copies));
+    WSB_CHECK_CUDA(cudaMemset(a, 0, static_cast<size_t>(64) * K * 2));
+    WSB_CHECK_CUDA(cudaMemset(x, 0, static_cast<size_t>(64) * K * 4));
+    WSB_CHECK_CUDA(cudaMemset(gb, 0, static_cast<size_t>(K) * 8 + static_cast<size_t>(N) * 4));
+    WSB_CHECK_CUDA(cudaMemset(stats, 0, sizeof(float) * 160 * 128 * 2));
+    WSB_CHECK_CUDA(cudaMemset(out, 0, static_cast<size_t>(64) * N * 4));
+    cudaStream_t s = nullptr;
+    cudaEvent_t e0, e1;
+    WSB_CHECK_CUDA(cudaEventCreate(&e0));
+    WSB_CHECK_CUDA(cudaEventCreate(&e1));
+    Gemv16Args g;
+    if (mode <= 1) {
+        g.x = x;
+        g.stats = stats;
+        g.stats_parts = gemv16_parts(K);
+        g.gamma = gb;
+        g.beta = gb + K;
+    } else {
+        g.a = a;
+    }
+    g.bias = gb + 2 * K;
+    if (mode == 0) g.out_f32 = out;
+    else if (mode == 1) g.out_bf16_gelu = reinterpret_cast<__nv_bfloat16*>(out);
+    else {
+        g.resid = out;
+        g.stats_out = stats + 160 * 128;
+    }
+    g.M = M;
+    g.N = N;
+    g.K = K;
+    for (int it = -3; it < iters; ++it) {
+        if (it == 0) WSB_CHECK_CUDA(cudaEventRecord(e0, s));
+        g.W = w + wn * ((it + 3) % weight_copies);
+        WSB_RUN(gemv16(g, s));
+    }
+    WSB_CHECK_CUDA(cudaEventRecord(e1, s));
+    WSB_CHECK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    WSB_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *us_per_launch = ms * 1000.0f / iters;
     return 0;
 }
 int wsb_encoder_attention(const void* qkv_dev, void* out_dev, int batch, int T, int n_heads, void* stream) {

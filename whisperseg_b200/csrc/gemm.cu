@@ -111,8 +111,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // everything above (descriptor prefetch, barrier init, TMEM allocation) overlapped the previous kernel
-    pdl_wait();
+    // everything above (descriptor prefetch, barrier init, TMEM allocation) overlaps the previous kernel under
+    // programmatic dependent launch; so do the first weight (B operand) tiles below -- weights are constants.
+    // Every thread that touches activations or outputs calls pdl_wait() first.
     pdl_launch_dependents();
 
     const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
@@ -123,6 +124,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int pre = 0;                                // stages already armed, their B tile in flight
+            if (static_cast<int>(blockIdx.x) < total_tiles) {
+                const int tile = blockIdx.x;
+                const int sp = tile % p.splits, mn = tile / p.splits;
+                const int nti = mn % p.n_tiles;
+                const int nt = p.n_tile_list ? p.n_tile_list[nti] : nti;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
+                pre = min(S, kb1 - kb0);
+                for (int i = 0; i < pre; ++i) {
+                    mbar_arrive_expect_tx(&full[i], Cfg::kStageBytes);
+                    tma_load_2d(smem + i * Cfg::kStageBytes + kABytes, &tmB, &full[i], (kb0 + i) * kBK, nt * BN);
+                }
+            }
+            pdl_wait();
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int sp = tile % p.splits, mn = tile / p.splits;
                 const int mt = mn / p.n_tiles, nti = mn - mt * p.n_tiles;
@@ -137,11 +152,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     a_row = mt * kBM;
                 }
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* sa = smem + stage * Cfg::kStageBytes;
-                    mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-                    tma_load_3d(sa, &tmA, &full[stage], kb * kBK, a_row, a_batch);
-                    tma_load_2d(sa + kABytes, &tmB, &full[stage], kb * kBK, nt * BN);
+                    if (pre > 0) {                      // armed before the dependency wait: only A is missing
+                        --pre;
+                        tma_load_3d(sa, &tmA, &full[stage], kb * kBK, a_row, a_batch);
+                    } else {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+                        tma_load_3d(sa, &tmA, &full[stage], kb * kBK, a_row, a_batch);
+                        tma_load_2d(sa + kABytes, &tmB, &full[stage], kb * kBK, nt * BN);
+                    }
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1;
@@ -184,6 +204,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else if (warp >= 4) {
         // ---- epilogue: 8 warps; warp (4 + e) owns TMEM lanes 32*(e%4).. (hardware restriction: a warp
         // may only touch the lane quarter warp_id % 4) and the 32-column chunks c with c % 2 == e / 4.
+        pdl_wait();
         const int e = warp - 4;
         const int q = e & 3, half = e >> 2;        // half = column group index
         float* tbuf = epi_buf + e * (32 * 33);            // per-warp 32x32 transpose tile (padded)
@@ -257,20 +278,54 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     float bias_v = 0.0f;
                     if (cvalid && p.bias) bias_v = __ldg(p.bias + col);
                     if constexpr (EPI == EPI_F32_RESID) {
-                        // the residual aliases the output (in-place stream update): batch the loads ahead of
-                        // the stores explicitly, the compiler may not reorder them
-                        const float* rs = p.resid + grow0 * p.ldr + col;
-                        float* o = reinterpret_cast<float*>(p.out) + grow0 * p.ldc + col;
+                        // the residual aliases the output (in-place stream update): all loads are issued ahead of
+                        // the stores explicitly, the compiler may not reorder them.  lane = 8 * rs + j owns columns
+                        // 4j..4j+3 of rows rs, rs + 4, ...: 16-byte accesses, 128 contiguous bytes per row
+                        const int rs4 = lane >> 3, j4 = (lane & 7) * 4;
+                        const int c4 = n0 + j4;
+                        const bool vec4 = c4 + 4 <= p.N && (p.ldc & 3) == 0 && (p.ldr & 3) == 0 &&
+                                          ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.resid)) & 15) == 0;
+                        if (__all_sync(0xffffffffu, vec4)) {
+                            float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias) {
+                                bz.x = __ldg(p.bias + c4);
+                                bz.y = __ldg(p.bias + c4 + 1);
+                                bz.z = __ldg(p.bias + c4 + 2);
+                                bz.w = __ldg(p.bias + c4 + 3);
+                            }
+                            const float* rs = p.resid + (grow0 + rs4) * p.ldr + c4;
+                            float* o = reinterpret_cast<float*>(p.out) + (grow0 + rs4) * p.ldc + c4;
+                            float4 res[8];
 #pragma unroll
-                        for (int r0 = 0; r0 < 32; r0 += 16) {
-                            float res[16];
+                            for (int it = 0; it < 8; ++it)
+                                res[it] = (it * 4 + rs4 < nvalid) ? *reinterpret_cast<const float4*>(rs + static_cast<long long>(it * 4) * p.ldr)
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                res[j] = (cvalid && r0 + j < nvalid) ? rs[static_cast<long long>(r0 + j) * p.ldr] : 0.0f;
+                            for (int it = 0; it < 8; ++it) {
+                                const int rr = it * 4 + rs4;
+                                if (rr < nvalid) {
+                                    float4 v;
+                                    v.x = tbuf[rr * 33 + j4] + bz.x + res[it].x;
+                                    v.y = tbuf[rr * 33 + j4 + 1] + bz.y + res[it].y;
+                                    v.z = tbuf[rr * 33 + j4 + 2] + bz.z + res[it].z;
+                                    v.w = tbuf[rr * 33 + j4 + 3] + bz.w + res[it].w;
+                                    *reinterpret_cast<float4*>(o + static_cast<long long>(it * 4) * p.ldc) = v;
+                                }
+                            }
+                        } else {
+                            const float* rs = p.resid + grow0 * p.ldr + col;
+                            float* o = reinterpret_cast<float*>(p.out) + grow0 * p.ldc + col;
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (cvalid && r0 + j < nvalid)
-                                    o[static_cast<long long>(r0 + j) * p.ldc] = tbuf[(r0 + j) * 33 + lane] + bias_v + res[j];
+                            for (int r0 = 0; r0 < 32; r0 += 16) {
+                                float res[16];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    res[j] = (cvalid && r0 + j < nvalid) ? rs[static_cast<long long>(r0 + j) * p.ldr] : 0.0f;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (cvalid && r0 + j < nvalid)
+                                        o[static_cast<long long>(r0 + j) * p.ldc] = tbuf[(r0 + j) * 33 + lane] + bias_v + res[j];
+                            }
                         }
                     } else if constexpr (EPI == EPI_F32 || EPI == EPI_F32_GELU_ROWVEC) {
                         float* o = reinterpret_cast<float*>(p.out) + sp * p.split_stride + grow0 * p.ldc + col;
@@ -294,17 +349,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             if (cvalid && !((skip_mask >> rr) & 1u)) o[static_cast<long long>(rr) * p.ldc] = v;
                         }
                     } else {   // bf16 outputs: EPI_BF16, EPI_BF16_GELU, EPI_HEADMAJOR
+                        // lane = 4 * rsub + j owns columns 8j..8j+7 of rows rsub, rsub + 8, ...: one 16-byte store per
+                        // lane, 64 contiguous bytes per row and instruction, 4 store instructions per 32x32 chunk
+                        // (tbuf reads are conflict-free: bank = (row + 8j + i) mod 32 over the 32 lanes)
+                        const int rsub = lane >> 2, j8 = (lane & 3) * 8;
+                        const int c8 = n0 + j8;
+                        bool vec = c8 + 8 <= p.N && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+                        if constexpr (EPI != EPI_HEADMAJOR) vec = vec && (p.ldc & 7) == 0;
+                        float b8[8];
+                        if (p.bias && c8 + 8 <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+                            const float4 u0 = __ldg(reinterpret_cast<const float4*>(p.bias + c8));
+                            const float4 u1 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 + 4));
+                            b8[0] = u0.x; b8[1] = u0.y; b8[2] = u0.z; b8[3] = u0.w;
+                            b8[4] = u1.x; b8[5] = u1.y; b8[6] = u1.z; b8[7] = u1.w;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) b8[i] = (p.bias && c8 + i < p.N) ? __ldg(p.bias + c8 + i) : 0.0f;
+                        }
                         long long hm_b = 0;
                         int hm_t = 0;
                         if constexpr (EPI == EPI_HEADMAJOR) {
                             hm_b = grow0 / p.rows_per_batch;
                             hm_t = static_cast<int>(grow0 - hm_b * p.rows_per_batch);
                         }
-                        auto store_row = [&](int rr) {
-                            float v = tbuf[rr * 33 + lane] + bias_v;
-                            if constexpr (EPI == EPI_BF16_GELU) v = gelu_fast(v);
-                            const float hi = __shfl_down_sync(0xffffffffu, v, 1);
-                            const long long grow = grow0 + rr;
+                        auto store_rows = [&](int it) {
+                            const int rr = it * 8 + rsub;
+                            if (rr >= nvalid) return;
+                            float v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                v[i] = tbuf[rr * 33 + j8 + i] + b8[i];
+                                if constexpr (EPI == EPI_BF16_GELU) v[i] = gelu_fast(v[i]);
+                            }
                             __nv_bfloat16* o;
                             if constexpr (EPI == EPI_HEADMAJOR) {
                                 int t = hm_t + rr;
@@ -314,24 +390,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                     b += 1;
                                 }
                                 o = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                    ((b * (p.N >> 6) + (col >> 6)) * p.rows_per_batch + t) * 64 + (col & 63);
+                                    ((b * (p.N >> 6) + (c8 >> 6)) * p.rows_per_batch + t) * 64 + (c8 & 63);
                             } else {
-                                o = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + col;
+                                o = reinterpret_cast<__nv_bfloat16*>(p.out) + (grow0 + rr) * p.ldc + c8;
                             }
-                            if ((lane & 1) == 0) {
-                                if (col + 1 < p.N) {
-                                    *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v, hi);
-                                } else if (cvalid) {
-                                    *o = __float2bfloat16(v);
-                                }
+                            if (vec) {
+                                uint4 w;
+                                w.x = pack_bf16x2(v[0], v[1]);
+                                w.y = pack_bf16x2(v[2], v[3]);
+                                w.z = pack_bf16x2(v[4], v[5]);
+                                w.w = pack_bf16x2(v[6], v[7]);
+                                *reinterpret_cast<uint4*>(o) = w;
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    if (c8 + i < p.N) o[i] = __float2bfloat16(v[i]);
                             }
                         };
-                        if (nvalid == 32) {
 #pragma unroll
-                            for (int rr = 0; rr < 32; ++rr) store_row(rr);
-                        } else {
-                            for (int rr = 0; rr < nvalid; ++rr) store_row(rr);
-                        }
+                        for (int it = 0; it < 4; ++it) store_rows(it);
                     }
                     __syncwarp();
                 }

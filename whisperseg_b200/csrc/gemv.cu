@@ -23,6 +23,7 @@
 #include "wsb_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace wsb {
 
@@ -31,10 +32,12 @@ constexpr int kGvWarps = kGvThreads / 32;
 constexpr int kGvBatch = 3;             // k-blocks (of 32) per warp whose activation fragments are in flight
 constexpr int kGvMaxNT = 5;
 constexpr int kGvWPad = 64;             // bytes of padding per weight row in smem (row shift = 16 banks)
+constexpr int kGvMaxRows = 64;          // 4 m-tiles of 16 rows
+constexpr int kGvMaxSmem = 220 * 1024;
 
 struct GvParams {
     const float* x;                     // LN input: fp32 [M][K] (IN_LN) ...
-    const float* stats;                 // [parts][16][2] partial (sum, sum of squares) of every row of x
+    const float* stats;                 // [parts][MP][2] partial (sum, sum of squares) of every row of x (MP = 16, 32 or 64)
     int stats_parts;
     const float* gamma;
     const float* beta;
@@ -44,7 +47,7 @@ struct GvParams {
     float* out_f32;                     // EPI 0: [M][N]
     __nv_bfloat16* out_bf16;            // EPI 1: [M][N] = gelu(.)
     float* resid;                       // EPI 2: [M][N] += .
-    float* stats_out;                   // EPI 2: [gridDim.x][16][2] partial row statistics of the updated rows
+    float* stats_out;                   // EPI 2: [gridDim.x][MP][2] partial row statistics of the updated rows
     const unsigned char* row_skip;      // [M] or null: rows not stored
     int M, N, K;
 };
@@ -72,20 +75,28 @@ __device__ __forceinline__ uint4 ln_pack8(const float4& v0, const float4& v1, fl
     return r;
 }
 
-template <int IN_LN, int EPI, int NT>
+// MT = number of 16-row m-tiles (1, 2 or 4 -> up to 64 rows).  The 16 warps are split into MT groups of
+// KS = 16 / MT warps: group mt owns rows [16 mt, 16 mt + 16) and its warps split K.  The weight tile is
+// fetched once per CTA whatever MT is; the activation fragments of a warp are loaded in batches of kGvBatch
+// k-blocks, the next batch in flight while the current one feeds the MMAs.  m-tiles whose rows are all
+// finished are skipped (no loads, no MMAs), finished rows of a live tile are not loaded.
+template <int IN_LN, int EPI, int NT, int MT>
 __global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p) {
+    constexpr int KS = kGvWarps / MT;                    // warps splitting K inside one m-tile
+    constexpr int MP = 16 * MT;                          // padded row count (statistics layout [parts][MP][2])
     extern __shared__ __align__(128) unsigned char gv_smem[];
-    __shared__ float red[kGvWarps][NT][16][8];
-    __shared__ float s_new[EPI == 2 ? NT : 1][16][8];
-    __shared__ float s_mean[16], s_rstd[16];
+    __shared__ float s_mean[MP], s_rstd[MP];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int mt = warp / KS, kw = warp % KS, rb = mt * 16;
     const int n0 = blockIdx.x * 8 * NT;
     const int nkb = p.K >> 5;
     const int w_stride = p.K * 2 + kGvWPad;              // bytes
     unsigned char* w_s = gv_smem;
     float* gam_s = reinterpret_cast<float*>(gv_smem + static_cast<size_t>(8 * NT) * w_stride);
-    float* bet_s = gam_s + p.K;
+    float* bet_s = gam_s + (IN_LN ? p.K : 0);
+    float* red_s = bet_s + (IN_LN ? p.K : 0);            // [16 warps][NT][16][8]
+    float* new_s = red_s + kGvWarps * NT * 128;          // EPI 2: [NT][MP][8]
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
@@ -109,7 +120,6 @@ __global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[nt][i] = 0.0f;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-    uint4 a_lo[kGvBatch], a_hi[kGvBatch];
     if constexpr (IN_LN) {
         for (int j = tid; j < (p.K >> 2); j += kGvThreads) {
             reinterpret_cast<float4*>(gam_s)[j] = __ldg(reinterpret_cast<const float4*>(p.gamma) + j);
@@ -118,81 +128,111 @@ __global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p)
     }
     pdl_wait();
 
-    if constexpr (IN_LN) {
-        // fp32 fragments of this warp's k-blocks (K <= 1536 -> at most 3 per warp), normalised on the fly
-        float4 xl[kGvBatch][2], xh[kGvBatch][2];
+    // which of this lane's two rows are loaded (inside M and not finished), and is the tile live at all
+    const int r_lo = rb + g, r_hi = rb + g + 8;
+    const bool use_lo = r_lo < p.M && !(p.row_skip && p.row_skip[r_lo]);
+    const bool use_hi = r_hi < p.M && !(p.row_skip && p.row_skip[r_hi]);
+    const bool tile_live = __any_sync(0xffffffffu, use_lo || use_hi);
+    const int my_blocks = (tile_live && kw < nkb) ? (nkb - kw + KS - 1) / KS : 0;      // k-blocks kw, kw + KS, ...
+    const int n_batches = (my_blocks + kGvBatch - 1) / kGvBatch;
+
+    // raw activation fragments of one batch: fp32 (LayerNorm path) or bf16
+    float4 xl[IN_LN ? kGvBatch : 1][2], xh[IN_LN ? kGvBatch : 1][2];
+    uint4 a_lo[kGvBatch], a_hi[kGvBatch], n_lo[IN_LN ? 1 : kGvBatch], n_hi[IN_LN ? 1 : kGvBatch];
+    auto load_batch = [&](int bi) {
 #pragma unroll
         for (int i = 0; i < kGvBatch; ++i) {
-            const int kb = warp + i * kGvWarps;
-            xl[i][0] = xl[i][1] = xh[i][0] = xh[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kb < nkb) {
-                const int ko = kb * 32 + t * 8;
-                if (g < p.M) {
-                    const float4* s = reinterpret_cast<const float4*>(p.x + static_cast<long long>(g) * p.K + ko);
-                    xl[i][0] = s[0];
-                    xl[i][1] = s[1];
+            const int j = bi * kGvBatch + i;
+            const int ko = (kw + j * KS) * 32 + t * 8;
+            if constexpr (IN_LN) {
+                xl[i][0] = xl[i][1] = xh[i][0] = xh[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < my_blocks) {
+                    if (use_lo) {
+                        const float4* s = reinterpret_cast<const float4*>(p.x + static_cast<long long>(r_lo) * p.K + ko);
+                        xl[i][0] = s[0];
+                        xl[i][1] = s[1];
+                    }
+                    if (use_hi) {
+                        const float4* s = reinterpret_cast<const float4*>(p.x + static_cast<long long>(r_hi) * p.K + ko);
+                        xh[i][0] = s[0];
+                        xh[i][1] = s[1];
+                    }
                 }
-                if (g + 8 < p.M) {
-                    const float4* s = reinterpret_cast<const float4*>(p.x + static_cast<long long>(g + 8) * p.K + ko);
-                    xh[i][0] = s[0];
-                    xh[i][1] = s[1];
+            } else {
+                n_lo[i] = zero4;
+                n_hi[i] = zero4;
+                if (j < my_blocks) {
+                    if (use_lo) n_lo[i] = *reinterpret_cast<const uint4*>(p.a + static_cast<long long>(r_lo) * p.K + ko);
+                    if (use_hi) n_hi[i] = *reinterpret_cast<const uint4*>(p.a + static_cast<long long>(r_hi) * p.K + ko);
                 }
             }
         }
-        {   // row `warp`: add the producer's partial statistics in a fixed order
+    };
+    if (n_batches > 0) load_batch(0);
+
+    float m_lo = 0.f, rs_lo = 0.f, m_hi = 0.f, rs_hi = 0.f;
+    if constexpr (IN_LN) {
+        // row statistics: 512 / MP threads per row add the producer's partials in a fixed order (all their loads
+        // in flight together), then an xor tree inside the row's lane group
+        {
+            constexpr int TPR = kGvThreads / MP;         // 32, 16 or 8 threads per row
+            const int r = tid / TPR, sub = tid % TPR;
             float sm = 0.0f, sq = 0.0f;
-            for (int pp = lane; pp < p.stats_parts; pp += 32) {
-                const float2 v = *reinterpret_cast<const float2*>(p.stats + (static_cast<long long>(pp) * 16 + warp) * 2);
-                sm += v.x;
-                sq += v.y;
+            if (r < p.M) {
+                for (int pp = sub; pp < p.stats_parts; pp += TPR) {
+                    const float2 v = *reinterpret_cast<const float2*>(p.stats + (static_cast<long long>(pp) * MP + r) * 2);
+                    sm += v.x;
+                    sq += v.y;
+                }
             }
-            sm = warp_sum(sm);
-            sq = warp_sum(sq);
-            if (lane == 0) {
+#pragma unroll
+            for (int o = TPR / 2; o > 0; o >>= 1) {
+                sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            }
+            if (sub == 0) {
                 const float mean = sm / p.K;
                 const float var = fmaxf(sq / p.K - mean * mean, 0.0f);
-                s_mean[warp] = mean;
-                s_rstd[warp] = rsqrtf(var + 1e-5f);
+                s_mean[r] = mean;
+                s_rstd[r] = rsqrtf(var + 1e-5f);
             }
         }
-        __syncthreads();
-        const float m_lo = s_mean[g], r_lo = s_rstd[g], m_hi = s_mean[g + 8], r_hi = s_rstd[g + 8];
-#pragma unroll
-        for (int i = 0; i < kGvBatch; ++i) {
-            const int kb = warp + i * kGvWarps;
-            a_lo[i] = zero4;
-            a_hi[i] = zero4;
-            if (kb < nkb) {
-                const int ko = kb * 32 + t * 8;
-                if (g < p.M) a_lo[i] = ln_pack8(xl[i][0], xl[i][1], m_lo, r_lo, gam_s + ko, bet_s + ko);
-                if (g + 8 < p.M) a_hi[i] = ln_pack8(xh[i][0], xh[i][1], m_hi, r_hi, gam_s + ko, bet_s + ko);
-            }
-        }
+        __syncthreads();                                 // also publishes gam_s / bet_s
+        m_lo = s_mean[r_lo];
+        rs_lo = s_rstd[r_lo];
+        m_hi = s_mean[r_hi];
+        rs_hi = s_rstd[r_hi];
     }
 
     bool w_ready = false;
-    for (int kb0 = warp; kb0 < nkb; kb0 += kGvBatch * kGvWarps) {
-        if constexpr (!IN_LN) {
+    for (int bi = 0; bi < n_batches; ++bi) {
+        // raw -> bf16 fragments of this batch, then put the next batch's loads in flight
 #pragma unroll
-            for (int i = 0; i < kGvBatch; ++i) {
-                const int kb = kb0 + i * kGvWarps;
+        for (int i = 0; i < kGvBatch; ++i) {
+            if constexpr (IN_LN) {
+                const int j = bi * kGvBatch + i;
+                const int ko = (kw + j * KS) * 32 + t * 8;
                 a_lo[i] = zero4;
                 a_hi[i] = zero4;
-                if (kb < nkb) {
-                    const int ko = kb * 32 + t * 8;
-                    if (g < p.M) a_lo[i] = *reinterpret_cast<const uint4*>(p.a + static_cast<long long>(g) * p.K + ko);
-                    if (g + 8 < p.M) a_hi[i] = *reinterpret_cast<const uint4*>(p.a + static_cast<long long>(g + 8) * p.K + ko);
+                if (j < my_blocks) {
+                    if (use_lo) a_lo[i] = ln_pack8(xl[i][0], xl[i][1], m_lo, rs_lo, gam_s + ko, bet_s + ko);
+                    if (use_hi) a_hi[i] = ln_pack8(xh[i][0], xh[i][1], m_hi, rs_hi, gam_s + ko, bet_s + ko);
                 }
+            } else {
+                a_lo[i] = n_lo[i];
+                a_hi[i] = n_hi[i];
             }
         }
+        if (bi + 1 < n_batches) load_batch(bi + 1);
         if (!w_ready) {
             mbar_wait(&bar, 0);
             w_ready = true;
         }
 #pragma unroll
         for (int i = 0; i < kGvBatch; ++i) {
-            const int kb = kb0 + i * kGvWarps;
-            if (kb < nkb) {
+            const int j = bi * kGvBatch + i;
+            if (j < my_blocks) {
+                const int kb = kw + j * KS;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const uint4 b = *reinterpret_cast<const uint4*>(w_s + static_cast<size_t>(nt * 8 + g) * w_stride + (kb * 32 + t * 8) * 2);
@@ -204,24 +244,27 @@ __global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p)
         }
     }
     if (!w_ready) mbar_wait(&bar, 0);                    // never leave bulk copies in flight behind an exited CTA
+    float* red_w = red_s + warp * (NT * 128);
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-        red[warp][nt][g][2 * t] = acc[nt][0];
-        red[warp][nt][g][2 * t + 1] = acc[nt][1];
-        red[warp][nt][g + 8][2 * t] = acc[nt][2];
-        red[warp][nt][g + 8][2 * t + 1] = acc[nt][3];
+        red_w[nt * 128 + g * 8 + 2 * t] = acc[nt][0];
+        red_w[nt * 128 + g * 8 + 2 * t + 1] = acc[nt][1];
+        red_w[nt * 128 + (g + 8) * 8 + 2 * t] = acc[nt][2];
+        red_w[nt * 128 + (g + 8) * 8 + 2 * t + 1] = acc[nt][3];
     }
     __syncthreads();
-    for (int idx = tid; idx < NT * 128; idx += kGvThreads) {
-        const int nt = idx >> 7, r = (idx & 127) >> 3, c = idx & 7;
+    for (int idx = tid; idx < MT * NT * 128; idx += kGvThreads) {
+        const int m = idx / (NT * 128), rem = idx - m * (NT * 128);
+        const int nt = rem >> 7, r = (rem & 127) >> 3, c = rem & 7;
+        const int row = m * 16 + r;
         const int n = n0 + nt * 8 + c;
         float v = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kGvWarps; ++w) v += red[w][nt][r][c];
-        const bool valid = r < p.M && n < p.N;
+        for (int w = 0; w < KS; ++w) v += red_s[(m * KS + w) * (NT * 128) + nt * 128 + r * 8 + c];
+        const bool valid = row < p.M && n < p.N;
         if (valid && p.bias) v += __ldg(p.bias + n);
-        const bool store = valid && !(p.row_skip && p.row_skip[r]);
-        const long long o = static_cast<long long>(r) * p.N + n;
+        const bool store = valid && !(p.row_skip && p.row_skip[row]);
+        const long long o = static_cast<long long>(row) * p.N + n;
         if constexpr (EPI == 0) {
             if (store) p.out_f32[o] = v;
         }
@@ -234,23 +277,23 @@ __global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p)
                 xn = p.resid[o] + (store ? v : 0.0f);
                 if (store) p.resid[o] = xn;
             }
-            s_new[nt][r][c] = xn;
+            new_s[(nt * MP + row) * 8 + c] = xn;
         }
     }
     if constexpr (EPI == 2) {
         if (p.stats_out) {
             __syncthreads();
-            if (tid < 16) {
+            if (tid < MP) {
                 float sm = 0.0f, sq = 0.0f;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const float v = s_new[nt][tid][c];
+                        const float v = new_s[(nt * MP + tid) * 8 + c];
                         sm += v;
                         sq = fmaf(v, v, sq);
                     }
-                *reinterpret_cast<float2*>(p.stats_out + (static_cast<long long>(blockIdx.x) * 16 + tid) * 2) = make_float2(sm, sq);
+                *reinterpret_cast<float2*>(p.stats_out + (static_cast<long long>(blockIdx.x) * MP + tid) * 2) = make_float2(sm, sq);
             }
         }
     }
@@ -287,7 +330,7 @@ __global__ void row_stats_kernel(const float* __restrict__ x, int K, float* __re
 }
 
 int row_stats16(const float* x, int M, int K, float* stats, cudaStream_t stream) {
-    WSB_REQUIRE(M >= 1 && M <= 16, "row_stats16 handles at most 16 rows");
+    WSB_REQUIRE(M >= 1 && M <= kGvMaxRows, "row_stats16 handles at most 64 rows");
     WSB_CHECK_CUDA(launch_kernel(row_stats_kernel, dim3(M), dim3(256), 0, stream, x, K, stats));
     count_launch();
     return 0;
@@ -297,35 +340,44 @@ int gemv16_parts(int N) {                                // CTAs (= partial stat
     const int nt = std::min(kGvMaxNT, std::max(1, ceil_div(ceil_div(N, 8), 148)));
     return ceil_div(N, 8 * nt);
 }
+int gemv16_max_rows() { return kGvMaxRows; }
 
-template <int IN_LN, int EPI, int NT>
+template <int IN_LN, int EPI, int NT, int MT>
 static int launch_gemv(const GvParams& p, cudaStream_t stream) {
-    const size_t smem = static_cast<size_t>(8 * NT) * (static_cast<size_t>(p.K) * 2 + kGvWPad) + (IN_LN ? static_cast<size_t>(p.K) * 8 : 0);
-    WSB_REQUIRE(smem <= 180 * 1024, "gemv16: weight tile does not fit in shared memory (K too large)");
+    const size_t smem = static_cast<size_t>(8 * NT) * (static_cast<size_t>(p.K) * 2 + kGvWPad) + (IN_LN ? static_cast<size_t>(p.K) * 8 : 0) +
+                        sizeof(float) * kGvWarps * NT * 128 + (EPI == 2 ? sizeof(float) * NT * 16 * MT * 8 : 0);
+    WSB_REQUIRE(smem <= kGvMaxSmem, "gemv16: weight tile does not fit in shared memory (K too large)");
     static PerDeviceOnce once;
     int dev = 0;
     if (once.need(&dev)) {
-        WSB_CHECK_CUDA(cudaFuncSetAttribute(gemv16_kernel<IN_LN, EPI, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+        WSB_CHECK_CUDA(cudaFuncSetAttribute(gemv16_kernel<IN_LN, EPI, NT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGvMaxSmem));
         once.mark(dev);
     }
-    WSB_CHECK_CUDA(launch_kernel(gemv16_kernel<IN_LN, EPI, NT>, dim3(ceil_div(p.N, 8 * NT)), dim3(kGvThreads), smem, stream, p));
+    WSB_CHECK_CUDA(launch_kernel(gemv16_kernel<IN_LN, EPI, NT, MT>, dim3(ceil_div(p.N, 8 * NT)), dim3(kGvThreads), smem, stream, p));
     count_launch();
     return 0;
 }
 
-template <int IN_LN, int EPI>
+template <int IN_LN, int EPI, int MT>
 static int dispatch_nt(const GvParams& p, int nt, cudaStream_t stream) {
     switch (nt) {
-        case 1: return launch_gemv<IN_LN, EPI, 1>(p, stream);
-        case 2: return launch_gemv<IN_LN, EPI, 2>(p, stream);
-        case 3: return launch_gemv<IN_LN, EPI, 3>(p, stream);
-        case 4: return launch_gemv<IN_LN, EPI, 4>(p, stream);
-        default: return launch_gemv<IN_LN, EPI, 5>(p, stream);
+        case 1: return launch_gemv<IN_LN, EPI, 1, MT>(p, stream);
+        case 2: return launch_gemv<IN_LN, EPI, 2, MT>(p, stream);
+        case 3: return launch_gemv<IN_LN, EPI, 3, MT>(p, stream);
+        case 4: return launch_gemv<IN_LN, EPI, 4, MT>(p, stream);
+        default: return launch_gemv<IN_LN, EPI, 5, MT>(p, stream);
     }
 }
 
+template <int IN_LN, int EPI>
+static int dispatch_mt(const GvParams& p, int nt, cudaStream_t stream) {
+    if (p.M <= 16) return dispatch_nt<IN_LN, EPI, 1>(p, nt, stream);
+    if (p.M <= 32) return dispatch_nt<IN_LN, EPI, 2>(p, nt, stream);
+    return dispatch_nt<IN_LN, EPI, 4>(p, nt, stream);
+}
+
 int gemv16(const Gemv16Args& a, cudaStream_t stream) {
-    WSB_REQUIRE(a.M >= 1 && a.M <= 16, "gemv16 handles at most 16 rows");
+    WSB_REQUIRE(a.M >= 1 && a.M <= kGvMaxRows, "gemv16 handles at most 64 rows");
     WSB_REQUIRE(a.K % 32 == 0 && a.K >= 32, "gemv16: K must be a multiple of 32");
     WSB_REQUIRE((a.x != nullptr) != (a.a != nullptr), "gemv16: exactly one of the fp32 (LayerNorm) and bf16 inputs");
     WSB_REQUIRE(!a.x || (a.K <= 1536 && a.gamma && a.beta && a.stats && a.stats_parts >= 1),
@@ -350,16 +402,19 @@ int gemv16(const Gemv16Args& a, cudaStream_t stream) {
     p.M = a.M;
     p.N = a.N;
     p.K = a.K;
-    const int nt = std::min(kGvMaxNT, std::max(1, ceil_div(ceil_div(a.N, 8), 148)));
+    int nt = std::min(kGvMaxNT, std::max(1, ceil_div(ceil_div(a.N, 8), 148)));
+    static const int nt_env = std::getenv("WSB_GEMV_NT") ? std::atoi(std::getenv("WSB_GEMV_NT")) : 0;   // diagnostics
+    if (nt_env >= 1 && nt_env <= kGvMaxNT && static_cast<size_t>(8 * nt_env) * (static_cast<size_t>(a.K) * 2 + kGvWPad) <= 160 * 1024)
+        nt = nt_env;
     const int epi = a.out_f32 ? 0 : (a.out_bf16_gelu ? 1 : 2);
     if (a.x) {
-        if (epi == 0) return dispatch_nt<1, 0>(p, nt, stream);
-        if (epi == 1) return dispatch_nt<1, 1>(p, nt, stream);
-        return dispatch_nt<1, 2>(p, nt, stream);
+        if (epi == 0) return dispatch_mt<1, 0>(p, nt, stream);
+        if (epi == 1) return dispatch_mt<1, 1>(p, nt, stream);
+        return dispatch_mt<1, 2>(p, nt, stream);
     }
-    if (epi == 0) return dispatch_nt<0, 0>(p, nt, stream);
-    if (epi == 1) return dispatch_nt<0, 1>(p, nt, stream);
-    return dispatch_nt<0, 2>(p, nt, stream);
+    if (epi == 0) return dispatch_mt<0, 0>(p, nt, stream);
+    if (epi == 1) return dispatch_mt<0, 1>(p, nt, stream);
+    return dispatch_mt<0, 2>(p, nt, stream);
 }
 
 }  // namespace wsb

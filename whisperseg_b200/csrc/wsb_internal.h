@@ -77,12 +77,13 @@ int splitk_reduce_resid_ln(const float* partial, int splits, int64_t split_strid
 int embed_tokens(const int* tokens, const int* positions, const __nv_bfloat16* emb, const float* pos_emb, float* x,
                  int B, int d, cudaStream_t stream);
 
-// ------------------------------------------------------------------ K5c skinny linear for <= 16 rows (gemv.cu)
-// out = epilogue(in[M,K] * W[N,K]^T + bias), M <= 16, one launch, no split-K.  Input: either fp32 rows `x` with
-// the consumer's LayerNorm (gamma, beta) fused in -- `stats` = [stats_parts][16][2] partial (sum, sum of squares)
+// ------------------------------------------------------------------ K5c skinny linear for <= 64 rows (gemv.cu)
+// out = epilogue(in[M,K] * W[N,K]^T + bias), M <= 64, one launch, no split-K.  MP = 16, 32 or 64 = M rounded up to
+// 1, 2 or 4 m-tiles.  Input: either fp32 rows `x` with
+// the consumer's LayerNorm (gamma, beta) fused in -- `stats` = [stats_parts][MP][2] partial (sum, sum of squares)
 // of every row, left by the producer of x -- or bf16 activations `a`.  Output: exactly one of fp32 `out_f32`,
 // bf16 `out_bf16_gelu` (GELU applied) or the in-place fp32 residual update `resid` (+=), which also writes the
-// updated rows' partial statistics to `stats_out` [gemv16_parts(N)][16][2] when given.
+// updated rows' partial statistics to `stats_out` [gemv16_parts(N)][MP][2] when given.
 struct Gemv16Args {
     const float* x = nullptr;
     const float* stats = nullptr;
@@ -100,6 +101,7 @@ struct Gemv16Args {
     int M = 0, N = 0, K = 0;
 };
 int gemv16(const Gemv16Args& a, cudaStream_t stream);
+int gemv16_max_rows();
 int gemv16_parts(int N);                                 // CTAs (= statistics partials) of a launch with N outputs
 int row_stats16(const float* x, int M, int K, float* stats, cudaStream_t stream);   // exact statistics, 1 part
 

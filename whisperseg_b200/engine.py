@@ -117,7 +117,7 @@ class Engine:
             self._enter()
             _lib.check(self.lib.wsb_generate(self.handle, batch, prompt, len(prompt_ids), eos_id, pad_id, max_length,
                                              _ptr(forced), _ptr(tokens), ctypes.byref(n_steps),
-                                             (1 if use_graph else 0) | (2 if os.environ.get("WSB_PDL") else 0) | (4 if os.environ.get("WSB_NO_COMPACT") else 0) | (8 if os.environ.get("WSB_NO_GEMV") else 0),
+                                             (1 if use_graph else 0) | (0 if os.environ.get("WSB_NO_PDL") else 2) | (4 if os.environ.get("WSB_NO_COMPACT") else 0) | (8 if os.environ.get("WSB_NO_GEMV") else 0),
                                              ctypes.c_void_p(self.stream.cuda_stream)), "wsb_generate")
             self._exit()
         return tokens, n_steps.value
