@@ -21,6 +21,7 @@ def lib():
     (128, 256, 64, 256), (128, 128, 64, 128), (256, 512, 128, 256), (1000, 1280, 1280, 256), (1000, 1280, 1280, 128),
     (777, 384, 1536, 128), (300, 1152, 384, 64), (5, 1536, 384, 32), (240, 5120, 1280, 0), (2500, 3840, 1280, 0),
     (130, 200, 64, 64), (64, 51880, 384, 0),
+    (2432 + 70, 16384, 2048, 256),      # B operand 67 MB > half of L2: grouped raster, 16 + 4 m-tiles (short last group)
 ])
 def test_gemm_plain(lib, M, N, K, bn):
     import torch

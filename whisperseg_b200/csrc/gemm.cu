@@ -51,7 +51,26 @@ struct GemmDev {
     long long split_stride;        // elements between partial planes of the output
     const unsigned char* row_skip; // optional [M]: rows flagged non-zero are not stored (finished decode rows)
     const int* n_tile_list;        // optional: only these n-tiles are computed (n_tiles = length of the list)
+    int group_m;                   // 0: tiles run n-fastest (A read from HBM once, B re-read per m-tile out of L2);
+                                   // G > 0: when B is too big for L2, super-rows of G m-tiles are walked n-outer /
+                                   // m-inner, so the CTAs in flight share a few B tiles and B streams once per super-row
 };
+
+// persistent tile index -> (split, m-tile, n-tile slot)
+__device__ __forceinline__ void tile_coords(const GemmDev& p, int tile, int& sp, int& mt, int& nti) {
+    sp = tile % p.splits;
+    const int mn = tile / p.splits;
+    if (p.group_m > 0) {
+        const int per_group = p.group_m * p.n_tiles;
+        const int g = mn / per_group, r = mn - g * per_group;
+        const int gm = min(p.group_m, p.m_tiles - g * p.group_m);     // rows of the (possibly short) last group
+        nti = r / gm;
+        mt = g * p.group_m + (r - nti * gm);
+    } else {
+        mt = mn / p.n_tiles;
+        nti = mn - mt * p.n_tiles;
+    }
+}
 
 template <int BN, int EPIW>
 struct GemmCfg {
@@ -127,8 +146,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int pre = 0;                                // stages already armed, their B tile in flight
             if (static_cast<int>(blockIdx.x) < total_tiles) {
                 const int tile = blockIdx.x;
-                const int sp = tile % p.splits, mn = tile / p.splits;
-                const int nti = mn % p.n_tiles;
+                int sp, mt, nti;
+                tile_coords(p, tile, sp, mt, nti);
                 const int nt = p.n_tile_list ? p.n_tile_list[nti] : nti;
                 const int kb0 = sp * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
                 pre = min(S, kb1 - kb0);
@@ -139,8 +158,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             pdl_wait();
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int sp = tile % p.splits, mn = tile / p.splits;
-                const int mt = mn / p.n_tiles, nti = mn - mt * p.n_tiles;
+                int sp, mt, nti;
+                tile_coords(p, tile, sp, mt, nti);
                 const int nt = p.n_tile_list ? p.n_tile_list[nti] : nti;
                 const int kb0 = sp * p.kb_per_split, kb1 = min(k_blocks, kb0 + p.kb_per_split);
                 int a_row, a_batch;
@@ -210,8 +229,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         float* tbuf = epi_buf + e * (32 * 33);            // per-warp 32x32 transpose tile (padded)
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-            const int sp = tile % p.splits, mn = tile / p.splits;
-            const int mt = mn / p.n_tiles, nti = mn - mt * p.n_tiles;
+            int sp, mt, nti;
+            tile_coords(p, tile, sp, mt, nti);
             const int nt = p.n_tile_list ? p.n_tile_list[nti] : nti;       // nti: dense slot of the arg-max partials
             const int as = local & 1;
             const uint32_t aphase = (local >> 1) & 1;
@@ -548,6 +567,9 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.splits = ceil_div(a.K / kBK, p.kb_per_split);          // drop empty trailing splits
     p.split_stride = a.split_stride;
     p.row_skip = a.row_skip;
+    // B (weights) beyond half of the 126 MB L2 (the cross-K/V projection of all decoder layers: 210 MB): walk
+    // super-rows of 16 m-tiles so that B streams from HBM once per super-row instead of once per m-tile
+    p.group_m = (static_cast<double>(a.N) * a.K * 2.0 > 64e6 && p.m_tiles > 1) ? 16 : 0;
     const int total = p.m_tiles * p.n_tiles * p.splits;
     const int grid = std::min(total, num_sms);
     WSB_CHECK_CUDA(launch_kernel(gemm_kernel<BN, EPI, EPIW>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, tmA, tmB, p));
