@@ -84,6 +84,7 @@ class Engine:
         self.n_cols = 2 * cfg["max_source_positions"]
         self.T = cfg["max_source_positions"]
         self.logmel = LogmelRunner(self.device)
+        self._stage, self._stage_evt, self._stage_elems = None, None, 4 << 20     # 2 x 16 MB pinned staging
 
     def workspace_bytes(self):
         return int(self.lib.wsb_model_workspace_bytes(self.handle))
@@ -159,7 +160,25 @@ class Engine:
         a = np.ascontiguousarray(piece, dtype=np.float32)
         if a.size == 0:
             return torch.zeros(4, dtype=torch.float32, device=self.device)
-        return torch.from_numpy(a).pin_memory().to(self.device, non_blocking=True)
+        # Two persistent pinned staging buffers: the host copy of chunk i + 1 overlaps the H2D copy of chunk i
+        # (a fresh pin_memory() of the whole recording costs a page-locking allocation per call).
+        with torch.cuda.device(self.device):
+            n = a.size
+            src = torch.from_numpy(a)
+            dev = torch.empty(n, dtype=torch.float32, device=self.device)
+            if self._stage is None:
+                self._stage = [torch.empty(self._stage_elems, dtype=torch.float32).pin_memory() for _ in range(2)]
+                self._stage_evt = [torch.cuda.Event(), torch.cuda.Event()]
+            for i, off in enumerate(range(0, n, self._stage_elems)):
+                k, m = i & 1, min(self._stage_elems, n - off)
+                if i >= 2:
+                    self._stage_evt[k].synchronize()           # the copy that last read this buffer has finished
+                self._stage[k][:m].copy_(src[off:off + m])
+                dev[off:off + m].copy_(self._stage[k][:m], non_blocking=True)
+                self._stage_evt[k].record()
+            for k in range(min(2, -(-n // self._stage_elems))):    # leave both buffers idle for the next caller
+                self._stage_evt[k].synchronize()
+            return dev
 
     def window_descriptors(self, windows, slice_start, n_valid):
         desc = np.array([[w.start - slice_start, 0, n_valid] for w in windows], dtype=np.int64).reshape(-1, 3)
