@@ -130,13 +130,16 @@ int wsb_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_
 /* Skinny linear layer for decode batches of at most 64 rows (csrc/gemv.cu): out = epilogue(in * W^T + bias) in
  * one launch.  Input: fp32 rows x_f32_dev [M][K] with the LayerNorm (gamma, beta) fused in, or (x NULL) bf16
  * activations a_bf16_dev [M][K].  w_dev bf16 [N][K].  out_mode 0: float32 [M][N]; 1: bf16 [M][N] = GELU(.);
- * 2: float32 [M][N] += (in-place residual update).  Replaces nn.Linear (+ the preceding nn.LayerNorm) of
+ * 2: float32 [M][N] += (in-place residual update).  Folded-LayerNorm form (x given, beta_dev NULL): w_dev =
+ * bf16(W o gamma), gamma_dev = c1 [N] (row sums of w_dev), bias_dev = c2 = b + W beta; the kernel reads bf16(x) and
+ * applies rstd (acc - mean c1) + c2.  Replaces nn.Linear (+ the preceding nn.LayerNorm) of
  * HF WhisperDecoderLayer (modeling_whisper.py:417-506) at small batch.                                       */
 int wsb_gemv16(const float* x_f32_dev, const float* gamma_dev, const float* beta_dev, const void* a_bf16_dev,
                const void* w_dev, const float* bias_dev, int M, int N, int K, int out_mode, void* out_dev, void* stream);
 
 /* Diagnostics: steady-state microseconds per wsb_gemv16-style launch (weights rotating through `weight_copies`
- * buffers so that they stream from HBM).  mode 0: LayerNorm -> fp32, 1: LayerNorm -> GELU bf16, 2: bf16 -> residual. */
+ * buffers so that they stream from HBM).  mode 0: LayerNorm -> fp32, 1: LayerNorm -> GELU bf16, 2: bf16 -> residual,
+ * 3 / 4: folded LayerNorm -> fp32 / GELU bf16. */
 int wsb_gemv16_bench(int M, int N, int K, int mode, int iters, int weight_copies, float* us_per_launch);
 
 /* qkv bf16 [batch*T][3*n_heads*64] (q pre-scaled) -> out bf16 [batch*T][n_heads*64] */

@@ -102,19 +102,42 @@ def test_encoder_attention(lib, B, T, H):
                                    (16, 1536, 384), (12, 384, 1536), (3, 52, 96),
                                    (17, 1280, 1280), (32, 3840, 1280), (40, 5120, 1280), (64, 1280, 5120), (64, 3840, 1280),
                                    (50, 1152, 384), (33, 384, 1536), (64, 52, 96)])
-@pytest.mark.parametrize("mode", ["ln_f32", "ln_gelu", "bf16_resid", "bf16_f32", "ln_resid", "bf16_gelu"])
+@pytest.mark.parametrize("mode", ["ln_f32", "ln_gelu", "bf16_resid", "bf16_f32", "ln_resid", "bf16_gelu", "fold_f32", "fold_gelu"])
 def test_gemv16(lib, M, N, K, mode):
     """Skinny linear for <= 64 rows (1, 2 or 4 m-tiles of 16; fused LayerNorm / bias / GELU / residual) against torch fp32 on the
     same bf16-rounded operands.  Tolerance: fp32 accumulation-order noise (2e-3 relative to the output scale),
     bf16 output rounding for the GELU mode."""
     import torch
     from whisperseg_b200 import _lib
-    if mode.startswith("ln") and K > 1536:
+    if mode.startswith(("ln", "fold")) and K > 1536:
         pytest.skip("fused LayerNorm is for d_model-wide inputs")
     torch.manual_seed(M * 31 + N + K)
     dev = "cuda"
     w = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
     bias = torch.randn(N, device=dev)
+    if mode.startswith("fold"):
+        # LayerNorm affine folded into the projection (weights.py: fold_layernorm): the kernel reads bf16(x) and
+        # applies rstd (acc - mean c1) + c2; reference = fp32 LayerNorm + linear on the unfolded fp32 weights
+        x = torch.randn(M, K, device=dev) * 3.0 + 0.5
+        gamma, beta = torch.rand(K, device=dev) + 0.5, torch.randn(K, device=dev) * 0.1
+        w32 = w.float()
+        wf = (w32 * gamma[None, :]).to(torch.bfloat16)
+        c1 = wf.float().sum(1).contiguous()
+        c2 = (bias + w32 @ beta).contiguous()
+        ref = torch.nn.functional.layer_norm(x, (K,), gamma, beta, 1e-5) @ w32.t() + bias
+        scale = max(1.0, ref.abs().max().item())
+        if mode.endswith("f32"):
+            out = torch.full((M, N), float("nan"), device=dev)
+            _lib.check(lib.wsb_gemv16(_p(x), _p(c1), _p(None), _p(None), _p(wf), _p(c2), M, N, K, 0, _p(out), None), "gemv16 fold")
+            torch.cuda.synchronize()
+            assert (out - ref).abs().max().item() < 6e-3 * scale      # bf16 rounding of x and of W o gamma
+        else:
+            out = torch.zeros((M, N), device=dev, dtype=torch.bfloat16)
+            _lib.check(lib.wsb_gemv16(_p(x), _p(c1), _p(None), _p(None), _p(wf), _p(c2), M, N, K, 1, _p(out), None), "gemv16 fold")
+            torch.cuda.synchronize()
+            refg = torch.nn.functional.gelu(ref)
+            assert (out.float() - refg).abs().max().item() < 1.2e-2 * scale
+        return
     if mode.startswith("ln"):
         x = torch.randn(M, K, device=dev) * 3.0 + 0.5
         gamma, beta = torch.rand(K, device=dev) + 0.5, torch.randn(K, device=dev) * 0.1

@@ -58,9 +58,17 @@ def test_encoder_matches_golden_probe(setup, golden_dir):
     assert err.max() <= 0.08
 
 
-def test_decoder_teacher_forced(setup):
+@pytest.mark.parametrize("path", ["fused-folded-ln", "fused-exact-ln", "tcgen05-splitk"])
+def test_decoder_teacher_forced(setup, monkeypatch, path):
+    """All three decode implementations of the linear layers against the fp32 oracle: the <= 64-row fused kernels
+    with the LayerNorm folded into the projection (default), the same kernels with the exact on-the-fly LayerNorm
+    (WSB_NO_FOLD=1), and the tcgen05 split-K GEMM + reduce pair used above 64 rows (WSB_NO_GEMV=1)."""
     import torch
     from tools import synth
+    if path == "fused-exact-ln":
+        monkeypatch.setenv("WSB_NO_FOLD", "1")
+    elif path == "tcgen05-splitk":
+        monkeypatch.setenv("WSB_NO_GEMV", "1")
     seg, orc, hf, x = setup["seg"], setup["orc"], setup["hf"], setup["x"]
     eng = seg.engines[0]
     tok = seg.tokenizer
@@ -88,8 +96,8 @@ def test_decoder_teacher_forced(setup):
     confident = valid & (margins > BF16_MARGIN)
     conf = ((got == ids) & confident).sum().item() / max(1, confident.sum().item())
     mism = margins[valid & (got != ids)]
-    print("teacher-forced agreement: raw %.4f (%d positions), margin>%.2f: %.4f (%d positions); "
-          "oracle margins at mismatches: %s" % (raw, valid.sum().item(), BF16_MARGIN, conf, confident.sum().item(),
+    print("teacher-forced agreement [%s]: raw %.4f (%d positions), margin>%.2f: %.4f (%d positions); "
+          "oracle margins at mismatches: %s" % (path, raw, valid.sum().item(), BF16_MARGIN, conf, confident.sum().item(),
                                                  [round(float(v), 4) for v in mism[:12]]))
     assert conf >= 0.999
     assert raw >= 0.90
@@ -169,10 +177,13 @@ def test_batch_compaction_equals_uncompacted(tiny_checkpoint, monkeypatch):
 
 @pytest.mark.parametrize("seconds,max_batch", [(13.0, 16), (29.0, 32), (45.0, 64)])
 def test_small_batch_linear_path_matches_tensor_core_path(tiny_checkpoint, monkeypatch, seconds, max_batch):
-    """Batches of <= 64 rows (1, 2 or 4 m-tiles of 16) run the fused LayerNorm + mma.sync linear kernels (gemv.cu) instead of the tcgen05
-    split-K GEMM + reduce pair.  Same bf16 operands, fp32 accumulation in a different order: teacher-forced on
-    the tensor-core path's own tokens, the per-position arg-max must agree on >= 99 % of the positions (near-ties of a random-init model flip), and
-    the free-running outputs of most rows must be identical."""
+    """Batches of <= 64 rows (1, 2 or 4 m-tiles of 16) run the fused mma.sync linear kernels (gemv.cu) instead of the
+    tcgen05 split-K GEMM + reduce pair, with the LayerNorm folded into the projection (the kernel reads bf16(x) and
+    applies rstd (acc - mean c1) + c2), so the two paths round different quantities to bf16: independent rounding
+    noise of the same size.  Teacher-forced on the tensor-core path's own tokens, the per-position arg-max must agree
+    on >= 98.5 % of the positions (near-ties of a random-init model flip; 99.0-99.1 % measured, 99.2-99.7 % with the
+    exact on-the-fly LayerNorm, WSB_NO_FOLD=1), and the free-running outputs of most rows must be identical.  Parity
+    of this path against the fp32 oracle is asserted by the teacher-forced tests above (they run <= 64 rows)."""
     import torch
     from tools import synth
     from whisperseg_b200.frontend import FrontendPlan
@@ -201,5 +212,5 @@ def test_small_batch_linear_path_matches_tensor_core_path(tiny_checkpoint, monke
     tf_old, _ = eng.generate(n, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length, forced=forced, use_graph=False)
     agree = (tf_new == tf_old).float().mean().item()
     print("small-batch path: %d windows, free-running rows identical %.3f, teacher-forced arg-max agreement %.4f" % (n, same_rows, agree))
-    assert agree >= 0.99
+    assert agree >= 0.985
     assert same_rows >= 0.75

@@ -9,7 +9,8 @@ from whisperseg_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
 shapes = [("qkv  LN->f32 ", 3840, 1280, 0), ("cq   LN->f32 ", 1280, 1280, 0), ("fc1  LN->gelu", 5120, 1280, 1),
-          ("so/co  ->res ", 1280, 1280, 2), ("fc2    ->res ", 1280, 5120, 2)]
+          ("so/co  ->res ", 1280, 1280, 2), ("fc2    ->res ", 1280, 5120, 2),
+          ("qkv  fold->f32", 3840, 1280, 3), ("cq   fold->f32", 1280, 1280, 3), ("fc1  fold->gelu", 5120, 1280, 4)]
 rows = [int(a) for a in sys.argv[1:]] or [16, 32, 48, 64]
 print("NT override:", os.environ.get("WSB_GEMV_NT", "auto"))
 for name, N, K, mode in shapes:

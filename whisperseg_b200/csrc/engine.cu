@@ -103,6 +103,10 @@ struct DecLayer {
     const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
     const __nv_bfloat16 *sqkv_w, *so_w, *cq_w, *co_w, *fc1_w, *fc2_w;
     const float *sqkv_b, *so_b, *cq_b, *co_b, *fc1_b, *fc2_b;
+    // optional (all or none): the three LayerNorm-consuming projections with the LayerNorm affine folded in --
+    // *_wf = bf16(W o gamma), *_c1[n] = sum_k wf[n][k], *_c2 = b + W beta (weights.py: fold_layernorm)
+    const __nv_bfloat16 *sqkv_wf = nullptr, *cq_wf = nullptr, *fc1_wf = nullptr;
+    const float *sqkv_c1 = nullptr, *sqkv_c2 = nullptr, *cq_c1 = nullptr, *cq_c2 = nullptr, *fc1_c1 = nullptr, *fc1_c2 = nullptr;
 };
 
 struct Model {
@@ -139,6 +143,7 @@ struct Model {
     std::map<std::tuple<int, int, int, int, int, int, int>, GraphEntry> graphs;
     bool use_pdl = false;
     bool use_gemv = true;               // few decode rows: fused LN + mma.sync linear layers (gemv.cu)
+    bool use_fold = true;               // ... with the LayerNorm folded into the projection when the folded tensors exist
     int gemv_rows = 64;                 // ... used up to this many rows (WSB_GEMV_ROWS, <= 64)
     std::vector<int> ladder{64, 32, 16};   // compaction levels, descending, all <= kCompactRows (override: WSB_LADDER=64,16)
     int* pinned_active = nullptr;
@@ -294,6 +299,11 @@ static int model_create(const wsb_model_config* cfg, const char* const* names, c
         WSB_GET(e.ln3_g, p + "ln3.g"); WSB_GET(e.ln3_b, p + "ln3.b");
         WSB_GET(e.fc1_w, p + "fc1.w"); WSB_GET(e.fc1_b, p + "fc1.b");
         WSB_GET(e.fc2_w, p + "fc2.w"); WSB_GET(e.fc2_b, p + "fc2.b");
+        if (tab.count(p + "sqkv.wf")) {
+            WSB_GET(e.sqkv_wf, p + "sqkv.wf"); WSB_GET(e.sqkv_c1, p + "sqkv.c1"); WSB_GET(e.sqkv_c2, p + "sqkv.c2");
+            WSB_GET(e.cq_wf, p + "cq.wf"); WSB_GET(e.cq_c1, p + "cq.c1"); WSB_GET(e.cq_c2, p + "cq.c2");
+            WSB_GET(e.fc1_wf, p + "fc1.wf"); WSB_GET(e.fc1_c1, p + "fc1.c1"); WSB_GET(e.fc1_c2, p + "fc1.c2");
+        }
     }
     m->logits_bn = gemm_pick_block_n(cfg->max_batch, cfg->vocab_size);
     {   // vocabulary tiles in which every token is suppressed (additive -inf mask) can never win the arg-max:
@@ -476,20 +486,31 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
         // The residual stream's row statistics travel with it: embed -> (exact) -> qkv; out-proj -> cq;
         // cross-out -> fc1; fc2 -> next layer's qkv.
         int parts = 1;
+        // folded LayerNorm (default when the checkpoint loader provided the folded tensors): the consumers read the
+        // residual stream as bf16 (m->dxn, written next to the fp32 stream by its producer) and apply
+        // rstd (acc - mean c1) + c2 in their epilogue; WSB_NO_FOLD=1 keeps the exact on-the-fly LayerNorm
+        const bool fold = m->use_fold && m->dec[0].sqkv_wf != nullptr;
         {
             ProfScope ps(PROF_DEC_LN, 4.0 * B * d, s);
-            WSB_RUN(row_stats16(m->dx, B, d, m->gv_stats, s));
+            WSB_RUN(row_stats16(m->dx, B, d, m->gv_stats, s, fold ? m->dxn : nullptr));
         }
-        auto lin_ln = [&](const float* g_, const float* b_, const __nv_bfloat16* W, const float* bias, int N, float* out_f32,
-                          __nv_bfloat16* out_gelu) -> int {
+        auto lin_ln = [&](const float* g_, const float* b_, const __nv_bfloat16* W, const float* bias, const __nv_bfloat16* Wf,
+                          const float* c1, const float* c2, int N, float* out_f32, __nv_bfloat16* out_gelu) -> int {
             Gemv16Args ga;
-            ga.x = m->dx;
+            if (fold) {
+                ga.a = m->dxn;
+                ga.c1 = c1;
+                ga.W = Wf;
+                ga.bias = c2;
+            } else {
+                ga.x = m->dx;
+                ga.gamma = g_;
+                ga.beta = b_;
+                ga.W = W;
+                ga.bias = bias;
+            }
             ga.stats = m->gv_stats;
             ga.stats_parts = parts;
-            ga.gamma = g_;
-            ga.beta = b_;
-            ga.W = W;
-            ga.bias = bias;
             ga.out_f32 = out_f32;
             ga.out_bf16_gelu = out_gelu;
             ga.row_skip = fin;
@@ -505,6 +526,7 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
             ga.W = W;
             ga.bias = bias;
             ga.resid = m->dx;
+            ga.xb_out = fold ? m->dxn : nullptr;
             ga.stats_out = m->gv_stats;
             ga.row_skip = fin;
             ga.M = B;
@@ -520,16 +542,16 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
             part.planes = m->dpart;
             part.splits = 1;
             part.bias = nullptr;
-            WSB_RUN(lin_ln(e.ln1_g, e.ln1_b, e.sqkv_w, e.sqkv_b, 3 * d, m->dpart, nullptr));
+            WSB_RUN(lin_ln(e.ln1_g, e.ln1_b, e.sqkv_w, e.sqkv_b, e.sqkv_wf, e.sqkv_c1, e.sqkv_c2, 3 * d, m->dpart, nullptr));
             part.split_stride = static_cast<long long>(B) * 3 * d;
             WSB_RUN(decode_self_attention(nullptr, &part, d, st.k_cache + l * cache_l, st.v_cache + l * cache_l, tmax, m->step, 0,
                                           fin, m->datt, B, H, s, st.anc, st.anc_ld));
             WSB_RUN(lin_resid(m->datt, e.so_w, e.so_b, d));
-            WSB_RUN(lin_ln(e.ln2_g, e.ln2_b, e.cq_w, e.cq_b, d, m->dpart, nullptr));
+            WSB_RUN(lin_ln(e.ln2_g, e.ln2_b, e.cq_w, e.cq_b, e.cq_wf, e.cq_c1, e.cq_c2, d, m->dpart, nullptr));
             part.split_stride = static_cast<long long>(B) * d;
             WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s, st.kv_div));
             WSB_RUN(lin_resid(m->datt, e.co_w, e.co_b, d));
-            WSB_RUN(lin_ln(e.ln3_g, e.ln3_b, e.fc1_w, e.fc1_b, F, nullptr, m->dff));
+            WSB_RUN(lin_ln(e.ln3_g, e.ln3_b, e.fc1_w, e.fc1_b, e.fc1_wf, e.fc1_c1, e.fc1_c2, F, nullptr, m->dff));
             WSB_RUN(lin_resid(m->dff, e.fc2_w, e.fc2_b, F));
         }
         if (with_logits) WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec_ln_g, m->dec_ln_b, m->dxn, nullptr, B, d, s));
@@ -616,6 +638,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     m->use_pdl = (flags & 2) != 0;                      // bit1: programmatic dependent launch (GEMM weight tiles and gemv weight rows
                                                         // are fetched before the dependency wait)
     m->use_gemv = (flags & 8) == 0;                     // bit3: keep the tcgen05 split-K path for small batches too
+    m->use_fold = std::getenv("WSB_NO_FOLD") == nullptr;
     if (const char* e = std::getenv("WSB_GEMV_ROWS")) m->gemv_rows = std::max(0, std::min(64, std::atoi(e)));
     if (const char* e = std::getenv("WSB_LADDER")) {
         std::vector<int> lv;
@@ -681,7 +704,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     const bool allow_compaction = (flags & 4) == 0 && forced == nullptr;
     Model::GraphEntry* graph = nullptr;
     auto get_graph = [&](const DecState& cur, Model::GraphEntry** out) -> int {
-        const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 32 * m->gemv_rows : 16), cur.row_map != nullptr ? 1 : 0, max_new,
+        const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 32 * m->gemv_rows + (m->use_fold ? 4096 : 0) : 16), cur.row_map != nullptr ? 1 : 0, max_new,
                                          prompt_len, eos_id, pad_id);
         auto it = m->graphs.find(key);
         if (it == m->graphs.end()) {
@@ -1073,15 +1096,28 @@ int wsb_gemv16(const float* x_f32_dev, const float* gamma_dev, const float* beta
         ~Free() { cudaFree(p); }
     } guard{stats};
     WSB_CHECK_CUDA(cudaMalloc(&stats, sizeof(float) * 160 * 128 * 2));
-    if (x_f32_dev) {                                      // stand-alone use: exact row statistics, one part
+    __nv_bfloat16* xb = nullptr;
+    struct FreeB {
+        __nv_bfloat16*& p;
+        ~FreeB() { cudaFree(p); }
+    } guard_b{xb};
+    g.a = static_cast<const __nv_bfloat16*>(a_bf16_dev);
+    if (x_f32_dev && gamma_dev && !beta_dev) {            // folded LayerNorm: gamma_dev = c1, w_dev = bf16(W o gamma), bias_dev = c2
+        WSB_REQUIRE(M >= 1 && M <= gemv16_max_rows() && K >= 32, "gemv16 shape");
+        WSB_CHECK_CUDA(cudaMalloc(&xb, sizeof(__nv_bfloat16) * static_cast<size_t>(M) * K));
+        WSB_RUN(row_stats16(x_f32_dev, M, K, stats, s, xb));
+        g.a = xb;
+        g.c1 = gamma_dev;
+        g.stats = stats;
+        g.stats_parts = 1;
+    } else if (x_f32_dev) {                               // stand-alone use: exact row statistics, one part
         WSB_RUN(row_stats16(x_f32_dev, M, K, stats, s));
         g.x = x_f32_dev;
         g.stats = stats;
         g.stats_parts = 1;
+        g.gamma = gamma_dev;
+        g.beta = beta_dev;
     }
-    g.gamma = gamma_dev;
-    g.beta = beta_dev;
-    g.a = static_cast<const __nv_bfloat16*>(a_bf16_dev);
     g.W = static_cast<const __nv_bfloat16*>(w_dev);
     g.bias = bias_dev;
     if (out_mode == 0) g.out_f32 = static_cast<float*>(out_dev);
@@ -1099,7 +1135,7 @@ int wsb_gemv16(const float* x_f32_dev, const float* gamma_dev, const float* beta
 }
 int wsb_gemv16_bench(int M, int N, int K, int mode, int iters, int weight_copies, float* us_per_launch) {
     // diagnostics: steady-state time of one skinny-linear launch; the weights rotate through `weight_copies`
-    // buffers so that they come from HBM, not L2.  mode 0: LN -> fp32, 1: LN -> GELU bf16, 2: bf16 -> residual
+    // buffers so that they come from HBM, not L2.  mode 0: LN -> fp32, 1: LN -> GELU bf16, 2: bf16 -> residual, 3 / 4: folded LN -> fp32 / GELU bf16
     WSB_REQUIRE(M >= 1 && M <= gemv16_max_rows() && iters >= 1 && weight_copies >= 1 && us_per_launch, "bad arguments");
     const size_t wn = static_cast<size_t>(N) * K;
     __nv_bfloat16 *w = nullptr, *a = nullptr;
@@ -1132,12 +1168,17 @@ int wsb_gemv16_bench(int M, int N, int K, int mode, int iters, int weight_copies
         g.stats_parts = gemv16_parts(K);
         g.gamma = gb;
         g.beta = gb + K;
+    } else if (mode >= 3) {                             // folded LayerNorm: 3 -> fp32, 4 -> GELU bf16
+        g.a = a;
+        g.c1 = gb + 2 * K;
+        g.stats = stats;
+        g.stats_parts = gemv16_parts(K);
     } else {
         g.a = a;
     }
     g.bias = gb + 2 * K;
-    if (mode == 0) g.out_f32 = out;
-    else if (mode == 1) g.out_bf16_gelu = reinterpret_cast<__nv_bfloat16*>(out);
+    if (mode == 0 || mode == 3) g.out_f32 = out;
+    else if (mode == 1 || mode == 4) g.out_bf16_gelu = reinterpret_cast<__nv_bfloat16*>(out);
     else {
         g.resid = out;
         g.stats_out = stats + 160 * 128;

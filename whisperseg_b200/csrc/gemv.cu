@@ -42,12 +42,15 @@ struct GvParams {
     const float* gamma;
     const float* beta;
     const __nv_bfloat16* a;             // ... or bf16 activations [M][K]
+    const float* c1;                    // IN_LN 2 (folded LayerNorm): a = bf16(x), W = bf16(W o gamma), c1[n] = sum_k W[n][k],
+                                        // bias = b + W beta; out = rstd (acc - mean c1) + bias, statistics as for IN_LN 1
     const __nv_bfloat16* W;             // [N][K]
     const float* bias;                  // [N] or null
     float* out_f32;                     // EPI 0: [M][N]
     __nv_bfloat16* out_bf16;            // EPI 1: [M][N] = gelu(.)
     float* resid;                       // EPI 2: [M][N] += .
     float* stats_out;                   // EPI 2: [gridDim.x][MP][2] partial row statistics of the updated rows
+    __nv_bfloat16* xb_out;              // EPI 2, optional: bf16 copy of the updated rows (input of a folded-LayerNorm consumer)
     const unsigned char* row_skip;      // [M] or null: rows not stored
     int M, N, K;
 };
@@ -94,8 +97,8 @@ __global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p)
     const int w_stride = p.K * 2 + kGvWPad;              // bytes
     unsigned char* w_s = gv_smem;
     float* gam_s = reinterpret_cast<float*>(gv_smem + static_cast<size_t>(8 * NT) * w_stride);
-    float* bet_s = gam_s + (IN_LN ? p.K : 0);
-    float* red_s = bet_s + (IN_LN ? p.K : 0);            // [16 warps][NT][16][8]
+    float* bet_s = gam_s + (IN_LN == 1 ? p.K : 0);
+    float* red_s = bet_s + (IN_LN == 1 ? p.K : 0);            // [16 warps][NT][16][8]
     float* new_s = red_s + kGvWarps * NT * 128;          // EPI 2: [NT][MP][8]
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[nt][i] = 0.0f;
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-    if constexpr (IN_LN) {
+    if constexpr (IN_LN == 1) {
         for (int j = tid; j < (p.K >> 2); j += kGvThreads) {
             reinterpret_cast<float4*>(gam_s)[j] = __ldg(reinterpret_cast<const float4*>(p.gamma) + j);
             reinterpret_cast<float4*>(bet_s)[j] = __ldg(reinterpret_cast<const float4*>(p.beta) + j);
@@ -137,14 +140,14 @@ __global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p)
     const int n_batches = (my_blocks + kGvBatch - 1) / kGvBatch;
 
     // raw activation fragments of one batch: fp32 (LayerNorm path) or bf16
-    float4 xl[IN_LN ? kGvBatch : 1][2], xh[IN_LN ? kGvBatch : 1][2];
-    uint4 a_lo[kGvBatch], a_hi[kGvBatch], n_lo[IN_LN ? 1 : kGvBatch], n_hi[IN_LN ? 1 : kGvBatch];
+    float4 xl[IN_LN == 1 ? kGvBatch : 1][2], xh[IN_LN == 1 ? kGvBatch : 1][2];
+    uint4 a_lo[kGvBatch], a_hi[kGvBatch], n_lo[IN_LN == 1 ? 1 : kGvBatch], n_hi[IN_LN == 1 ? 1 : kGvBatch];
     auto load_batch = [&](int bi) {
 #pragma unroll
         for (int i = 0; i < kGvBatch; ++i) {
             const int j = bi * kGvBatch + i;
             const int ko = (kw + j * KS) * 32 + t * 8;
-            if constexpr (IN_LN) {
+            if constexpr (IN_LN == 1) {
                 xl[i][0] = xl[i][1] = xh[i][0] = xh[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (j < my_blocks) {
                     if (use_lo) {
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p)
     if (n_batches > 0) load_batch(0);
 
     float m_lo = 0.f, rs_lo = 0.f, m_hi = 0.f, rs_hi = 0.f;
-    if constexpr (IN_LN) {
+    if constexpr (IN_LN != 0) {
         // row statistics: 512 / MP threads per row add the producer's partials in a fixed order (all their loads
         // in flight together), then an xor tree inside the row's lane group
         {
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p)
         // raw -> bf16 fragments of this batch, then put the next batch's loads in flight
 #pragma unroll
         for (int i = 0; i < kGvBatch; ++i) {
-            if constexpr (IN_LN) {
+            if constexpr (IN_LN == 1) {
                 const int j = bi * kGvBatch + i;
                 const int ko = (kw + j * KS) * 32 + t * 8;
                 a_lo[i] = zero4;
@@ -262,6 +265,9 @@ __global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p)
 #pragma unroll
         for (int w = 0; w < KS; ++w) v += red_s[(m * KS + w) * (NT * 128) + nt * 128 + r * 8 + c];
         const bool valid = row < p.M && n < p.N;
+        if constexpr (IN_LN == 2) {
+            if (valid) v = s_rstd[row] * (v - s_mean[row] * __ldg(p.c1 + n));
+        }
         if (valid && p.bias) v += __ldg(p.bias + n);
         const bool store = valid && !(p.row_skip && p.row_skip[row]);
         const long long o = static_cast<long long>(row) * p.N + n;
@@ -275,7 +281,10 @@ __global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p)
             float xn = 0.0f;
             if (valid) {
                 xn = p.resid[o] + (store ? v : 0.0f);
-                if (store) p.resid[o] = xn;
+                if (store) {
+                    p.resid[o] = xn;
+                    if (p.xb_out) p.xb_out[o] = __float2bfloat16(xn);
+                }
             }
             new_s[(nt * MP + row) * 8 + c] = xn;
         }
@@ -300,13 +309,14 @@ __global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p)
 }
 
 // exact (sum, sum of squares) of every row: the statistics of a residual stream that no gemv16 launch produced
-__global__ void row_stats_kernel(const float* __restrict__ x, int K, float* __restrict__ stats) {
+__global__ void row_stats_kernel(const float* __restrict__ x, int K, float* __restrict__ stats, __nv_bfloat16* __restrict__ xb) {
     const int r = blockIdx.x;
     pdl_wait();
     pdl_launch_dependents();
     float sm = 0.0f, sq = 0.0f;
     for (int j = threadIdx.x; j < K; j += blockDim.x) {
         const float v = x[static_cast<long long>(r) * K + j];
+        if (xb) xb[static_cast<long long>(r) * K + j] = __float2bfloat16(v);
         sm += v;
         sq = fmaf(v, v, sq);
     }
@@ -329,9 +339,9 @@ __global__ void row_stats_kernel(const float* __restrict__ x, int K, float* __re
     }
 }
 
-int row_stats16(const float* x, int M, int K, float* stats, cudaStream_t stream) {
+int row_stats16(const float* x, int M, int K, float* stats, cudaStream_t stream, __nv_bfloat16* xb) {
     WSB_REQUIRE(M >= 1 && M <= kGvMaxRows, "row_stats16 handles at most 64 rows");
-    WSB_CHECK_CUDA(launch_kernel(row_stats_kernel, dim3(M), dim3(256), 0, stream, x, K, stats));
+    WSB_CHECK_CUDA(launch_kernel(row_stats_kernel, dim3(M), dim3(256), 0, stream, x, K, stats, xb));
     count_launch();
     return 0;
 }
@@ -344,7 +354,7 @@ int gemv16_max_rows() { return kGvMaxRows; }
 
 template <int IN_LN, int EPI, int NT, int MT>
 static int launch_gemv(const GvParams& p, cudaStream_t stream) {
-    const size_t smem = static_cast<size_t>(8 * NT) * (static_cast<size_t>(p.K) * 2 + kGvWPad) + (IN_LN ? static_cast<size_t>(p.K) * 8 : 0) +
+    const size_t smem = static_cast<size_t>(8 * NT) * (static_cast<size_t>(p.K) * 2 + kGvWPad) + (IN_LN == 1 ? static_cast<size_t>(p.K) * 8 : 0) +
                         sizeof(float) * kGvWarps * NT * 128 + (EPI == 2 ? sizeof(float) * NT * 16 * MT * 8 : 0);
     WSB_REQUIRE(smem <= kGvMaxSmem, "gemv16: weight tile does not fit in shared memory (K too large)");
     static PerDeviceOnce once;
@@ -382,6 +392,7 @@ int gemv16(const Gemv16Args& a, cudaStream_t stream) {
     WSB_REQUIRE((a.x != nullptr) != (a.a != nullptr), "gemv16: exactly one of the fp32 (LayerNorm) and bf16 inputs");
     WSB_REQUIRE(!a.x || (a.K <= 1536 && a.gamma && a.beta && a.stats && a.stats_parts >= 1),
                 "gemv16: fused LayerNorm needs gamma/beta, row statistics and K <= 1536");
+    WSB_REQUIRE(!a.c1 || (a.a && a.stats && a.stats_parts >= 1 && !a.resid), "gemv16: folded LayerNorm needs bf16 rows and row statistics");
     const int outs = (a.out_f32 != nullptr) + (a.out_bf16_gelu != nullptr) + (a.resid != nullptr);
     WSB_REQUIRE(outs == 1, "gemv16: exactly one output mode");
     WSB_REQUIRE(ceil_div(a.N, 8 * kGvMaxNT) <= 1024, "gemv16: N too large");
@@ -392,6 +403,8 @@ int gemv16(const Gemv16Args& a, cudaStream_t stream) {
     p.gamma = a.gamma;
     p.beta = a.beta;
     p.a = a.a;
+    p.c1 = a.c1;
+    p.xb_out = a.xb_out;
     p.W = a.W;
     p.bias = a.bias;
     p.out_f32 = a.out_f32;
@@ -411,6 +424,10 @@ int gemv16(const Gemv16Args& a, cudaStream_t stream) {
         if (epi == 0) return dispatch_mt<1, 0>(p, nt, stream);
         if (epi == 1) return dispatch_mt<1, 1>(p, nt, stream);
         return dispatch_mt<1, 2>(p, nt, stream);
+    }
+    if (a.c1) {
+        if (epi == 0) return dispatch_mt<2, 0>(p, nt, stream);
+        return dispatch_mt<2, 1>(p, nt, stream);
     }
     if (epi == 0) return dispatch_mt<0, 0>(p, nt, stream);
     if (epi == 1) return dispatch_mt<0, 1>(p, nt, stream);

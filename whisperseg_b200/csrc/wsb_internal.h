@@ -92,6 +92,8 @@ struct Gemv16Args {
     const float* gamma = nullptr;
     const float* beta = nullptr;
     const __nv_bfloat16* a = nullptr;
+    const float* c1 = nullptr;           // folded LayerNorm: a = bf16(x), W = bf16(W o gamma), c1 = row sums of W, bias = b + W beta
+    __nv_bfloat16* xb_out = nullptr;     // residual mode: also write the updated rows as bf16
     const __nv_bfloat16* W = nullptr;
     const float* bias = nullptr;
     float* out_f32 = nullptr;
@@ -103,7 +105,8 @@ struct Gemv16Args {
 int gemv16(const Gemv16Args& a, cudaStream_t stream);
 int gemv16_max_rows();
 int gemv16_parts(int N);                                 // CTAs (= statistics partials) of a launch with N outputs
-int row_stats16(const float* x, int M, int K, float* stats, cudaStream_t stream);   // exact statistics, 1 part
+int row_stats16(const float* x, int M, int K, float* stats, cudaStream_t stream,
+                __nv_bfloat16* xb = nullptr);            // exact statistics, 1 part (+ optional bf16 copy of x)
 
 // ------------------------------------------------------------------ K4 encoder attention (attention.cu)
 int encoder_attention(const __nv_bfloat16* qkv /*[B*T, 3d]*/, __nv_bfloat16* out /*[B*T, d]*/, int B, int T,

@@ -82,6 +82,15 @@ def prepare_tensors(cfg, sd, gen, device):
     out["enc.ln.g"] = f32(g("model.encoder.layer_norm.weight"))
     out["enc.ln.b"] = f32(g("model.encoder.layer_norm.bias"))
 
+    def fold_layernorm(w, b, gamma, beta):
+        """LayerNorm affine folded into the projection that consumes it (decode at <= 64 rows, csrc/gemv.cu):
+        W LN(x) + b = rstd (Wf x - mean c1) + c2 with Wf = W o gamma, c1 = row sums of Wf *as rounded to bf16*
+        (the kernel multiplies exactly those values), c2 = b + W beta."""
+        wf = (w * gamma[None, :]).to(torch.bfloat16)
+        c1 = wf.to(torch.float32).sum(1)
+        c2 = (b if b is not None else 0.0) + w @ beta
+        return wf.contiguous().to(device), c1.contiguous().to(device), c2.to(torch.float32).contiguous().to(device)
+
     def attn_qkv(prefix):
         qw, kw, vw = g(prefix + "q_proj.weight") * scale, g(prefix + "k_proj.weight"), g(prefix + "v_proj.weight")
         qb, vb = g(prefix + "q_proj.bias") * scale, g(prefix + "v_proj.bias")
@@ -107,13 +116,20 @@ def prepare_tensors(cfg, sd, gen, device):
         out[o + "ln1.g"], out[o + "ln1.b"] = f32(g(p + "self_attn_layer_norm.weight")), f32(g(p + "self_attn_layer_norm.bias"))
         w, b = attn_qkv(p + "self_attn.")
         out[o + "sqkv.w"], out[o + "sqkv.b"] = bf16(w), f32(b)
+        out[o + "sqkv.wf"], out[o + "sqkv.c1"], out[o + "sqkv.c2"] = fold_layernorm(
+            w, b, g(p + "self_attn_layer_norm.weight"), g(p + "self_attn_layer_norm.bias"))
         out[o + "so.w"], out[o + "so.b"] = bf16(g(p + "self_attn.out_proj.weight")), f32(g(p + "self_attn.out_proj.bias"))
         out[o + "ln2.g"], out[o + "ln2.b"] = f32(g(p + "encoder_attn_layer_norm.weight")), f32(g(p + "encoder_attn_layer_norm.bias"))
         out[o + "cq.w"] = bf16(g(p + "encoder_attn.q_proj.weight") * scale)
         out[o + "cq.b"] = f32(g(p + "encoder_attn.q_proj.bias") * scale)
+        out[o + "cq.wf"], out[o + "cq.c1"], out[o + "cq.c2"] = fold_layernorm(
+            g(p + "encoder_attn.q_proj.weight") * scale, g(p + "encoder_attn.q_proj.bias") * scale,
+            g(p + "encoder_attn_layer_norm.weight"), g(p + "encoder_attn_layer_norm.bias"))
         out[o + "co.w"], out[o + "co.b"] = bf16(g(p + "encoder_attn.out_proj.weight")), f32(g(p + "encoder_attn.out_proj.bias"))
         out[o + "ln3.g"], out[o + "ln3.b"] = f32(g(p + "final_layer_norm.weight")), f32(g(p + "final_layer_norm.bias"))
         out[o + "fc1.w"], out[o + "fc1.b"] = bf16(g(p + "fc1.weight")), f32(g(p + "fc1.bias"))
+        out[o + "fc1.wf"], out[o + "fc1.c1"], out[o + "fc1.c2"] = fold_layernorm(
+            g(p + "fc1.weight"), g(p + "fc1.bias"), g(p + "final_layer_norm.weight"), g(p + "final_layer_norm.bias"))
         out[o + "fc2.w"], out[o + "fc2.b"] = bf16(g(p + "fc2.weight")), f32(g(p + "fc2.bias"))
         vb = g(p + "encoder_attn.v_proj.bias")
         ckw += [g(p + "encoder_attn.k_proj.weight"), g(p + "encoder_attn.v_proj.weight")]
