@@ -117,6 +117,37 @@ def test_weight_preparation_layouts(tiny):
     assert (t["dec.suppress"] == 0).sum().item() == len(synth.allowed_token_ids())
 
 
+def test_layernorm_fold_matches_hf_modules(tiny):
+    """weights.py: fold_layernorm -- the three LayerNorm-consuming projections of a decoder layer with the LayerNorm
+    affine folded in (what csrc/gemv.cu multiplies at <= 64 decode rows): rstd (Wf bf16(x) - mean c1) + c2 must
+    reproduce HF's own LayerNorm -> Linear modules (modeling_whisper.py:417-506) within bf16 operand rounding."""
+    from whisperseg_b200.weights import load_checkpoint, prepare_tensors
+    cfg, sd, gen = load_checkpoint(tiny["path"])
+    t = prepare_tensors(cfg, sd, gen, "cpu")
+    d = cfg["d_model"]
+    layer = tiny["hf"].model.decoder.layers[1]
+    torch.manual_seed(5)
+    x = torch.randn(24, d) * 2.5 + 0.3
+    mean = x.mean(1, keepdim=True)
+    rstd = torch.rsqrt(x.var(1, unbiased=False, keepdim=True) + 1e-5)
+    xb = x.to(torch.bfloat16).float()
+
+    def folded(name):
+        wf, c1, c2 = t["dec.1.%s.wf" % name].float(), t["dec.1.%s.c1" % name], t["dec.1.%s.c2" % name]
+        assert torch.equal(c1, wf.sum(1))                 # c1 = row sums of the weights exactly as stored
+        return rstd * (xb @ wf.t() - mean * c1) + c2
+
+    with torch.no_grad():
+        ln1 = layer.self_attn_layer_norm(x)
+        ref_qkv = torch.cat([layer.self_attn.q_proj(ln1) * 0.125, layer.self_attn.k_proj(ln1), layer.self_attn.v_proj(ln1)], 1)
+        ref_cq = layer.encoder_attn.q_proj(layer.encoder_attn_layer_norm(x)) * 0.125
+        ref_fc1 = layer.fc1(layer.final_layer_norm(x))
+    for name, ref in (("sqkv", ref_qkv), ("cq", ref_cq), ("fc1", ref_fc1)):
+        got = folded(name)
+        err = (got - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+        assert got.shape == ref.shape and err < 6e-3, "%s: %g" % (name, err)
+
+
 @pytest.mark.parametrize("eos_scale,length_penalty,max_length", [(1.0, 1.0, 48), (1.15, 1.0, 40), (1.15, 0.6, 40), (1.3, 2.0, 24)])
 def test_beam_oracle_matches_hf_generate(eos_scale, length_penalty, max_length):
     """oracle/beam_np.py (HF beam search restated) against HF `generate(num_beams=4)` -- the reference's
