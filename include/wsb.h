@@ -137,6 +137,18 @@ int wsb_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_
 int wsb_gemv16(const float* x_f32_dev, const float* gamma_dev, const float* beta_dev, const void* a_bf16_dev,
                const void* w_dev, const float* bias_dev, int M, int N, int K, int out_mode, void* out_dev, void* stream);
 
+/* Skinny linear layer for decode batches of 65..256 rows (csrc/skinny.cu): one launch, split-K across a thread-block
+ * cluster (splits = 0: chosen; else 1, 2, 4 or 8), partial tiles reduced through distributed shared memory.
+ * Folded-LayerNorm form (x_f32_dev [M][K] given): w_dev = bf16(W o gamma) [N][K], c1_dev [N] = its row sums, bias_dev =
+ * c2 = b + W beta; out_mode 0: float32 [M][N], 1: bf16 [M][N] = GELU(.).  Residual form (x NULL, a_bf16_dev [M][K]):
+ * out_mode 2, out_dev float32 [M][N] += a W^T + bias, and optionally xb_out_dev bf16 [M][N] = the updated rows,
+ * stats_out_dev float32 [N / 128][M][2] = per-tile (sum, sum of squares) of every updated row.  N % 128 == 0,
+ * K % 64 == 0.  Replaces nn.Linear (+ the preceding nn.LayerNorm) of HF WhisperDecoderLayer
+ * (modeling_whisper.py:417-506) at medium batch.                                                              */
+int wsb_skinny_linear(const float* x_f32_dev, const float* c1_dev, const void* a_bf16_dev, const void* w_dev,
+                      const float* bias_dev, int M, int N, int K, int out_mode, int splits, void* out_dev,
+                      void* xb_out_dev, float* stats_out_dev, void* stream);
+
 /* Diagnostics: steady-state microseconds per wsb_gemv16-style launch (weights rotating through `weight_copies`
  * buffers so that they stream from HBM).  mode 0: LayerNorm -> fp32, 1: LayerNorm -> GELU bf16, 2: bf16 -> residual,
  * 3 / 4: folded LayerNorm -> fp32 / GELU bf16. */

@@ -165,3 +165,57 @@ def test_gemv16(lib, M, N, K, mode):
         _lib.check(lib.wsb_gemv16(*args, _p(w), _p(bias), M, N, K, 2, _p(out), None), "gemv16")
         torch.cuda.synchronize()
         assert (out - (resid + ref)).abs().max().item() < 2e-3 * scale
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(240, 3840, 1280, 0), (240, 1280, 1280, 0), (240, 5120, 1280, 0), (240, 1280, 5120, 0),
+                                          (130, 1280, 1280, 0), (65, 384, 384, 0), (256, 1536, 384, 0), (100, 384, 1536, 0),
+                                          (240, 1280, 1280, 1), (240, 1280, 1280, 2), (240, 1280, 1280, 8), (77, 1280, 5120, 8),
+                                          (5, 128, 64, 1)])
+@pytest.mark.parametrize("mode", ["fold_f32", "fold_gelu", "resid"])
+def test_skinny_cluster_linear(lib, M, N, K, splits, mode):
+    """Cluster split-K skinny linear (csrc/skinny.cu): DSMEM-reduced partial tiles, folded LayerNorm / in-place
+    residual epilogues (+ bf16 copy and per-tile row statistics), against torch fp32.  Tolerances as for gemv16."""
+    import torch
+    from whisperseg_b200 import _lib
+    torch.manual_seed(M * 17 + N + K + splits)
+    dev = "cuda"
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    if mode.startswith("fold"):
+        x = torch.randn(M, K, device=dev) * 3.0 + 0.5
+        gamma, beta = torch.rand(K, device=dev) + 0.5, torch.randn(K, device=dev) * 0.1
+        w32 = w.float()
+        wf = (w32 * gamma[None, :]).to(torch.bfloat16)
+        c1 = wf.float().sum(1).contiguous()
+        c2 = (bias + w32 @ beta).contiguous()
+        ref = torch.nn.functional.layer_norm(x, (K,), gamma, beta, 1e-5) @ w32.t() + bias
+        scale = max(1.0, ref.abs().max().item())
+        if mode == "fold_f32":
+            out = torch.full((M, N), float("nan"), device=dev)
+            _lib.check(lib.wsb_skinny_linear(_p(x), _p(c1), _p(None), _p(wf), _p(c2), M, N, K, 0, splits, _p(out), _p(None),
+                                             _p(None), None), "skinny fold")
+            torch.cuda.synchronize()
+            assert (out - ref).abs().max().item() < 6e-3 * scale
+        else:
+            out = torch.zeros((M, N), device=dev, dtype=torch.bfloat16)
+            _lib.check(lib.wsb_skinny_linear(_p(x), _p(c1), _p(None), _p(wf), _p(c2), M, N, K, 1, splits, _p(out), _p(None),
+                                             _p(None), None), "skinny fold gelu")
+            torch.cuda.synchronize()
+            refg = torch.nn.functional.gelu(ref)
+            assert (out.float() - refg).abs().max().item() < 1.2e-2 * scale
+        return
+    a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    resid = torch.randn(M, N, device=dev)
+    ref = resid + a.float() @ w.float().t() + bias
+    out = resid.clone()
+    xb = torch.zeros((M, N), device=dev, dtype=torch.bfloat16)
+    stats = torch.full((N // 128, M, 2), float("nan"), device=dev)
+    _lib.check(lib.wsb_skinny_linear(_p(None), _p(None), _p(a), _p(w), _p(bias), M, N, K, 2, splits, _p(out), _p(xb), _p(stats),
+                                     None), "skinny resid")
+    torch.cuda.synchronize()
+    scale = max(1.0, ref.abs().max().item())
+    assert (out - ref).abs().max().item() < 2e-3 * scale
+    assert torch.equal(xb, out.to(torch.bfloat16))
+    tiles = out.view(M, N // 128, 128).permute(1, 0, 2)
+    assert (stats[..., 0] - tiles.sum(-1)).abs().max().item() < 1e-2 * scale
+    assert (stats[..., 1] - (tiles * tiles).sum(-1)).abs().max().item() < 1e-3 * (tiles * tiles).sum(-1).max().item()

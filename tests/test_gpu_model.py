@@ -69,6 +69,7 @@ def test_decoder_teacher_forced(setup, monkeypatch, path):
         monkeypatch.setenv("WSB_NO_FOLD", "1")
     elif path == "tcgen05-splitk":
         monkeypatch.setenv("WSB_NO_GEMV", "1")
+        monkeypatch.setenv("WSB_NO_CLUSTER", "1")
     seg, orc, hf, x = setup["seg"], setup["orc"], setup["hf"], setup["x"]
     eng = seg.engines[0]
     tok = seg.tokenizer
@@ -175,9 +176,10 @@ def test_batch_compaction_equals_uncompacted(tiny_checkpoint, monkeypatch):
     assert outs["compact"][1] == outs["plain"][1]
 
 
-@pytest.mark.parametrize("seconds,max_batch", [(13.0, 16), (29.0, 32), (45.0, 64)])
+@pytest.mark.parametrize("seconds,max_batch", [(13.0, 16), (29.0, 32), (45.0, 64), (85.0, 96)])
 def test_small_batch_linear_path_matches_tensor_core_path(tiny_checkpoint, monkeypatch, seconds, max_batch):
-    """Batches of <= 64 rows (1, 2 or 4 m-tiles of 16) run the fused mma.sync linear kernels (gemv.cu) instead of the
+    """Batches of 65..256 rows run one cluster split-K launch per linear layer (skinny.cu, the 85-window case) and
+    batches of <= 64 rows (1, 2 or 4 m-tiles of 16) run the fused mma.sync linear kernels (gemv.cu) instead of the
     tcgen05 split-K GEMM + reduce pair, with the LayerNorm folded into the projection (the kernel reads bf16(x) and
     applies rstd (acc - mean c1) + c2), so the two paths round different quantities to bf16: independent rounding
     noise of the same size.  Teacher-forced on the tensor-core path's own tokens, the per-position arg-max must agree
@@ -199,16 +201,20 @@ def test_small_batch_linear_path_matches_tensor_core_path(tiny_checkpoint, monke
     feats = eng.features(plan, audio, wins)
     max_length = 64
     eng.encode(feats)
-    monkeypatch.setenv("WSB_NO_GEMV", "1")
+    def tensor_core_path(on):
+        for k in ("WSB_NO_GEMV", "WSB_NO_CLUSTER"):
+            monkeypatch.setenv(k, "1") if on else monkeypatch.delenv(k, raising=False)
+
+    tensor_core_path(True)
     ref, _ = eng.generate(n, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length)
-    monkeypatch.delenv("WSB_NO_GEMV")
+    tensor_core_path(False)
     got, _ = eng.generate(n, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length)
     same_rows = (ref == got).all(dim=1).float().mean().item()
     forced = torch.full((n, max_length), tok.eos_token_id, dtype=torch.int32, device=eng.device)
     forced[:, :3] = torch.tensor(tok.prompt_ids, dtype=torch.int32, device=eng.device)
     forced[:, 3:] = ref
     tf_new, _ = eng.generate(n, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length, forced=forced, use_graph=False)
-    monkeypatch.setenv("WSB_NO_GEMV", "1")
+    tensor_core_path(True)
     tf_old, _ = eng.generate(n, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length, forced=forced, use_graph=False)
     agree = (tf_new == tf_old).float().mean().item()
     print("small-batch path: %d windows, free-running rows identical %.3f, teacher-forced arg-max agreement %.4f" % (n, same_rows, agree))

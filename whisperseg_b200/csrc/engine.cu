@@ -143,6 +143,7 @@ struct Model {
     std::map<std::tuple<int, int, int, int, int, int, int>, GraphEntry> graphs;
     bool use_pdl = false;
     bool use_gemv = true;               // few decode rows: fused LN + mma.sync linear layers (gemv.cu)
+    bool use_cluster = true;            // 65..256 decode rows: cluster split-K linear layers with folded LayerNorm (skinny.cu)
     bool use_fold = true;               // ... with the LayerNorm folded into the projection when the folded tensors exist
     int gemv_rows = 64;                 // ... used up to this many rows (WSB_GEMV_ROWS, <= 64)
     std::vector<int> ladder{64, 32, 16};   // compaction levels, descending, all <= kCompactRows (override: WSB_LADDER=64,16)
@@ -202,7 +203,7 @@ static int model_layout(Model* m, bool assign) {
     m->dff = carve<__nv_bfloat16>(p, B * F);
     m->dpart_floats = 16 * B * std::max<size_t>(F, 3 * d);
     m->dpart = carve<float>(p, m->dpart_floats);
-    m->gv_stats = carve<float>(p, 160 * 64 * 2);
+    m->gv_stats = carve<float>(p, std::max<size_t>(160 * 64 * 2, static_cast<size_t>(c.d_model / 128 + 1) * B * 2));
     m->am_val = carve<float>(p, B * m->am_tiles);
     m->am_idx = carve<int>(p, B * m->am_tiles);
     m->tokens = carve<int>(p, B * c.max_target_positions);
@@ -555,6 +556,82 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
             WSB_RUN(lin_resid(m->dff, e.fc2_w, e.fc2_b, F));
         }
         if (with_logits) WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec_ln_g, m->dec_ln_b, m->dxn, nullptr, B, d, s));
+    } else if (m->use_cluster && m->use_fold && m->dec[0].sqkv_wf != nullptr && B <= 256 && skinny_cluster_supported(B, d, d) &&
+               skinny_cluster_supported(B, F, d) && skinny_cluster_supported(B, d, F)) {
+        // 65..256 rows: one cluster split-K launch per linear layer (skinny.cu), LayerNorm folded into the consumers,
+        // 8 launches per layer instead of 12.  The residual stream travels as fp32 (m->dx) + bf16 (m->dxn) + per-tile
+        // row statistics (m->gv_stats: [parts][B][2]).
+        int parts = 1;
+        {
+            ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
+            WSB_RUN(row_stats_any(m->dx, B, d, m->gv_stats, m->dxn, s));
+        }
+        auto lin_fold = [&](const __nv_bfloat16* Wf, const float* c1, const float* c2, int N, float* out_f32,
+                            __nv_bfloat16* out_gelu) -> int {
+            SkinnyArgs a;
+            a.A = m->dxn;
+            a.lda = d;
+            a.W = Wf;
+            a.M = B;
+            a.N = N;
+            a.K = d;
+            a.bias = c2;
+            a.c1 = c1;
+            a.stats = m->gv_stats;
+            a.stats_parts = parts;
+            a.stats_ld = B;
+            a.out_f32 = out_f32;
+            a.out_bf16_gelu = out_gelu;
+            a.row_skip = fin;
+            ProfScope ps(PROF_DEC_GEMM, 2.0 * B * N * d, s);
+            return skinny_cluster_linear(a, s);
+        };
+        auto lin_resid = [&](const __nv_bfloat16* a_, const __nv_bfloat16* W, const float* bias, int K) -> int {
+            SkinnyArgs a;
+            a.A = a_;
+            a.lda = K;
+            a.W = W;
+            a.M = B;
+            a.N = d;
+            a.K = K;
+            a.bias = bias;
+            a.resid = m->dx;
+            a.xb_out = m->dxn;
+            a.stats_out = m->gv_stats;
+            a.stats_out_ld = B;
+            a.row_skip = fin;
+            parts = d / 128;
+            ProfScope ps(PROF_DEC_GEMM, 2.0 * B * d * K, s);
+            return skinny_cluster_linear(a, s);
+        };
+        for (int l = 0; l < L; ++l) {
+            const DecLayer& e = m->dec[l];
+            SplitkInput part;
+            part.planes = m->dpart;
+            part.splits = 1;
+            part.bias = nullptr;
+            WSB_RUN(lin_fold(e.sqkv_wf, e.sqkv_c1, e.sqkv_c2, 3 * d, m->dpart, nullptr));
+            part.split_stride = static_cast<long long>(B) * 3 * d;
+            {
+                ProfScope ps(PROF_DEC_SELF_ATTN, 0.0, s);
+                WSB_RUN(decode_self_attention(nullptr, &part, d, st.k_cache + l * cache_l, st.v_cache + l * cache_l, tmax, m->step, 0,
+                                              fin, m->datt, B, H, s, st.anc, st.anc_ld));
+            }
+            WSB_RUN(lin_resid(m->datt, e.so_w, e.so_b, d));
+            WSB_RUN(lin_fold(e.cq_wf, e.cq_c1, e.cq_c2, d, m->dpart, nullptr));
+            part.split_stride = static_cast<long long>(B) * d;
+            {
+                ProfScope ps(PROF_DEC_CROSS_ATTN, 4.0 * B * H * T * 64.0, s);
+                WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s, st.kv_div));
+            }
+            WSB_RUN(lin_resid(m->datt, e.co_w, e.co_b, d));
+            WSB_RUN(lin_fold(e.fc1_wf, e.fc1_c1, e.fc1_c2, F, nullptr, m->dff));
+            WSB_RUN(lin_resid(m->dff, e.fc2_w, e.fc2_b, F));
+        }
+        if (with_logits) {
+            ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
+            WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec_ln_g, m->dec_ln_b, m->dxn, nullptr, B, d, s));
+        }
     } else {
     {
         ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
@@ -639,6 +716,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
                                                         // are fetched before the dependency wait)
     m->use_gemv = (flags & 8) == 0;                     // bit3: keep the tcgen05 split-K path for small batches too
     m->use_fold = std::getenv("WSB_NO_FOLD") == nullptr;
+    m->use_cluster = std::getenv("WSB_NO_CLUSTER") == nullptr;
     if (const char* e = std::getenv("WSB_GEMV_ROWS")) m->gemv_rows = std::max(0, std::min(64, std::atoi(e)));
     if (const char* e = std::getenv("WSB_LADDER")) {
         std::vector<int> lv;
@@ -704,7 +782,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     const bool allow_compaction = (flags & 4) == 0 && forced == nullptr;
     Model::GraphEntry* graph = nullptr;
     auto get_graph = [&](const DecState& cur, Model::GraphEntry** out) -> int {
-        const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 32 * m->gemv_rows + (m->use_fold ? 4096 : 0) : 16), cur.row_map != nullptr ? 1 : 0, max_new,
+        const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 32 * m->gemv_rows + (m->use_fold ? 4096 : 0) : 16) + (m->use_cluster ? 8192 : 0), cur.row_map != nullptr ? 1 : 0, max_new,
                                          prompt_len, eos_id, pad_id);
         auto it = m->graphs.find(key);
         if (it == m->graphs.end()) {
@@ -1130,6 +1208,54 @@ int wsb_gemv16(const float* x_f32_dev, const float* gamma_dev, const float* beta
     g.N = N;
     g.K = K;
     WSB_RUN(gemv16(g, s));
+    WSB_CHECK_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+int wsb_skinny_linear(const float* x_f32_dev, const float* c1_dev, const void* a_bf16_dev, const void* w_dev, const float* bias_dev,
+                      int M, int N, int K, int out_mode, int splits, void* out_dev, void* xb_out_dev, float* stats_out_dev,
+                      void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SkinnyArgs g;
+    float* stats = nullptr;
+    __nv_bfloat16* xb = nullptr;
+    struct Free {
+        float*& a;
+        __nv_bfloat16*& b;
+        ~Free() {
+            cudaFree(a);
+            cudaFree(b);
+        }
+    } guard{stats, xb};
+    if (x_f32_dev) {                                      // folded LayerNorm: exact row statistics (one part) + bf16 rows
+        WSB_REQUIRE(M >= 1 && K >= 1 && c1_dev && out_mode <= 1, "wsb_skinny_linear: folded form needs c1 and out_mode 0 / 1");
+        WSB_CHECK_CUDA(cudaMalloc(&stats, sizeof(float) * 2 * M));
+        WSB_CHECK_CUDA(cudaMalloc(&xb, sizeof(__nv_bfloat16) * static_cast<size_t>(M) * K));
+        WSB_RUN(row_stats_any(x_f32_dev, M, K, stats, xb, s));
+        g.A = xb;
+        g.c1 = c1_dev;
+        g.stats = stats;
+        g.stats_parts = 1;
+        g.stats_ld = M;
+    } else {
+        WSB_REQUIRE(a_bf16_dev && out_mode == 2, "wsb_skinny_linear: bf16 activations feed the residual form (out_mode 2)");
+        g.A = static_cast<const __nv_bfloat16*>(a_bf16_dev);
+    }
+    g.lda = K;
+    g.W = static_cast<const __nv_bfloat16*>(w_dev);
+    g.bias = bias_dev;
+    g.M = M;
+    g.N = N;
+    g.K = K;
+    g.splits = splits;
+    if (out_mode == 0) g.out_f32 = static_cast<float*>(out_dev);
+    else if (out_mode == 1) g.out_bf16_gelu = static_cast<__nv_bfloat16*>(out_dev);
+    else {
+        g.resid = static_cast<float*>(out_dev);
+        g.xb_out = static_cast<__nv_bfloat16*>(xb_out_dev);
+        g.stats_out = stats_out_dev;
+        g.stats_out_ld = M;
+    }
+    WSB_RUN(skinny_cluster_linear(g, s));
     WSB_CHECK_CUDA(cudaStreamSynchronize(s));
     return 0;
 }

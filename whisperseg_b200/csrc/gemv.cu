@@ -346,6 +346,13 @@ int row_stats16(const float* x, int M, int K, float* stats, cudaStream_t stream,
     return 0;
 }
 
+int row_stats_any(const float* x, int M, int K, float* stats, __nv_bfloat16* xb, cudaStream_t stream) {
+    if (M <= 0) return 0;
+    WSB_CHECK_CUDA(launch_kernel(row_stats_kernel, dim3(M), dim3(256), 0, stream, x, K, stats, xb));
+    count_launch();
+    return 0;
+}
+
 int gemv16_parts(int N) {                                // CTAs (= partial statistics) of a launch with N outputs
     const int nt = std::min(kGvMaxNT, std::max(1, ceil_div(ceil_div(N, 8), 148)));
     return ceil_div(N, 8 * nt);

@@ -108,6 +108,35 @@ int gemv16_parts(int N);                                 // CTAs (= statistics p
 int row_stats16(const float* x, int M, int K, float* stats, cudaStream_t stream,
                 __nv_bfloat16* xb = nullptr);            // exact statistics, 1 part (+ optional bf16 copy of x)
 
+// ------------------------------------------------------------------ K5d skinny linear for 65..256 rows (skinny.cu)
+// One launch per linear layer: split-K across a thread-block cluster, partial tiles reduced through DSMEM, LayerNorm
+// folded into the projection (A = bf16 rows of the residual stream, W = bf16(W o gamma), c1 = row sums of W, bias = c2,
+// `stats` = [stats_parts][stats_ld][2] partial (sum, sum of squares) per row) -> fp32 `out_f32` | GELU bf16
+// `out_bf16_gelu`; or the in-place residual update `resid` += A W^T + bias (A = bf16 activations), which also writes
+// the updated rows as bf16 (`xb_out`) and this launch's per-tile row statistics `stats_out` [N / 128][stats_out_ld][2].
+struct SkinnyArgs {
+    const __nv_bfloat16* A = nullptr;
+    int64_t lda = 0;
+    const __nv_bfloat16* W = nullptr;    // [N][K]
+    int M = 0, N = 0, K = 0;
+    const float* bias = nullptr;
+    const float* c1 = nullptr;
+    const float* stats = nullptr;
+    int stats_parts = 0, stats_ld = 0;
+    float* out_f32 = nullptr;
+    __nv_bfloat16* out_bf16_gelu = nullptr;
+    float* resid = nullptr;
+    __nv_bfloat16* xb_out = nullptr;
+    float* stats_out = nullptr;
+    int stats_out_ld = 0;
+    const unsigned char* row_skip = nullptr;
+    int splits = 0;                      // 0 = choose (1, 2, 4 or 8 CTAs per cluster along K)
+};
+bool skinny_cluster_supported(int M, int N, int K);
+int skinny_cluster_splits(int M, int N, int K);
+int skinny_cluster_linear(const SkinnyArgs& a, cudaStream_t stream);
+int row_stats_any(const float* x, int M, int K, float* stats, __nv_bfloat16* xb, cudaStream_t stream);   // gemv.cu: any M
+
 // ------------------------------------------------------------------ K4 encoder attention (attention.cu)
 int encoder_attention(const __nv_bfloat16* qkv /*[B*T, 3d]*/, __nv_bfloat16* out /*[B*T, d]*/, int B, int T,
                       int n_heads, cudaStream_t stream);
