@@ -69,7 +69,6 @@ def test_decoder_teacher_forced(setup, monkeypatch, path):
         monkeypatch.setenv("WSB_NO_FOLD", "1")
     elif path == "tcgen05-splitk":
         monkeypatch.setenv("WSB_NO_GEMV", "1")
-        monkeypatch.setenv("WSB_NO_CLUSTER", "1")
     seg, orc, hf, x = setup["seg"], setup["orc"], setup["hf"], setup["x"]
     eng = seg.engines[0]
     tok = seg.tokenizer
@@ -178,7 +177,8 @@ def test_batch_compaction_equals_uncompacted(tiny_checkpoint, monkeypatch):
 
 @pytest.mark.parametrize("seconds,max_batch", [(13.0, 16), (29.0, 32), (45.0, 64), (85.0, 96)])
 def test_small_batch_linear_path_matches_tensor_core_path(tiny_checkpoint, monkeypatch, seconds, max_batch):
-    """Batches of 65..256 rows run one cluster split-K launch per linear layer (skinny.cu, the 85-window case) and
+    """Batches of 65..256 rows can run one cluster split-K launch per linear layer (skinny.cu, opt-in with WSB_CLUSTER=1:
+    the 85-window case) and
     batches of <= 64 rows (1, 2 or 4 m-tiles of 16) run the fused mma.sync linear kernels (gemv.cu) instead of the
     tcgen05 split-K GEMM + reduce pair, with the LayerNorm folded into the projection (the kernel reads bf16(x) and
     applies rstd (acc - mean c1) + c2), so the two paths round different quantities to bf16: independent rounding
@@ -201,9 +201,9 @@ def test_small_batch_linear_path_matches_tensor_core_path(tiny_checkpoint, monke
     feats = eng.features(plan, audio, wins)
     max_length = 64
     eng.encode(feats)
-    def tensor_core_path(on):
-        for k in ("WSB_NO_GEMV", "WSB_NO_CLUSTER"):
-            monkeypatch.setenv(k, "1") if on else monkeypatch.delenv(k, raising=False)
+    def tensor_core_path(on):                  # reference = tcgen05 split-K pair; else gemv.cu (<= 64 rows) / skinny.cu (opt-in)
+        monkeypatch.setenv("WSB_NO_GEMV", "1") if on else monkeypatch.delenv("WSB_NO_GEMV", raising=False)
+        monkeypatch.delenv("WSB_CLUSTER", raising=False) if on else monkeypatch.setenv("WSB_CLUSTER", "1")
 
     tensor_core_path(True)
     ref, _ = eng.generate(n, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length)

@@ -143,7 +143,8 @@ struct Model {
     std::map<std::tuple<int, int, int, int, int, int, int>, GraphEntry> graphs;
     bool use_pdl = false;
     bool use_gemv = true;               // few decode rows: fused LN + mma.sync linear layers (gemv.cu)
-    bool use_cluster = true;            // 65..256 decode rows: cluster split-K linear layers with folded LayerNorm (skinny.cu)
+    bool use_cluster = false;           // 65..256 decode rows: cluster split-K linear layers with folded LayerNorm (skinny.cu);
+                                        // opt-in (WSB_CLUSTER=1): parity-green, but measured 0-4 % slower than the split-K pair
     bool use_fold = true;               // ... with the LayerNorm folded into the projection when the folded tensors exist
     int gemv_rows = 64;                 // ... used up to this many rows (WSB_GEMV_ROWS, <= 64)
     std::vector<int> ladder{64, 32, 16};   // compaction levels, descending, all <= kCompactRows (override: WSB_LADDER=64,16)
@@ -716,7 +717,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
                                                         // are fetched before the dependency wait)
     m->use_gemv = (flags & 8) == 0;                     // bit3: keep the tcgen05 split-K path for small batches too
     m->use_fold = std::getenv("WSB_NO_FOLD") == nullptr;
-    m->use_cluster = std::getenv("WSB_NO_CLUSTER") == nullptr;
+    m->use_cluster = std::getenv("WSB_CLUSTER") != nullptr;
     if (const char* e = std::getenv("WSB_GEMV_ROWS")) m->gemv_rows = std::max(0, std::min(64, std::atoi(e)));
     if (const char* e = std::getenv("WSB_LADDER")) {
         std::vector<int> lv;
