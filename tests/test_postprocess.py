@@ -103,6 +103,29 @@ def test_random_streams_product_equals_oracle():
         assert a["onset"] == sorted(a["onset"])
 
 
+def test_dbscan_labels_equal_sklearn_precomputed():
+    """`_dbscan_labels` (windowed neighbour search + connected components of the core graph, no O(n^2) matrix, no
+    replay of sklearn's stack) against the call the reference makes (model.py:305-309): pairwise_distances with the
+    Python-callable metric of model.py:285-288, then DBSCAN(metric="precomputed") -- identical labels, including
+    the numbering of the clusters and which cluster a border point joins; and the merged segments bit for bit."""
+    from sklearn.cluster import DBSCAN
+    rng = np.random.default_rng(77)
+    for case in range(60):
+        n = int(rng.integers(1, 150))
+        base = np.sort(rng.uniform(0, n * rng.choice([0.01, 0.05, 0.4]), n))
+        on = base + rng.normal(0, rng.choice([1e-3, 1e-2]), n)
+        off = on + rng.uniform(0.005, 0.2, n)
+        if case % 2:                                   # a token grid makes exact ties and exact eps hits
+            on, off = np.round(on / 0.005) * 0.005, np.round(off / 0.005) * 0.005
+        eps, ms = float(rng.choice([0.005, 0.02, 0.04, 0.2])), int(rng.integers(1, 5))
+        dist = (np.abs(on[:, None] - on[None, :]) + np.abs(off[:, None] - off[None, :])) / 2
+        ref = DBSCAN(eps=eps, min_samples=ms, metric="precomputed").fit(dist).labels_
+        assert np.array_equal(P._dbscan_labels(on, off, eps, ms), ref)
+        names = rng.choice(["a", "b"], size=n).tolist()
+        trials = [{"onset": on.tolist(), "offset": off.tolist(), "cluster": names}]
+        assert P.consolidate_trials_by_clustering(trials, eps, ms) == PR.consolidate_by_clustering(trials, eps, ms)
+
+
 def test_scoring_known_answer():
     pred = {"onset": [1, 2, 3], "offset": [1.5, 2.5, 3.5], "cluster": ["vocal", "vocal", "b"]}
     label = {"onset": [1.005, 2.2, 3], "offset": [1.5, 2.6, 3.5], "cluster": ["vocal", "vocal", "b"]}

@@ -1,5 +1,5 @@
 """GPU aid: steady-state time of the skinny-linear kernel (gemv.cu) for the decoder shapes of whisper-large,
-by row count.  WSB_GEMV_NT=<1..5> overrides the features-per-CTA choice (diagnostics)."""
+by row count."""
 import ctypes
 import os
 import sys
@@ -12,7 +12,6 @@ shapes = [("qkv  LN->f32 ", 3840, 1280, 0), ("cq   LN->f32 ", 1280, 1280, 0), ("
           ("so/co  ->res ", 1280, 1280, 2), ("fc2    ->res ", 1280, 5120, 2),
           ("qkv  fold->f32", 3840, 1280, 3), ("cq   fold->f32", 1280, 1280, 3), ("fc1  fold->gelu", 5120, 1280, 4)]
 rows = [int(a) for a in sys.argv[1:]] or [16, 32, 48, 64]
-print("NT override:", os.environ.get("WSB_GEMV_NT", "auto"))
 for name, N, K, mode in shapes:
     line = []
     for M in rows:

@@ -23,7 +23,6 @@
 #include "wsb_internal.h"
 
 #include <algorithm>
-#include <cstdlib>
 
 namespace wsb {
 
@@ -422,10 +421,7 @@ int gemv16(const Gemv16Args& a, cudaStream_t stream) {
     p.M = a.M;
     p.N = a.N;
     p.K = a.K;
-    int nt = std::min(kGvMaxNT, std::max(1, ceil_div(ceil_div(a.N, 8), 148)));
-    static const int nt_env = std::getenv("WSB_GEMV_NT") ? std::atoi(std::getenv("WSB_GEMV_NT")) : 0;   // diagnostics
-    if (nt_env >= 1 && nt_env <= kGvMaxNT && static_cast<size_t>(8 * nt_env) * (static_cast<size_t>(a.K) * 2 + kGvWPad) <= 160 * 1024)
-        nt = nt_env;
+    const int nt = std::min(kGvMaxNT, std::max(1, ceil_div(ceil_div(a.N, 8), 148)));
     const int epi = a.out_f32 ? 0 : (a.out_bf16_gelu ? 1 : 2);
     if (a.x) {
         if (epi == 0) return dispatch_mt<1, 0>(p, nt, stream);

@@ -47,47 +47,81 @@ def _stitch_trial(per_window):
     return acc
 
 
-def _dbscan_labels(onsets, offsets, eps, min_samples):
-    """DBSCAN on the metric (|d_onset| + |d_offset|)/2 (model.py:285-288, 305-309).
+def _neighbour_pairs(onsets, offsets, eps):
+    """All ordered pairs (i, j) with (|d_onset| + |d_offset|)/2 <= eps (i == j included), sorted by (i, j).
 
-    Same labels as sklearn's DBSCAN(metric="precomputed"): core test counts the point itself,
-    clusters are grown from unlabeled core points in index order with a LIFO frontier."""
+    Candidates come from a window over the onset-sorted points (a pair within eps has |d_onset| <= 2 eps; the
+    window is taken slightly wider, the exact test below decides), so the work is O(n * window), not O(n^2)."""
     n = len(onsets)
     order = np.argsort(onsets, kind="stable")
     so = onsets[order]
-    neigh = [None] * n
-    lo = 0
-    for r in range(n):
-        i = order[r]
-        while so[r] - so[lo] > 2 * eps + 1e-9:
-            lo += 1
-        hi = r
-        while hi + 1 < n and so[hi + 1] - so[r] <= 2 * eps + 1e-9:
-            hi += 1
-        cand = order[lo:hi + 1]
-        d = (np.abs(onsets[cand] - onsets[i]) + np.abs(offsets[cand] - offsets[i])) / 2
-        nb = cand[d <= eps]
-        nb.sort()
-        neigh[i] = nb
-    core = np.fromiter((len(nb) >= min_samples for nb in neigh), dtype=bool, count=n)
+    reach = 2 * eps + 1e-6
+    lo = np.searchsorted(so, so - reach, side="left")
+    hi = np.searchsorted(so, so + reach, side="right")
+    width = hi - lo
+    src_r = np.repeat(np.arange(n), width)                       # rank of i in onset order
+    starts = np.cumsum(width) - width
+    dst_r = np.arange(int(width.sum())) - np.repeat(starts, width) + np.repeat(lo, width)
+    i, j = order[src_r], order[dst_r]
+    d = (np.abs(onsets[j] - onsets[i]) + np.abs(offsets[j] - offsets[i])) / 2
+    keep = d <= eps
+    i, j = i[keep], j[keep]
+    srt = np.lexsort((j, i))
+    return i[srt], j[srt]
+
+
+def _dbscan_labels(onsets, offsets, eps, min_samples):
+    """DBSCAN on the metric (|d_onset| + |d_offset|)/2 (model.py:285-288, 305-309).
+
+    Same labels as sklearn's DBSCAN(metric="precomputed"), without replaying its stack: the core test counts the
+    point itself; sklearn grows clusters from unlabeled core points in index order and finishes one cluster before
+    it starts the next, so (a) the clusters of the core points are the connected components of the core-core
+    neighbour graph, numbered by their smallest member index, and (b) a non-core point takes the smallest label
+    among its core neighbours (the first cluster that reaches it), or -1 (noise) if it has none."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    n = len(onsets)
+    i, j = _neighbour_pairs(onsets, offsets, eps)
+    core = np.bincount(i, minlength=n) >= min_samples
     labels = np.full(n, -1, dtype=np.int64)
-    current = 0
-    for seed in range(n):
-        if labels[seed] != -1 or not core[seed]:
-            continue
-        stack, i = [], seed
-        while True:
-            if labels[i] == -1:
-                labels[i] = current
-                if core[i]:
-                    for v in neigh[i]:
-                        if labels[v] == -1:
-                            stack.append(v)
-            if not stack:
-                break
-            i = stack.pop()
-        current += 1
+    core_idx = np.nonzero(core)[0]
+    if len(core_idx) == 0:
+        return labels
+    cc = core[i] & core[j]
+    remap = np.full(n, -1, dtype=np.int64)
+    remap[core_idx] = np.arange(len(core_idx))
+    graph = coo_matrix((np.ones(int(cc.sum()), dtype=np.int8), (remap[i[cc]], remap[j[cc]])), shape=(len(core_idx),) * 2)
+    _, comp = connected_components(graph, directed=False)
+    # number the components by first appearance in index order (= order of their smallest core index)
+    first = np.full(comp.max() + 1, n, dtype=np.int64)
+    np.minimum.at(first, comp, core_idx)
+    rank = np.empty_like(first)
+    rank[np.argsort(first, kind="stable")] = np.arange(len(first))
+    labels[core_idx] = rank[comp]
+    # border points: smallest label among their core neighbours
+    bc = ~core[i] & core[j]
+    if bc.any():
+        best = np.full(n, np.iinfo(np.int64).max, dtype=np.int64)
+        np.minimum.at(best, i[bc], labels[j[bc]])
+        reached = best != np.iinfo(np.int64).max
+        labels[reached] = best[reached]
     return labels
+
+
+def _group_means(values, starts, counts):
+    """np.mean of every segment values[starts[g] : starts[g] + counts[g]], bit-identical to calling np.mean on the
+    segment (what the reference does per cluster, model.py:322-326).  numpy adds fewer than 8 float64 values strictly
+    left to right, so those segments are accumulated together, one member position per pass; longer segments (its
+    blocked pairwise summation) are rare and go through np.mean itself.  (np.add.reduceat associates differently.)"""
+    sums = np.zeros(len(starts), dtype=np.float64)
+    small = counts < 8
+    for k in range(int(counts[small].max()) if small.any() else 0):
+        sel = small & (counts > k)
+        sums[sel] += values[starts[sel] + k]
+    means = sums / counts
+    for g in np.nonzero(~small)[0]:
+        means[g] = np.mean(values[starts[g]:starts[g] + counts[g]])
+    return means
 
 
 def consolidate_trials_by_clustering(trials, eps, min_samples):
@@ -98,19 +132,33 @@ def consolidate_trials_by_clustering(trials, eps, min_samples):
     if len(onsets) == 0:
         return {"onset": [], "offset": [], "cluster": []}
     labels = _dbscan_labels(onsets, offsets, eps, min_samples)
-    merged = []
-    for label in range(int(labels.max()) + 1 if len(labels) else 0):
-        members = np.nonzero(labels == label)[0]
-        if len(members) == 0:
+    # members of every cluster in index order (stable sort by label); noise (-1) sorts first and is dropped
+    order = np.argsort(labels, kind="stable")
+    order = order[np.searchsorted(labels[order], 0, side="left"):]
+    if len(order) == 0:
+        return {"onset": [], "offset": [], "cluster": []}
+    lab = labels[order]
+    starts = np.concatenate([[0], np.nonzero(np.diff(lab))[0] + 1])
+    counts = np.diff(np.concatenate([starts, [len(order)]]))
+    mean_on = _group_means(onsets[order], starts, counts)
+    mean_off = _group_means(offsets[order], starts, counts)
+    # majority name, first-seen wins ties (dict insertion order in the reference loop)
+    name_ids = {}
+    ids = np.fromiter((name_ids.setdefault(c, len(name_ids)) for c in names), dtype=np.int64, count=len(names))[order]
+    id_names = list(name_ids)
+    lo_id, hi_id = np.minimum.reduceat(ids, starts), np.maximum.reduceat(ids, starts)
+    chosen = []
+    for g in range(len(starts)):
+        if lo_id[g] == hi_id[g]:
+            chosen.append(id_names[lo_id[g]])
             continue
         tally = {}
-        for i in members:
-            tally[names[i]] = tally.get(names[i], 0) + 1
+        for k in ids[starts[g]:starts[g] + counts[g]]:
+            tally[k] = tally.get(k, 0) + 1
         best = max(tally.values())
-        name = next(k for k, v in tally.items() if v == best)          # first-seen wins ties
-        merged.append((np.mean([onsets[i] for i in members]), np.mean([offsets[i] for i in members]), name))
-    merged.sort(key=lambda s: s[0])
-    return {"onset": [s[0] for s in merged], "offset": [s[1] for s in merged], "cluster": [s[2] for s in merged]}
+        chosen.append(id_names[next(k for k, v in tally.items() if v == best)])
+    srt = sorted(range(len(starts)), key=lambda g: mean_on[g])          # stable, like list.sort on the onset
+    return {"onset": [mean_on[g] for g in srt], "offset": [mean_off[g] for g in srt], "cluster": [chosen[g] for g in srt]}
 
 
 def consolidate_trials_by_voting(trials, time_per_frame, cluster_codebook):
