@@ -11,13 +11,16 @@ Differences in *how* (not *what*):
   * multi-trial consolidation by clustering does not build the reference's O(n^2) Python-callable
     distance matrix (model.py:305); neighbours are found with a sliding window over the onset-
     sorted segments (a pair within `eps` must have |onset difference| <= 2*eps) and DBSCAN's
-    label assignment is replayed in sklearn's visiting order, which yields the same clusters;
+    labels are derived from the connected components of the core-point graph, numbered and
+    extended to border points the way sklearn's visiting order does -- the same clusters;
   * frame voting computes the per-frame mode with a counting pass instead of scipy.stats.mode.
 """
 import re
 from math import ceil
 
 import numpy as np
+from scipy.sparse import coo_matrix
+from scipy.sparse.csgraph import connected_components
 
 RATIO_DECODING_TIME_STEP_TO_SPEC_TIME_STEP = 2         # reference utils.py:5
 _SEGMENT_RE = re.compile(r"<\|([0-9]+)\|>(\d+?)<\|([0-9]+)\|>")
@@ -78,8 +81,6 @@ def _dbscan_labels(onsets, offsets, eps, min_samples):
     it starts the next, so (a) the clusters of the core points are the connected components of the core-core
     neighbour graph, numbered by their smallest member index, and (b) a non-core point takes the smallest label
     among its core neighbours (the first cluster that reaches it), or -1 (noise) if it has none."""
-    from scipy.sparse import coo_matrix
-    from scipy.sparse.csgraph import connected_components
     n = len(onsets)
     i, j = _neighbour_pairs(onsets, offsets, eps)
     core = np.bincount(i, minlength=n) >= min_samples
