@@ -93,6 +93,14 @@ def test_token_table_matches_hf_tokenizer(tiny):
     rows.append([synth.ID_TS0 + 10, 16, 17, synth.ID_TS0 + 60, synth.ID_EOT, synth.ID_EOT, 300, 220, 128, 200, 15])
     rows.append(rng.integers(0, 51372, size=64).tolist())
     assert table.batch_decode(rows) == tok.batch_decode(rows, skip_special_tokens=False)
+    # rectangular generate() output: rows padded with EOS (or cut while still emitting) up to max_length
+    rect = []
+    for k, tail in [(0, synth.ID_EOT), (1, synth.ID_EOT), (7, synth.ID_EOT), (40, synth.ID_EOT), (12, 16), (5, synth.ID_TS0 + 3)]:
+        rect.append((allowed[rng.integers(0, len(allowed), size=k)].tolist() + [tail] * 64)[:48])
+    rect.append(rng.integers(0, 51372, size=48).tolist())
+    arr = np.asarray(rect, dtype=np.int32)
+    assert table.batch_decode(arr) == tok.batch_decode(rect, skip_special_tokens=False)
+    assert table.batch_decode(arr[:, :1]) == tok.batch_decode([r[:1] for r in rect], skip_special_tokens=False)
 
 
 def test_weight_preparation_layouts(tiny):

@@ -82,7 +82,7 @@ def segment_sharded(segmenter, audio, sr, min_frequency=None, spec_time_step=Non
     texts = []
     for r in range(world):
         a, b, _ = shard_bounds(len(wins), world, r)
-        texts += tok.batch_decode(rows[r * per:r * per + (b - a)].tolist())
+        texts += tok.batch_decode(rows[r * per:r * per + (b - a)])
     pred = pp.parse_generation(texts, [w.as_tuple() for w in wins], min_segment_length, len(audio) / sr, spec_time_step,
                                num_trials, eps, time_per_frame_for_voting, consolidation_method,
                                segmenter.cluster_codebook, segmenter.precision_bits)

@@ -98,7 +98,7 @@ class SegmenterBase:
                 ids, n_steps = eng.generate_beam(chunk.shape[0], num_beams, tok.prompt_ids, tok.eos_token_id,
                                                  tok.pad_token_id, max_length, length_penalty)
             steps += n_steps
-            texts += tok.batch_decode(ids.cpu().numpy().tolist())
+            texts += tok.batch_decode(ids.cpu().numpy())
             if status_monitor is not None:                                       # model.py:672-674
                 status_monitor["progress"] = int(100 * min(1, (pos + per_call) / max(n, 1)))
         texts_out[slot] = texts

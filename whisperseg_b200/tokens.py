@@ -9,6 +9,8 @@ decoded as UTF-8 with replacement, added/special tokens are emitted verbatim.
 import json
 import os
 
+import numpy as np
+
 
 def _byte_decoder():
     bs = list(range(ord("!"), ord("~") + 1)) + list(range(0xA1, 0xAD)) + list(range(0xAE, 0x100))
@@ -76,6 +78,17 @@ class TokenTable:
     def decode(self, ids):
         out, run = [], bytearray()
         n = len(self.id_to_token)
+        # generated rows end in a long run of one special token (EOS / pad up to max_length): emit it in one piece
+        ids = list(ids)
+        tail_text = ""
+        if len(ids) > 1:
+            last = int(ids[-1])
+            if 0 <= last < n and self.is_added[last]:
+                k = len(ids)
+                while k > 0 and ids[k - 1] == ids[-1]:
+                    k -= 1
+                tail_text = self.id_to_token[last] * (len(ids) - k)
+                ids = ids[:k]
         for i in ids:
             i = int(i)
             if i < 0 or i >= n:
@@ -94,7 +107,23 @@ class TokenTable:
                         run.append(b)
         if run:
             out.append(run.decode("utf-8", errors="replace"))
+        out.append(tail_text)
         return "".join(out)
 
     def batch_decode(self, batch_ids, skip_special_tokens=False):
-        return [self.decode(row) for row in batch_ids]
+        """Same strings as HF `batch_decode(..., skip_special_tokens=False)` (reference model.py:668).  A rectangular
+        int array (what generate() returns) has its trailing EOS / pad runs measured in one vectorised pass."""
+        arr = batch_ids if isinstance(batch_ids, np.ndarray) else None
+        if arr is None or arr.ndim != 2 or arr.shape[1] < 2 or arr.shape[0] == 0:
+            return [self.decode(row) for row in batch_ids]
+        n = len(self.id_to_token)
+        differs = arr[:, ::-1] != arr[:, -1:]
+        tail = np.where(differs.any(axis=1), differs.argmax(axis=1), arr.shape[1])
+        out = []
+        for row, t in zip(arr, tail.tolist()):
+            last = int(row[-1])
+            if 0 <= last < n and self.is_added[last]:
+                out.append(self.decode(row[:arr.shape[1] - t].tolist()) + self.id_to_token[last] * t)
+            else:
+                out.append(self.decode(row.tolist()))
+        return out
