@@ -465,175 +465,189 @@ static int skinny_linear(Model* m, const __nv_bfloat16* A, const __nv_bfloat16* 
     return splitk_reduce_resid_ln(m->dpart, eff, plane, B, N, bias, x, gamma, beta, xn, row_skip, s);
 }
 
-// one decoder position for all rows.  with_logits: project + arg-max + finalize (or, with `beam`, raw logits +
-// beam bookkeeping); else prefill advance.
-static int decode_step(Model* m, const DecState& st, bool with_logits, bool first_generated, int prompt_len, int max_new,
-                       const int* forced, int forced_ld, int eos_id, int pad_id, cudaStream_t s,
-                       const BeamState* beam = nullptr) {
-    const wsb_model_config& c = m->cfg;
-    const int B = st.B;
-    const int d = c.d_model, F = c.ffn_dim, L = c.n_layers, H = c.n_heads, T = m->T, tmax = c.max_target_positions;
-    const unsigned char* fin = forced ? nullptr : st.finished;
-    struct PdlScope {
-        bool prev;
-        explicit PdlScope(bool on) : prev(g_use_pdl) { g_use_pdl = on; }
-        ~PdlScope() { g_use_pdl = prev; }
-    } pdl_scope(m->use_pdl || (m->use_gemv && B <= m->gemv_rows && c.d_model <= 1536));
-    // (programmatic dependent launch: the linear-layer kernels fetch their weight tiles before the dependency wait)
-    WSB_RUN(embed_tokens_step(st.next_token, m->step, 0, m->dec_emb, m->dec_pos, m->dx, B, d, s));
-    const long long cache_l = static_cast<long long>(B) * H * tmax * 64;
-    const bool small = m->use_gemv && B <= m->gemv_rows && d <= 1536;
-    if (small) {
-        // <= gemv_rows (64) rows: one launch per linear layer (LayerNorm, bias, activation / residual fused), 8 per layer.
-        // The residual stream's row statistics travel with it: embed -> (exact) -> qkv; out-proj -> cq;
-        // cross-out -> fc1; fc2 -> next layer's qkv.
-        int parts = 1;
-        // folded LayerNorm (default when the checkpoint loader provided the folded tensors): the consumers read the
-        // residual stream as bf16 (m->dxn, written next to the fp32 stream by its producer) and apply
-        // rstd (acc - mean c1) + c2 in their epilogue; WSB_NO_FOLD=1 keeps the exact on-the-fly LayerNorm
-        const bool fold = m->use_fold && m->dec[0].sqkv_wf != nullptr;
-        {
-            ProfScope ps(PROF_DEC_LN, 4.0 * B * d, s);
-            WSB_RUN(row_stats16(m->dx, B, d, m->gv_stats, s, fold ? m->dxn : nullptr));
-        }
-        auto lin_ln = [&](const float* g_, const float* b_, const __nv_bfloat16* W, const float* bias, const __nv_bfloat16* Wf,
-                          const float* c1, const float* c2, int N, float* out_f32, __nv_bfloat16* out_gelu) -> int {
-            Gemv16Args ga;
-            if (fold) {
-                ga.a = m->dxn;
-                ga.c1 = c1;
-                ga.W = Wf;
-                ga.bias = c2;
-            } else {
-                ga.x = m->dx;
-                ga.gamma = g_;
-                ga.beta = b_;
-                ga.W = W;
-                ga.bias = bias;
-            }
-            ga.stats = m->gv_stats;
-            ga.stats_parts = parts;
-            ga.out_f32 = out_f32;
-            ga.out_bf16_gelu = out_gelu;
-            ga.row_skip = fin;
-            ga.M = B;
-            ga.N = N;
-            ga.K = d;
-            ProfScope ps(PROF_DEC_GEMM, 2.0 * B * N * d, s);
-            return gemv16(ga, s);
-        };
-        auto lin_resid = [&](const __nv_bfloat16* a_, const __nv_bfloat16* W, const float* bias, int K) -> int {
-            Gemv16Args ga;
-            ga.a = a_;
+// what a decoder position's layer stack needs, whichever linear-layer implementation runs it
+struct StepCtx {
+    Model* m;
+    const DecState& st;
+    int B, d, F, L, H, T, tmax;
+    const unsigned char* fin;            // finished-row flags (null under teacher forcing)
+    long long cache_l;                   // elements of one layer's K (or V) cache
+    bool with_logits;
+    cudaStream_t s;
+};
+#define WSB_STEP_LOCALS                                                                                      \
+    Model* m = x.m;                                                                                          \
+    const DecState& st = x.st;                                                                               \
+    const int B = x.B, d = x.d, F = x.F, L = x.L, H = x.H, T = x.T, tmax = x.tmax;                          \
+    const unsigned char* fin = x.fin;                                                                        \
+    const long long cache_l = x.cache_l;                                                                     \
+    const bool with_logits = x.with_logits;                                                                  \
+    cudaStream_t s = x.s;                                                                                    \
+    (void)F; (void)T; (void)tmax; (void)with_logits
+
+// K5c: <= gemv_rows (64) rows, fused LayerNorm + linear kernels (gemv.cu), 8 launches per layer
+static int decode_layers_fused(const StepCtx& x) {
+    WSB_STEP_LOCALS;
+    // <= gemv_rows (64) rows: one launch per linear layer (LayerNorm, bias, activation / residual fused), 8 per layer.
+    // The residual stream's row statistics travel with it: embed -> (exact) -> qkv; out-proj -> cq;
+    // cross-out -> fc1; fc2 -> next layer's qkv.
+    int parts = 1;
+    // folded LayerNorm (default when the checkpoint loader provided the folded tensors): the consumers read the
+    // residual stream as bf16 (m->dxn, written next to the fp32 stream by its producer) and apply
+    // rstd (acc - mean c1) + c2 in their epilogue; WSB_NO_FOLD=1 keeps the exact on-the-fly LayerNorm
+    const bool fold = m->use_fold && m->dec[0].sqkv_wf != nullptr;
+    {
+        ProfScope ps(PROF_DEC_LN, 4.0 * B * d, s);
+        WSB_RUN(row_stats16(m->dx, B, d, m->gv_stats, s, fold ? m->dxn : nullptr));
+    }
+    auto lin_ln = [&](const float* g_, const float* b_, const __nv_bfloat16* W, const float* bias, const __nv_bfloat16* Wf,
+                      const float* c1, const float* c2, int N, float* out_f32, __nv_bfloat16* out_gelu) -> int {
+        Gemv16Args ga;
+        if (fold) {
+            ga.a = m->dxn;
+            ga.c1 = c1;
+            ga.W = Wf;
+            ga.bias = c2;
+        } else {
+            ga.x = m->dx;
+            ga.gamma = g_;
+            ga.beta = b_;
             ga.W = W;
             ga.bias = bias;
-            ga.resid = m->dx;
-            ga.xb_out = fold ? m->dxn : nullptr;
-            ga.stats_out = m->gv_stats;
-            ga.row_skip = fin;
-            ga.M = B;
-            ga.N = d;
-            ga.K = K;
-            parts = gemv16_parts(d);
-            ProfScope ps(PROF_DEC_GEMM, 2.0 * B * d * K, s);
-            return gemv16(ga, s);
-        };
-        for (int l = 0; l < L; ++l) {
-            const DecLayer& e = m->dec[l];
-            SplitkInput part;
-            part.planes = m->dpart;
-            part.splits = 1;
-            part.bias = nullptr;
-            WSB_RUN(lin_ln(e.ln1_g, e.ln1_b, e.sqkv_w, e.sqkv_b, e.sqkv_wf, e.sqkv_c1, e.sqkv_c2, 3 * d, m->dpart, nullptr));
-            part.split_stride = static_cast<long long>(B) * 3 * d;
+        }
+        ga.stats = m->gv_stats;
+        ga.stats_parts = parts;
+        ga.out_f32 = out_f32;
+        ga.out_bf16_gelu = out_gelu;
+        ga.row_skip = fin;
+        ga.M = B;
+        ga.N = N;
+        ga.K = d;
+        ProfScope ps(PROF_DEC_GEMM, 2.0 * B * N * d, s);
+        return gemv16(ga, s);
+    };
+    auto lin_resid = [&](const __nv_bfloat16* a_, const __nv_bfloat16* W, const float* bias, int K) -> int {
+        Gemv16Args ga;
+        ga.a = a_;
+        ga.W = W;
+        ga.bias = bias;
+        ga.resid = m->dx;
+        ga.xb_out = fold ? m->dxn : nullptr;
+        ga.stats_out = m->gv_stats;
+        ga.row_skip = fin;
+        ga.M = B;
+        ga.N = d;
+        ga.K = K;
+        parts = gemv16_parts(d);
+        ProfScope ps(PROF_DEC_GEMM, 2.0 * B * d * K, s);
+        return gemv16(ga, s);
+    };
+    for (int l = 0; l < L; ++l) {
+        const DecLayer& e = m->dec[l];
+        SplitkInput part;
+        part.planes = m->dpart;
+        part.splits = 1;
+        part.bias = nullptr;
+        WSB_RUN(lin_ln(e.ln1_g, e.ln1_b, e.sqkv_w, e.sqkv_b, e.sqkv_wf, e.sqkv_c1, e.sqkv_c2, 3 * d, m->dpart, nullptr));
+        part.split_stride = static_cast<long long>(B) * 3 * d;
+        WSB_RUN(decode_self_attention(nullptr, &part, d, st.k_cache + l * cache_l, st.v_cache + l * cache_l, tmax, m->step, 0,
+                                      fin, m->datt, B, H, s, st.anc, st.anc_ld));
+        WSB_RUN(lin_resid(m->datt, e.so_w, e.so_b, d));
+        WSB_RUN(lin_ln(e.ln2_g, e.ln2_b, e.cq_w, e.cq_b, e.cq_wf, e.cq_c1, e.cq_c2, d, m->dpart, nullptr));
+        part.split_stride = static_cast<long long>(B) * d;
+        WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s, st.kv_div));
+        WSB_RUN(lin_resid(m->datt, e.co_w, e.co_b, d));
+        WSB_RUN(lin_ln(e.ln3_g, e.ln3_b, e.fc1_w, e.fc1_b, e.fc1_wf, e.fc1_c1, e.fc1_c2, F, nullptr, m->dff));
+        WSB_RUN(lin_resid(m->dff, e.fc2_w, e.fc2_b, F));
+    }
+    if (with_logits) WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec_ln_g, m->dec_ln_b, m->dxn, nullptr, B, d, s));
+    return 0;
+}
+
+// K5d (opt-in): 65..256 rows, cluster split-K linear layers with folded LayerNorm (skinny.cu), 8 launches per layer
+static int decode_layers_cluster(const StepCtx& x) {
+    WSB_STEP_LOCALS;
+    // 65..256 rows: one cluster split-K launch per linear layer (skinny.cu), LayerNorm folded into the consumers,
+    // 8 launches per layer instead of 12.  The residual stream travels as fp32 (m->dx) + bf16 (m->dxn) + per-tile
+    // row statistics (m->gv_stats: [parts][B][2]).
+    int parts = 1;
+    {
+        ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
+        WSB_RUN(row_stats_any(m->dx, B, d, m->gv_stats, m->dxn, s));
+    }
+    auto lin_fold = [&](const __nv_bfloat16* Wf, const float* c1, const float* c2, int N, float* out_f32,
+                        __nv_bfloat16* out_gelu) -> int {
+        SkinnyArgs a;
+        a.A = m->dxn;
+        a.lda = d;
+        a.W = Wf;
+        a.M = B;
+        a.N = N;
+        a.K = d;
+        a.bias = c2;
+        a.c1 = c1;
+        a.stats = m->gv_stats;
+        a.stats_parts = parts;
+        a.stats_ld = B;
+        a.out_f32 = out_f32;
+        a.out_bf16_gelu = out_gelu;
+        a.row_skip = fin;
+        ProfScope ps(PROF_DEC_GEMM, 2.0 * B * N * d, s);
+        return skinny_cluster_linear(a, s);
+    };
+    auto lin_resid = [&](const __nv_bfloat16* a_, const __nv_bfloat16* W, const float* bias, int K) -> int {
+        SkinnyArgs a;
+        a.A = a_;
+        a.lda = K;
+        a.W = W;
+        a.M = B;
+        a.N = d;
+        a.K = K;
+        a.bias = bias;
+        a.resid = m->dx;
+        a.xb_out = m->dxn;
+        a.stats_out = m->gv_stats;
+        a.stats_out_ld = B;
+        a.row_skip = fin;
+        parts = d / 128;
+        ProfScope ps(PROF_DEC_GEMM, 2.0 * B * d * K, s);
+        return skinny_cluster_linear(a, s);
+    };
+    for (int l = 0; l < L; ++l) {
+        const DecLayer& e = m->dec[l];
+        SplitkInput part;
+        part.planes = m->dpart;
+        part.splits = 1;
+        part.bias = nullptr;
+        WSB_RUN(lin_fold(e.sqkv_wf, e.sqkv_c1, e.sqkv_c2, 3 * d, m->dpart, nullptr));
+        part.split_stride = static_cast<long long>(B) * 3 * d;
+        {
+            ProfScope ps(PROF_DEC_SELF_ATTN, 0.0, s);
             WSB_RUN(decode_self_attention(nullptr, &part, d, st.k_cache + l * cache_l, st.v_cache + l * cache_l, tmax, m->step, 0,
                                           fin, m->datt, B, H, s, st.anc, st.anc_ld));
-            WSB_RUN(lin_resid(m->datt, e.so_w, e.so_b, d));
-            WSB_RUN(lin_ln(e.ln2_g, e.ln2_b, e.cq_w, e.cq_b, e.cq_wf, e.cq_c1, e.cq_c2, d, m->dpart, nullptr));
-            part.split_stride = static_cast<long long>(B) * d;
-            WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s, st.kv_div));
-            WSB_RUN(lin_resid(m->datt, e.co_w, e.co_b, d));
-            WSB_RUN(lin_ln(e.ln3_g, e.ln3_b, e.fc1_w, e.fc1_b, e.fc1_wf, e.fc1_c1, e.fc1_c2, F, nullptr, m->dff));
-            WSB_RUN(lin_resid(m->dff, e.fc2_w, e.fc2_b, F));
         }
-        if (with_logits) WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec_ln_g, m->dec_ln_b, m->dxn, nullptr, B, d, s));
-    } else if (m->use_cluster && m->use_fold && m->dec[0].sqkv_wf != nullptr && B <= 256 && skinny_cluster_supported(B, d, d) &&
-               skinny_cluster_supported(B, F, d) && skinny_cluster_supported(B, d, F)) {
-        // 65..256 rows: one cluster split-K launch per linear layer (skinny.cu), LayerNorm folded into the consumers,
-        // 8 launches per layer instead of 12.  The residual stream travels as fp32 (m->dx) + bf16 (m->dxn) + per-tile
-        // row statistics (m->gv_stats: [parts][B][2]).
-        int parts = 1;
+        WSB_RUN(lin_resid(m->datt, e.so_w, e.so_b, d));
+        WSB_RUN(lin_fold(e.cq_wf, e.cq_c1, e.cq_c2, d, m->dpart, nullptr));
+        part.split_stride = static_cast<long long>(B) * d;
         {
-            ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
-            WSB_RUN(row_stats_any(m->dx, B, d, m->gv_stats, m->dxn, s));
+            ProfScope ps(PROF_DEC_CROSS_ATTN, 4.0 * B * H * T * 64.0, s);
+            WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s, st.kv_div));
         }
-        auto lin_fold = [&](const __nv_bfloat16* Wf, const float* c1, const float* c2, int N, float* out_f32,
-                            __nv_bfloat16* out_gelu) -> int {
-            SkinnyArgs a;
-            a.A = m->dxn;
-            a.lda = d;
-            a.W = Wf;
-            a.M = B;
-            a.N = N;
-            a.K = d;
-            a.bias = c2;
-            a.c1 = c1;
-            a.stats = m->gv_stats;
-            a.stats_parts = parts;
-            a.stats_ld = B;
-            a.out_f32 = out_f32;
-            a.out_bf16_gelu = out_gelu;
-            a.row_skip = fin;
-            ProfScope ps(PROF_DEC_GEMM, 2.0 * B * N * d, s);
-            return skinny_cluster_linear(a, s);
-        };
-        auto lin_resid = [&](const __nv_bfloat16* a_, const __nv_bfloat16* W, const float* bias, int K) -> int {
-            SkinnyArgs a;
-            a.A = a_;
-            a.lda = K;
-            a.W = W;
-            a.M = B;
-            a.N = d;
-            a.K = K;
-            a.bias = bias;
-            a.resid = m->dx;
-            a.xb_out = m->dxn;
-            a.stats_out = m->gv_stats;
-            a.stats_out_ld = B;
-            a.row_skip = fin;
-            parts = d / 128;
-            ProfScope ps(PROF_DEC_GEMM, 2.0 * B * d * K, s);
-            return skinny_cluster_linear(a, s);
-        };
-        for (int l = 0; l < L; ++l) {
-            const DecLayer& e = m->dec[l];
-            SplitkInput part;
-            part.planes = m->dpart;
-            part.splits = 1;
-            part.bias = nullptr;
-            WSB_RUN(lin_fold(e.sqkv_wf, e.sqkv_c1, e.sqkv_c2, 3 * d, m->dpart, nullptr));
-            part.split_stride = static_cast<long long>(B) * 3 * d;
-            {
-                ProfScope ps(PROF_DEC_SELF_ATTN, 0.0, s);
-                WSB_RUN(decode_self_attention(nullptr, &part, d, st.k_cache + l * cache_l, st.v_cache + l * cache_l, tmax, m->step, 0,
-                                              fin, m->datt, B, H, s, st.anc, st.anc_ld));
-            }
-            WSB_RUN(lin_resid(m->datt, e.so_w, e.so_b, d));
-            WSB_RUN(lin_fold(e.cq_wf, e.cq_c1, e.cq_c2, d, m->dpart, nullptr));
-            part.split_stride = static_cast<long long>(B) * d;
-            {
-                ProfScope ps(PROF_DEC_CROSS_ATTN, 4.0 * B * H * T * 64.0, s);
-                WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s, st.kv_div));
-            }
-            WSB_RUN(lin_resid(m->datt, e.co_w, e.co_b, d));
-            WSB_RUN(lin_fold(e.fc1_wf, e.fc1_c1, e.fc1_c2, F, nullptr, m->dff));
-            WSB_RUN(lin_resid(m->dff, e.fc2_w, e.fc2_b, F));
-        }
-        if (with_logits) {
-            ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
-            WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec_ln_g, m->dec_ln_b, m->dxn, nullptr, B, d, s));
-        }
-    } else {
+        WSB_RUN(lin_resid(m->datt, e.co_w, e.co_b, d));
+        WSB_RUN(lin_fold(e.fc1_wf, e.fc1_c1, e.fc1_c2, F, nullptr, m->dff));
+        WSB_RUN(lin_resid(m->dff, e.fc2_w, e.fc2_b, F));
+    }
+    if (with_logits) {
+        ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
+        WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec_ln_g, m->dec_ln_b, m->dxn, nullptr, B, d, s));
+    }
+    return 0;
+}
+
+// K5: any batch, tcgen05 split-K GEMM + fused second phase (12 launches per layer); leaves LayerNorm(x) of the final
+// decoder LayerNorm in m->dxn
+static int decode_layers_splitk(const StepCtx& x) {
+    WSB_STEP_LOCALS;
     {
         ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
         WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec[0].ln1_g, m->dec[0].ln1_b, m->dxn, nullptr, B, d, s));
@@ -660,6 +674,35 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
         WSB_RUN(skinny_linear(m, m->dxn, e.fc1_w, e.fc1_b, B, F, d, 1, m->dff, nullptr, nullptr, nullptr, nullptr, s, fin));
         WSB_RUN(skinny_linear(m, m->dff, e.fc2_w, e.fc2_b, B, d, F, 0, nullptr, m->dx, next_g, next_b, m->dxn, s, fin));
     }
+    return 0;
+}
+
+// one decoder position for all rows.  with_logits: project + arg-max + finalize (or, with `beam`, raw logits +
+// beam bookkeeping); else prefill advance.
+static int decode_step(Model* m, const DecState& st, bool with_logits, bool first_generated, int prompt_len, int max_new,
+                       const int* forced, int forced_ld, int eos_id, int pad_id, cudaStream_t s,
+                       const BeamState* beam = nullptr) {
+    const wsb_model_config& c = m->cfg;
+    const int B = st.B;
+    const int d = c.d_model, F = c.ffn_dim, L = c.n_layers, H = c.n_heads, T = m->T, tmax = c.max_target_positions;
+    const unsigned char* fin = forced ? nullptr : st.finished;
+    struct PdlScope {
+        bool prev;
+        explicit PdlScope(bool on) : prev(g_use_pdl) { g_use_pdl = on; }
+        ~PdlScope() { g_use_pdl = prev; }
+    } pdl_scope(m->use_pdl || (m->use_gemv && B <= m->gemv_rows && c.d_model <= 1536));
+    // (programmatic dependent launch: the linear-layer kernels fetch their weight tiles before the dependency wait)
+    WSB_RUN(embed_tokens_step(st.next_token, m->step, 0, m->dec_emb, m->dec_pos, m->dx, B, d, s));
+    const long long cache_l = static_cast<long long>(B) * H * tmax * 64;
+    const StepCtx x{m, st, B, d, F, L, H, T, tmax, fin, cache_l, with_logits, s};
+    const bool folded = m->use_fold && m->dec[0].sqkv_wf != nullptr;
+    if (m->use_gemv && B <= m->gemv_rows && d <= 1536) {
+        WSB_RUN(decode_layers_fused(x));
+    } else if (m->use_cluster && folded && B <= 256 && skinny_cluster_supported(B, d, d) && skinny_cluster_supported(B, F, d) &&
+               skinny_cluster_supported(B, d, F)) {
+        WSB_RUN(decode_layers_cluster(x));
+    } else {
+        WSB_RUN(decode_layers_splitk(x));
     }
     if (!with_logits) return prefill_advance(st.next_token, forced, forced_ld, m->prompt_dev, m->step, B, s);
     if (beam) {
