@@ -1,7 +1,7 @@
-// K5c -- skinny linear layers for decode batches of at most 16 rows (the tail of a greedy decode after batch
+// K5c -- skinny linear layers for decode batches of at most 64 rows (the tail of a greedy decode after batch
 // compaction, or a short recording with a handful of windows).
 //
-// At <= 16 rows the tcgen05 split-K GEMM + second-phase reduce pair is pure fixed latency (TMEM allocation,
+// At few rows the tcgen05 split-K GEMM + second-phase reduce pair is pure fixed latency (TMEM allocation,
 // tensor-map fetch, pipeline fill, plane write + re-read, two launches): ~13 us per linear layer against
 // ~2 us of weight streaming.  This kernel does the whole layer in one launch of <= 148 CTAs (one per SM):
 //   * a CTA owns 8*NT output features and the full K extent -> no split-K, no partial planes.  Its weight
@@ -9,15 +9,18 @@
 //     reads are bank-conflict free), all issued at kernel entry on one mbarrier: maximum memory-level
 //     parallelism at zero register cost;
 //   * the consumer's LayerNorm is fused in WITHOUT a separate pass: the producer of the residual stream (the
-//     previous residual-update launch of this kernel, or the embedding kernel) leaves per-CTA partial
-//     (sum, sum of squares) of every row; the consumer adds them in a fixed order, and normalises exactly the
-//     fp32 elements each lane needs for its MMA fragments, while the weights are still in flight;
-//   * 16 rows are exactly the M of a warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate): the 16 warps
-//     split K (the k order inside a 32-element block is permuted identically for both operands so that
-//     every lane's 8 contiguous elements feed two MMAs), the 16 partial tiles are summed through shared
-//     memory and the epilogue (bias; GELU -> bf16 | fp32 | in-place fp32 residual add + row statistics for
-//     the next LayerNorm) is applied.
-// HBM-bound by design: it streams each weight byte once; the decode step is launch-latency-bound around it.
+//     previous residual-update launch of this kernel, or the row-statistics kernel after the embedding) leaves
+//     per-CTA partial (sum, sum of squares) of every row; the consumer adds them in a fixed order and either
+//     (IN_LN 1) normalises exactly the fp32 elements each lane needs for its MMA fragments, or (IN_LN 2, the
+//     default) multiplies the producer's bf16 copy of the rows with weights that have the LayerNorm affine
+//     folded in and applies rstd (acc - mean c1) + c2 in the epilogue (weights.py: fold_layernorm);
+//   * 16 rows are exactly the M of a warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate).  MT = 1, 2 or 4
+//     m-tiles: the 16 warps form MT groups, a group owns 16 rows and its warps split K (the k order inside a
+//     32-element block is permuted identically for both operands so that every lane's 8 contiguous elements
+//     feed two MMAs); the partial tiles are summed through shared memory and the epilogue (bias; GELU -> bf16 |
+//     fp32 | in-place fp32 residual add + bf16 copy + row statistics for the next LayerNorm) is applied.
+// HBM-bound by design at <= 16 rows (it streams each weight byte once; the decode step is launch-latency-bound
+// around it); beyond that every CTA re-reads all activations and the kernel becomes L2-bound.
 // (tcgen05 needs M = 128 tiles and a TMEM prologue -- the wrong tool at M <= 16; this is deliberate.)
 #include "common.cuh"
 #include "wsb_internal.h"
