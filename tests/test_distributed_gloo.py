@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from whisperseg_b200 import postprocess as pp
-from whisperseg_b200.distributed import segment_sharded, shard_bounds
+from whisperseg_b200.distributed import folder_window_table, segment_many_sharded, segment_sharded, shard_bounds
 from whisperseg_b200.frontend import FrontendPlan, get_n_fft_given_sr
 
 SR, STS, MAX_LEN = 16000, 0.01, 40
@@ -119,3 +119,73 @@ def test_shard_bounds_cover_everything():
             spans = [shard_bounds(n, world, r)[:2] for r in range(world)]
             flat = [i for a, b in spans for i in range(a, b)]
             assert flat == list(range(n))
+
+
+# ------------------------------------------------------------------ folder mode (BASELINE configs[4]) sharded over ranks
+def _folder_clips(seed, n_clips):
+    """Ragged clips (0.3 .. 27 s at 16 kHz); clip i is filled with the constant i + 1 so that a worker can check
+    that its window descriptors point into the right clip."""
+    rng = np.random.default_rng(seed)
+    secs = rng.uniform(0.3, 27.0, n_clips)
+    secs[1] = 0.05                                       # shorter than one FFT frame
+    return [np.full(int(s_ * SR), i + 1, dtype=np.float32) for i, s_ in enumerate(secs)]
+
+
+def _expected_folder(clips, num_trials):
+    plan = FrontendPlan(SR, STS, 0)
+    per_clip, owners, spans = folder_window_table(plan, [len(c) for c in clips], num_trials)
+    texts = _Tok().batch_decode([_tokens_for(i, MAX_LEN - 3) for i in range(len(owners))])
+    out = []
+    for ci, (a, b) in enumerate(spans):
+        pred = pp.parse_generation(texts[a:b], [w.as_tuple() for w in per_clip[ci]], STS * 2, len(clips[ci]) / SR, STS,
+                                   num_trials, STS * 8, STS, "clustering", BOOK)
+        out.append(pp.correct_fft_blur_and_dedupe(pred, SR, get_n_fft_given_sr(SR)))
+    return out, owners, per_clip, spans
+
+
+def _folder_worker(rank, world, port, seed, n_clips, num_trials, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    clips = _folder_clips(seed, n_clips)
+    plan = FrontendPlan(SR, STS, 0)
+    per_clip, owners, spans = folder_window_table(plan, [len(c) for c in clips], num_trials)
+    checks = {"n": 0, "bad": 0}
+
+    def gen(first, descs, plan_, piece):
+        checks["n"] = len(descs)
+        for i, (start, clo, chi) in enumerate(descs.tolist()):
+            g = first + i
+            ci = owners[g]
+            w = per_clip[ci][g - spans[ci][0]]
+            ok = (chi - clo == len(clips[ci]) and start - clo == w.start and clo % 4 == 0 and
+                  (chi == clo or (piece[clo] == ci + 1 and piece[chi - 1] == ci + 1)))
+            checks["bad"] += 0 if ok else 1
+        return torch.tensor([_tokens_for(first + i, MAX_LEN - 3) for i in range(len(descs))], dtype=torch.int32).reshape(-1, MAX_LEN - 3)
+    res = segment_many_sharded(_Seg(), clips, SR, 0, STS, max_length=MAX_LEN, num_trials=num_trials, generate_fn=gen)
+    lo, hi, _ = shard_bounds(len(owners), world, rank)
+    q.put((rank, res, checks["n"], hi - lo, checks["bad"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("seed,n_clips,num_trials", [(1, 9, 1), (2, 5, 3), (3, 2, 1)])
+def test_sharded_folder_world2_gloo(seed, n_clips, num_trials):
+    """`segment_many_sharded`: the flattened window list of a ragged folder is cut into contiguous shards (a clip may
+    straddle the cut), each rank's local buffer holds only its clips, and after ONE all-gather every rank returns
+    the per-clip predictions of the single-process computation."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_folder_worker, args=(r, 2, port, seed, n_clips, num_trials, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    exp, owners, _, _ = _expected_folder(_folder_clips(seed, n_clips), num_trials)
+    assert len(exp) == n_clips and sum(len(e["onset"]) for e in exp) > 0
+    for rank, res, n_seen, n_mine, bad in got:
+        assert res == exp, "rank %d result differs from the single-process result" % rank
+        assert n_seen == n_mine and bad == 0

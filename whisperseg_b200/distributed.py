@@ -7,6 +7,8 @@ Here every rank computes the same window plan, takes a contiguous shard of the w
 windows touch, runs front-end + encoder + decode locally, and the generated token ids are
 exchanged with ONE all-gather of a padded int32 [windows_per_rank, max_new] tensor (NCCL over
 NVLink on GPUs, gloo in the CPU tests).  Post-processing then runs identically on every rank.
+`segment_many_sharded` does the same for folder mode: the windows of all clips, flattened in clip order, are
+sharded, and the gathered token ids are regrouped per clip.
 """
 import numpy as np
 import torch
@@ -89,18 +91,111 @@ def segment_sharded(segmenter, audio, sr, min_frequency=None, spec_time_step=Non
     return pp.correct_fft_blur_and_dedupe(pred, sr, get_n_fft_given_sr(sr))
 
 
-def _engine_generate(segmenter, plan, windows, piece, slice_start, n_total, max_length, num_beams=1, length_penalty=1.0):
-    eng = segmenter.engines[0]
+def folder_window_table(plan, lengths, num_trials):
+    """Folder mode: the windows of all clips flattened in clip order.  Returns (per_clip_windows, owner clip of
+    every window, [first, last+1) window range of every clip)."""
+    per_clip, owners, spans = [], [], []
+    for ci, n in enumerate(lengths):
+        wins = plan.windows(int(n), num_trials)
+        spans.append((len(owners), len(owners) + len(wins)))
+        per_clip.append(wins)
+        owners += [ci] * len(wins)
+    return per_clip, owners, spans
+
+
+def local_folder_buffer(audios, per_clip, owners, lo, hi):
+    """The samples rank-local windows [lo, hi) of the flattened list touch: the clips they belong to, concatenated
+    (each padded to a multiple of 4 samples, so every clip stays 16-byte aligned on the device), and one
+    [start, clip_lo, clip_hi) descriptor per window in local buffer coordinates -- the layout segment_many()
+    uses for the whole folder (per-window bounds keep clips from leaking into each other)."""
+    if hi <= lo:
+        return np.zeros(0, dtype=np.float32), np.zeros((0, 3), dtype=np.int64)
+    c_lo, c_hi = owners[lo], owners[hi - 1]
+    pieces, base_of, base = [], {}, 0
+    for ci in range(c_lo, c_hi + 1):
+        a = np.ascontiguousarray(np.asarray(audios[ci]), dtype=np.float32)
+        base_of[ci] = (base, len(a))
+        pieces.append(a)
+        pad = (-len(a)) % 4
+        if pad:
+            pieces.append(np.zeros(pad, dtype=np.float32))
+        base += len(a) + pad
+    first_of = {}
+    pos = 0
+    for ci, wins in enumerate(per_clip):
+        first_of[ci] = pos
+        pos += len(wins)
+    descs = []
+    for g in range(lo, hi):
+        ci = owners[g]
+        w = per_clip[ci][g - first_of[ci]]
+        b, n = base_of[ci]
+        descs.append([b + w.start, b, b + n])
+    return (np.concatenate(pieces) if pieces else np.zeros(0, dtype=np.float32)), np.asarray(descs, dtype=np.int64).reshape(-1, 3)
+
+
+def segment_many_sharded(segmenter, audios, sr, min_frequency=None, spec_time_step=None, min_segment_length=None, eps=None,
+                         time_per_frame_for_voting=None, consolidation_method="clustering", max_length=448, num_trials=1,
+                         group=None, generate_fn=None, num_beams=4, length_penalty=1.0):
+    """Folder mode under torch.distributed (BASELINE configs[4]: thousands of variable-length clips on 8 GPUs):
+    drop-in for `segmenter.segment_many(...)`, same list of predictions on every rank.
+
+    The windows of ALL clips are flattened in clip order (like segment_many) and that list is cut into contiguous
+    shards, so a rank's batches are filled across clip boundaries and the shards are balanced in windows, not in
+    clips; each rank uploads only the clips its windows belong to.  One all-gather of the token ids, then every
+    rank regroups them per clip and post-processes exactly like segment().
+    `generate_fn(first_global_window, local_descs, plan, local_audio) -> int32 [n_local, max_new]` can be injected
+    (the gloo CPU tests use a scripted generator); by default the rank's engine runs."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    cfgd = segmenter.default_segmentation_config
+    if min_frequency is None:
+        min_frequency = cfgd.get("min_frequency", 0)
+    if spec_time_step is None:
+        spec_time_step = cfgd.get("spec_time_step", 0.0025)
+    ratio = pp.RATIO_DECODING_TIME_STEP_TO_SPEC_TIME_STEP
+    if min_segment_length is None:
+        min_segment_length = spec_time_step * ratio
+    if eps is None:
+        eps = spec_time_step * ratio * 4
+    if time_per_frame_for_voting is None:
+        time_per_frame_for_voting = spec_time_step
+    plan = FrontendPlan(sr, spec_time_step, min_frequency, total_spec_columns=segmenter.total_spec_columns)
+    lengths = [len(a) for a in audios]
+    per_clip, owners, spans = folder_window_table(plan, lengths, num_trials)
+    if not owners:
+        return []
+    lo, hi, per = shard_bounds(len(owners), world, rank)
     tok = segmenter.tokenizer
     max_new = max_length - len(tok.prompt_ids)
-    if not windows:
-        return torch.zeros((0, max_new), dtype=torch.int32, device=eng.device)
-    feats = eng.features_sliced(plan, piece, windows, slice_start, n_total)
+    piece, descs = local_folder_buffer(audios, per_clip, owners, lo, hi)
+    if generate_fn is None:
+        local_ids = _engine_generate_folder(segmenter, plan, piece, descs, max_length, num_beams, length_penalty)
+    else:
+        local_ids = generate_fn(lo, descs, plan, piece)
+    gathered = all_gather_tokens(local_ids, per, max_new, tok.pad_token_id, group)
+    rows = gathered.cpu().numpy()
+    texts = []
+    for r in range(world):
+        a, b, _ = shard_bounds(len(owners), world, r)
+        texts += tok.batch_decode(rows[r * per:r * per + (b - a)])
+    n_fft = get_n_fft_given_sr(sr)
+    results = []
+    for ci, (a, b) in enumerate(spans):
+        pred = pp.parse_generation(texts[a:b], [w.as_tuple() for w in per_clip[ci]], min_segment_length, lengths[ci] / sr,
+                                   spec_time_step, num_trials, eps, time_per_frame_for_voting, consolidation_method,
+                                   segmenter.cluster_codebook, segmenter.precision_bits)
+        results.append(pp.correct_fft_blur_and_dedupe(pred, sr, n_fft))
+    return results
+
+
+def _generate_from_features(segmenter, feats, max_length, num_beams, length_penalty):
+    eng = segmenter.engines[0]
+    tok = segmenter.tokenizer
     outs = []
     if not 1 <= int(num_beams) <= 4:
         raise ValueError("whisperseg_b200 supports num_beams in [1, 4], got %r" % (num_beams,))
     per_call = eng.max_batch if num_beams == 1 else max(1, eng.max_batch // num_beams)
-    for pos in range(0, len(windows), per_call):
+    for pos in range(0, feats.shape[0], per_call):
         chunk = feats[pos:pos + per_call].contiguous()
         eng.encode(chunk)
         if num_beams == 1:
@@ -110,3 +205,25 @@ def _engine_generate(segmenter, plan, windows, piece, slice_start, n_total, max_
                                        max_length, length_penalty)
         outs.append(ids)
     return torch.cat(outs, 0)
+
+
+def _engine_generate_folder(segmenter, plan, piece, descs, max_length, num_beams=1, length_penalty=1.0):
+    eng = segmenter.engines[0]
+    max_new = max_length - len(segmenter.tokenizer.prompt_ids)
+    if len(descs) == 0:
+        return torch.zeros((0, max_new), dtype=torch.int32, device=eng.device)
+    audio_dev = eng.upload_audio(piece)
+    desc_dev = torch.from_numpy(np.ascontiguousarray(descs, dtype=np.int64)).to(eng.device)
+    feats = eng.features_device(plan, audio_dev, desc_dev, len(descs))
+    return _generate_from_features(segmenter, feats, max_length, num_beams, length_penalty)
+
+
+def _engine_generate(segmenter, plan, windows, piece, slice_start, n_total, max_length, num_beams=1, length_penalty=1.0):
+    eng = segmenter.engines[0]
+    tok = segmenter.tokenizer
+    max_new = max_length - len(tok.prompt_ids)
+    if not windows:
+        return torch.zeros((0, max_new), dtype=torch.int32, device=eng.device)
+    feats = eng.features_sliced(plan, piece, windows, slice_start, n_total)
+    return _generate_from_features(segmenter, feats, max_length, num_beams, length_penalty)
+
