@@ -125,3 +125,25 @@ def test_segment_files_groups_by_rate_and_builds_the_table(tmp_path):
     audio_io.segment_files(seg2, paths[:2], group_seconds=1.2)
     assert [c[0] for c in seg2.calls] == [1, 1]
     assert audio_io.segment_files(seg2, []) == ({}, {"filename": [], "onset": [], "offset": [], "cluster": []})
+
+
+def test_wav_info_matches_decode(tmp_path):
+    """Header-only length probe (what every rank reads of every file in sharded folder mode) against the decoder."""
+    rng = np.random.default_rng(11)
+    cases = [(2, 1, 16000, 12345, False), (2, 2, 22050, 777, False), (3, 1, 48000, 1001, True), (4, 3, 32000, 64, False),
+             (1, 1, 8000, 0, False)]
+    for i, (width, ch, sr, frames, ext) in enumerate(cases):
+        raw = rng.integers(0, 256, size=frames * ch * width, dtype=np.uint8).tobytes()
+        path = tmp_path / ("c%d.wav" % i)
+        path.write_bytes(_wav_bytes(raw, sr, width, ch, extensible=ext))
+        assert audio_io.wav_info(str(path)) == (frames, sr, ch)
+        assert audio_io.wav_info(str(path), head_bytes=40) == (frames, sr, ch)      # data chunk beyond the first read
+        audio, sr2 = audio_io.load_audio(str(path))
+        assert (len(audio), sr2) == (frames, sr)
+    trunc = tmp_path / "trunc.wav"                                                   # header announces more than is there
+    trunc.write_bytes(_wav_bytes(b"\x00" * 2000, 16000, 2, 1)[:-500])
+    assert audio_io.wav_info(str(trunc))[0] == len(audio_io.load_audio(str(trunc))[0]) == 750
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad.wav"
+        bad.write_bytes(b"OggS" + b"\x00" * 64)
+        audio_io.wav_info(str(bad))

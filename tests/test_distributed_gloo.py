@@ -189,3 +189,79 @@ def test_sharded_folder_world2_gloo(seed, n_clips, num_trials):
     for rank, res, n_seen, n_mine, bad in got:
         assert res == exp, "rank %d result differs from the single-process result" % rank
         assert n_seen == n_mine and bad == 0
+
+
+# ------------------------------------------------------------------ folder of WAV files, sharded (audio_io.segment_files_sharded)
+def _write_folder(root, seed, n_files):
+    import struct
+    rng = np.random.default_rng(seed)
+    paths = []
+    for i in range(n_files):
+        sr = SR if i % 4 else 2 * SR                     # two sample-rate groups
+        frames = int(rng.uniform(0.2, 18.0) * sr)
+        pcm = np.full(frames, 100 * (i + 1), dtype="<i2").tobytes()
+        fmt = struct.pack("<HHIIHH", 1, 1, sr, sr * 2, 2, 16)
+        body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"data" + struct.pack("<I", len(pcm)) + pcm
+        p = os.path.join(root, "clip%02d.wav" % i)
+        with open(p, "wb") as f:
+            f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+        paths.append(p)
+    return paths
+
+
+def _files_worker(rank, world, port, paths, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from whisperseg_b200 import audio_io
+    loaded = []
+    real_load = audio_io.load_audio
+
+    def counting_load(src, *a, **k):
+        loaded.append(os.path.basename(src))
+        return real_load(src, *a, **k)
+    audio_io.load_audio = counting_load
+
+    def gen(first, descs, plan_, piece):
+        return torch.tensor([_tokens_for(first + i, MAX_LEN - 3) for i in range(len(descs))], dtype=torch.int32).reshape(-1, MAX_LEN - 3)
+    per_file, table = audio_io.segment_files_sharded(_Seg(), paths, workers=2, generate_fn=gen, min_frequency=0,
+                                                     spec_time_step=STS, max_length=MAX_LEN, num_trials=1)
+    q.put((rank, per_file, table, sorted(loaded)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_files_world2_gloo(tmp_path):
+    """Folder of WAV files on 2 ranks: headers fix the plan, each rank decodes only the clips of its shard, results
+    are rank-identical and equal to the single-process per-clip post-processing of the same token rows."""
+    from whisperseg_b200 import audio_io
+    paths = _write_folder(str(tmp_path), 5, 9)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_files_worker, args=(r, 2, port, paths, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=180) for _ in procs], key=lambda g: g[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    # single-process expectation, one sample-rate group at a time (the window index restarts per group)
+    exp = {}
+    by_rate = {}
+    for p in paths:
+        by_rate.setdefault(audio_io.wav_info(p)[1], []).append(p)
+    for sr, group in by_rate.items():
+        plan = FrontendPlan(sr, STS, 0)
+        lens = [audio_io.wav_info(p)[0] for p in group]
+        per_clip, owners, spans = folder_window_table(plan, lens, 1)
+        texts = _Tok().batch_decode([_tokens_for(i, MAX_LEN - 3) for i in range(len(owners))])
+        for ci, (a, b) in enumerate(spans):
+            pred = pp.parse_generation(texts[a:b], [w.as_tuple() for w in per_clip[ci]], STS * 2, lens[ci] / sr, STS, 1,
+                                       STS * 8, STS, "clustering", BOOK)
+            exp[group[ci]] = pp.correct_fft_blur_and_dedupe(pred, sr, get_n_fft_given_sr(sr))
+    assert got[0][1] == exp and got[1][1] == exp and got[0][2] == got[1][2]
+    assert got[0][2]["filename"] and len(got[0][2]["filename"]) == len(got[0][2]["onset"])
+    names = sorted(os.path.basename(p) for p in paths)
+    assert sorted(set(got[0][3]) | set(got[1][3])) == names            # every clip decoded somewhere ...
+    assert len(got[0][3]) < len(names) and len(got[1][3]) < len(names)  # ... but no rank decoded the whole folder

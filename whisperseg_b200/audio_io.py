@@ -12,6 +12,8 @@ Replaces, for WAV input, the `librosa.load` calls either side of the hot path:
   * reference scripts/segment.py:41-56 (folder loop, one segment() call per file) -> `segment_files`:
     files are decoded by a small thread pool and handed to `segment_many` in groups, so decode, H2D and
     GPU work overlap and short clips share batches.
+  * the same folder on several GPUs (BASELINE configs[4]) -> `segment_files_sharded`: every rank reads the WAV
+    headers only (`wav_info`), decodes the clips of its own shard and joins one all-gather per sample-rate group.
 Only RIFF/WAVE is handled (the reference globs *.wav / *.WAV); anything else raises ValueError.
 """
 import io
@@ -33,27 +35,58 @@ def _read_bytes(src):
         return f.read()
 
 
-def decode_wav(data):
-    """RIFF/WAVE bytes -> (float32 array [channels, frames], sample_rate)."""
+def _wav_layout(data, total_size=None):
+    """Parse the RIFF chunk list: ((format tag, channels, sample rate, block align, bits), (data offset, data bytes)).
+    `data` may be just the head of the file when `total_size` (the file size) is given."""
     if len(data) < 12 or data[:4] not in (b"RIFF", b"RF64") or data[8:12] != b"WAVE":
         raise ValueError("not a RIFF/WAVE stream")
+    end = len(data) if total_size is None else total_size
     pos, fmt, payload = 12, None, None
     while pos + 8 <= len(data):
         cid, size = data[pos:pos + 4], struct.unpack_from("<I", data, pos + 4)[0]
         body = pos + 8
         if cid == b"fmt ":
+            if body + 16 > len(data):
+                break
             tag, ch, sr, _, align, bits = struct.unpack_from("<HHIIHH", data, body)
-            if tag == _EXTENSIBLE and size >= 26:
+            if tag == _EXTENSIBLE and size >= 26 and body + 26 <= len(data):
                 tag = struct.unpack_from("<H", data, body + 24)[0]
             fmt = (tag, ch, sr, align, bits)
         elif cid == b"data":
-            if size == 0xFFFFFFFF or body + size > len(data):      # streamed / truncated files: take what is there
-                size = len(data) - body
+            if size == 0xFFFFFFFF or body + size > end:            # streamed / truncated files: take what is there
+                size = end - body
             payload = (body, size)
             break
         pos = body + size + (size & 1)
     if fmt is None or payload is None:
         raise ValueError("WAVE stream without fmt/data chunk")
+    return fmt, payload
+
+
+def wav_info(path, head_bytes=1 << 16):
+    """(frames, sample_rate, channels) from the header of a WAV file, without decoding it (folder mode on several
+    GPUs: every rank needs every clip's length for the window plan, but decodes only its own clips)."""
+    path = os.fspath(path)
+    total = os.path.getsize(path)
+    with open(path, "rb") as f:
+        head = f.read(head_bytes)
+    try:
+        fmt, (body, size) = _wav_layout(head, total)
+    except ValueError:
+        if total <= len(head):
+            raise
+        with open(path, "rb") as f:                                # a long chunk list before the data: parse the whole file
+            fmt, (body, size) = _wav_layout(f.read())
+    _, ch, sr, _, bits = fmt
+    width = bits // 8
+    if ch < 1 or width < 1:
+        raise ValueError("bad WAVE header")
+    return size // (width * ch), int(sr), int(ch)
+
+
+def decode_wav(data):
+    """RIFF/WAVE bytes -> (float32 array [channels, frames], sample_rate)."""
+    fmt, payload = _wav_layout(data)
     tag, ch, sr, align, bits = fmt
     body, size = payload
     width = bits // 8
@@ -142,6 +175,37 @@ def segment_files(segmenter, paths, workers=4, group_seconds=1800.0, **segment_k
             group_sr = sr
             seconds += len(audio) / sr
         flush(group, group_sr)
+    for path in paths:
+        pred = per_file[path]
+        table["filename"] += [os.path.basename(path)] * len(pred["onset"])
+        table["onset"] += pred["onset"]
+        table["offset"] += pred["offset"]
+        table["cluster"] += pred["cluster"]
+    return per_file, table
+
+
+def segment_files_sharded(segmenter, paths, workers=4, group=None, generate_fn=None, **segment_kwargs):
+    """`segment_files` under torch.distributed (BASELINE configs[4]: a folder on all GPUs of a box): same
+    (per_file, table) on every rank.  Every rank reads only the WAV *headers* of all files (clip lengths fix the
+    window plan and the shards), decodes just the clips its shard of the flattened window list touches, and the
+    token ids are exchanged with one all-gather per sample-rate group (`distributed.segment_many_sharded`).
+    Files are segmented at their native sample rate, like the reference CLI (`librosa.load(path, sr=None)`)."""
+    from .distributed import LazyClips, segment_many_sharded
+    paths = list(paths)
+    per_file = {}
+    table = {"filename": [], "onset": [], "offset": [], "cluster": []}
+    if not paths:
+        return per_file, table
+    infos = [wav_info(p) for p in paths]
+    by_rate = {}
+    for i, (_, sr, _) in enumerate(infos):
+        by_rate.setdefault(sr, []).append(i)
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
+        for sr, idx in by_rate.items():
+            clips = LazyClips([infos[i][0] for i in idx], lambda k, _idx=idx: load_audio(paths[_idx[k]])[0], pool)
+            preds = segment_many_sharded(segmenter, clips, sr, group=group, generate_fn=generate_fn, **segment_kwargs)
+            for i, pred in zip(idx, preds):
+                per_file[paths[i]] = pred
     for path in paths:
         pred = per_file[path]
         table["filename"] += [os.path.basename(path)] * len(pred["onset"])

@@ -91,6 +91,32 @@ def segment_sharded(segmenter, audio, sr, min_frequency=None, spec_time_step=Non
     return pp.correct_fft_blur_and_dedupe(pred, sr, get_n_fft_given_sr(sr))
 
 
+class LazyClips:
+    """A folder of clips whose lengths are known up front (WAV headers) and whose samples are loaded on demand:
+    `segment_many_sharded` asks for the length of every clip but indexes only the clips of the rank's own shard.
+    `prefetch(range)` starts loading those on a thread pool."""
+
+    def __init__(self, lengths, load, pool=None):
+        self.lengths = [int(n) for n in lengths]
+        self._load, self._pool, self._pending = load, pool, {}
+
+    def __len__(self):
+        return len(self.lengths)
+
+    def prefetch(self, indices):
+        if self._pool is not None:
+            for k in indices:
+                if k not in self._pending:
+                    self._pending[k] = self._pool.submit(self._load, k)
+
+    def __getitem__(self, k):
+        fut = self._pending.pop(k, None)
+        a = fut.result() if fut is not None else self._load(k)
+        if len(a) != self.lengths[k]:
+            raise ValueError("clip %d: %d samples decoded, %d announced by its header" % (k, len(a), self.lengths[k]))
+        return a
+
+
 def folder_window_table(plan, lengths, num_trials):
     """Folder mode: the windows of all clips flattened in clip order.  Returns (per_clip_windows, owner clip of
     every window, [first, last+1) window range of every clip)."""
@@ -111,6 +137,8 @@ def local_folder_buffer(audios, per_clip, owners, lo, hi):
     if hi <= lo:
         return np.zeros(0, dtype=np.float32), np.zeros((0, 3), dtype=np.int64)
     c_lo, c_hi = owners[lo], owners[hi - 1]
+    if hasattr(audios, "prefetch"):
+        audios.prefetch(range(c_lo, c_hi + 1))
     pieces, base_of, base = [], {}, 0
     for ci in range(c_lo, c_hi + 1):
         a = np.ascontiguousarray(np.asarray(audios[ci]), dtype=np.float32)
@@ -160,7 +188,7 @@ def segment_many_sharded(segmenter, audios, sr, min_frequency=None, spec_time_st
     if time_per_frame_for_voting is None:
         time_per_frame_for_voting = spec_time_step
     plan = FrontendPlan(sr, spec_time_step, min_frequency, total_spec_columns=segmenter.total_spec_columns)
-    lengths = [len(a) for a in audios]
+    lengths = list(audios.lengths) if hasattr(audios, "lengths") else [len(a) for a in audios]
     per_clip, owners, spans = folder_window_table(plan, lengths, num_trials)
     if not owners:
         return []
