@@ -4,6 +4,7 @@ reference calls at model.py:609/655 -- and (b) the golden ids/segments produced 
 reference (tests/golden/model_tiny.npz)."""
 import copy
 import json
+import os
 
 import numpy as np
 import pytest
@@ -123,6 +124,24 @@ def test_weight_preparation_layouts(tiny):
     L = cfg["encoder_layers"]
     assert t["dec.crosskv.w"].shape == (2 * L * d, d)
     assert (t["dec.suppress"] == 0).sum().item() == len(synth.allowed_token_ids())
+
+
+@pytest.mark.parametrize("safe", [True, False])
+def test_sharded_checkpoint_layouts_load(tiny, tmp_path, safe):
+    """HF writes checkpoints above max_shard_size as several files + an index (whisper-large in fp32 does by default);
+    the loader must return the same state dict for the single-file and the sharded layout."""
+    from whisperseg_b200.weights import load_checkpoint
+    hf = tiny["hf"]
+    out = str(tmp_path / ("sharded_%s" % safe))
+    hf.save_pretrained(out, max_shard_size="20MB", safe_serialization=safe)
+    names = os.listdir(out)
+    assert any(n.endswith(".index.json") for n in names), names
+    cfg, sd, gen = load_checkpoint(out)
+    ref_cfg, ref_sd, _ = load_checkpoint(tiny["path"])
+    assert cfg["d_model"] == ref_cfg["d_model"] and set(ref_sd) <= set(sd) | {"proj_out.weight"}
+    for k, v in ref_sd.items():
+        if k in sd:
+            assert torch.equal(sd[k], v), k
 
 
 def test_layernorm_fold_matches_hf_modules(tiny):

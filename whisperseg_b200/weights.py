@@ -3,7 +3,7 @@
 Reads the same directory the reference hands to `WhisperForConditionalGeneration.from_pretrained`
 (reference model.py:633-637): `config.json` (+ the WhisperSeg fields `total_spec_columns`,
 `cluster_codebook`, `default_segmentation_config`, model.py:639-644), `model.safetensors` or
-`pytorch_model.bin`, optional `generation_config.json` (suppress_tokens / begin_suppress_tokens).
+`pytorch_model.bin` (single file or HF's sharded `*.index.json` layout), optional `generation_config.json` (suppress_tokens / begin_suppress_tokens).
 
 Prepared tensors handed to wsb_model_create (all on the target device):
   enc.conv1.wt  f32 [240][d]    (ci*3+k major, channel contiguous)     enc.conv1.b f32 [d]
@@ -24,9 +24,18 @@ import torch
 def load_checkpoint(model_path):
     cfg = json.load(open(os.path.join(model_path, "config.json")))
     st = os.path.join(model_path, "model.safetensors")
+    sd = {}
     if os.path.isfile(st):
         from safetensors.torch import load_file
         sd = load_file(st)
+    elif os.path.isfile(st + ".index.json"):            # sharded save (whisper-large in fp32 exceeds HF's 5 GB shard size)
+        from safetensors.torch import load_file
+        for shard in sorted(set(json.load(open(st + ".index.json"))["weight_map"].values())):
+            sd.update(load_file(os.path.join(model_path, shard)))
+    elif os.path.isfile(os.path.join(model_path, "pytorch_model.bin.index.json")):
+        index = json.load(open(os.path.join(model_path, "pytorch_model.bin.index.json")))
+        for shard in sorted(set(index["weight_map"].values())):
+            sd.update(torch.load(os.path.join(model_path, shard), map_location="cpu", weights_only=True))
     else:
         sd = torch.load(os.path.join(model_path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
     gen = {}
