@@ -127,7 +127,10 @@ def _folder_clips(seed, n_clips):
     that its window descriptors point into the right clip."""
     rng = np.random.default_rng(seed)
     secs = rng.uniform(0.3, 27.0, n_clips)
-    secs[1] = 0.05                                       # shorter than one FFT frame
+    if n_clips > 1:
+        secs[1] = 0.05                                   # shorter than one FFT frame
+    else:
+        secs[0] = 3.0                                    # a single one-window clip: rank 1's shard is empty
     return [np.full(int(s_ * SR), i + 1, dtype=np.float32) for i, s_ in enumerate(secs)]
 
 
@@ -169,7 +172,7 @@ def _folder_worker(rank, world, port, seed, n_clips, num_trials, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("seed,n_clips,num_trials", [(1, 9, 1), (2, 5, 3), (3, 2, 1)])
+@pytest.mark.parametrize("seed,n_clips,num_trials", [(1, 9, 1), (2, 5, 3), (3, 2, 1), (4, 1, 1)])
 def test_sharded_folder_world2_gloo(seed, n_clips, num_trials):
     """`segment_many_sharded`: the flattened window list of a ragged folder is cut into contiguous shards (a clip may
     straddle the cut), each rank's local buffer holds only its clips, and after ONE all-gather every rank returns
@@ -186,6 +189,8 @@ def test_sharded_folder_world2_gloo(seed, n_clips, num_trials):
         assert p.exitcode == 0
     exp, owners, _, _ = _expected_folder(_folder_clips(seed, n_clips), num_trials)
     assert len(exp) == n_clips and sum(len(e["onset"]) for e in exp) > 0
+    if n_clips == 1:
+        assert len(owners) == 1 and sorted(g[3] for g in got) == [0, 1]      # one window: one rank idles
     for rank, res, n_seen, n_mine, bad in got:
         assert res == exp, "rank %d result differs from the single-process result" % rank
         assert n_seen == n_mine and bad == 0
