@@ -171,24 +171,27 @@ def consolidate_trials_by_voting(trials, time_per_frame, cluster_codebook):
     n_frames = int(np.round((t_max - t_min) / time_per_frame))
     grid = np.full((len(trials), n_frames), -1, dtype=np.int64)
     for r, tr in enumerate(trials):
-        for on, off, name in zip(tr["onset"], tr["offset"], tr["cluster"]):
-            a = int(np.round((on - t_min) / time_per_frame))
-            b = int(np.round((off - t_min) / time_per_frame))
-            grid[r, a:b] = cluster_codebook[name]
+        # frame bounds of all segments at once (np.round is the same half-to-even rounding on arrays and scalars);
+        # the fill stays sequential: where a trial's segments overlap, the later one wins, as in the reference
+        a = np.round((np.asarray(tr["onset"], dtype=np.float64) - t_min) / time_per_frame).astype(np.int64)
+        b = np.round((np.asarray(tr["offset"], dtype=np.float64) - t_min) / time_per_frame).astype(np.int64)
+        ids = [cluster_codebook[name] for name in tr["cluster"]]
+        row = grid[r]
+        for lo, hi, cid in zip(a.tolist(), b.tolist(), ids):
+            row[lo:hi] = cid
     # per-frame mode, smallest value on ties (scipy.stats.mode semantics)
     values = np.unique(grid)
     counts = np.stack([(grid == v).sum(axis=0) for v in values], axis=0) if n_frames else np.zeros((len(values), 0))
     voted = values[np.argmax(counts, axis=0)] if n_frames else np.zeros(0, dtype=np.int64)
     edges = np.nonzero(np.diff(np.concatenate([[-1], voted, [-1]])) != 0)[0]
     inverse = {v: k for k, v in cluster_codebook.items()}
-    ons, offs, names = [], [], []
-    for a, b in zip(edges[:-1], edges[1:]):
-        cid = int(np.round(np.mean(voted[a:b].astype(np.float64))))
-        if cid == -1:
-            continue
-        ons.append(a * time_per_frame + t_min)
-        offs.append(b * time_per_frame + t_min)
-        names.append(inverse[cid])
+    # a run between two change points is constant, so the reference's round(mean(run)) is the run's value itself
+    run_ids = voted[edges[:-1]] if len(edges) > 1 else np.zeros(0, dtype=np.int64)
+    keep = run_ids != -1
+    starts, stops = edges[:-1][keep], edges[1:][keep]
+    ons = list(starts * time_per_frame + t_min)
+    offs = list(stops * time_per_frame + t_min)
+    names = [inverse[int(c)] for c in run_ids[keep]]
     return {"onset": ons, "offset": offs, "cluster": names}
 
 
