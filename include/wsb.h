@@ -26,6 +26,11 @@ int wsb_abi_version(void);
 const char* wsb_last_error(void);
 /* number of CUDA kernels launched by this library since the last call with reset != 0 */
 long long wsb_launch_count(int reset);
+/* Chunk pipelining (segmenter.py: the encoder of chunk i+1 runs while chunk i decodes; the reference runs them
+ * strictly one after the other, model.py:653-668): the persistent tcgen05 GEMMs launched BY THE CALLING THREAD from
+ * now on occupy at most (#SMs - n_sms) SMs, leaving the rest to the latency-bound decode kernels of other streams.
+ * Returns the previous value; 0 restores full-width launches.                                                    */
+int wsb_set_sm_reserve(int n_sms);
 
 /* ---- K1: log-mel front-end ------------------------------------------------------------------
  * Replaces SegmenterBase.get_sliced_audios_features's per-window feature extraction

@@ -125,6 +125,8 @@ class WhisperOracle:
             h = _ln(x, w[p + "final_layer_norm.weight"], w[p + "final_layer_norm.bias"])
             h = F.gelu(F.linear(h, w[p + "fc1.weight"], w[p + "fc1.bias"]))
             x = x + F.linear(h, w[p + "fc2.weight"], w[p + "fc2.bias"])
+        if return_hidden == "pre":                       # residual stream before the final LayerNorm (recipe tuning)
+            return x
         x = _ln(x, w["model.decoder.layer_norm.weight"], w["model.decoder.layer_norm.bias"])
         if return_hidden:
             return x

@@ -88,6 +88,53 @@ def allowed_token_ids(ts_step=25, n_digits=4):
                   list(range(ID_DIGIT0, ID_DIGIT0 + n_digits)) + [ID_EOT])
 
 
+def round_weights_bf16_(sd):
+    """Make the checkpoint bf16-exact: every tensor the engine multiplies as bf16 (all matrices except conv1, which
+    it keeps in fp32, and the fp32 position tables) is rounded to a bf16-representable fp32 value.  The engine's own
+    conversion is then lossless, so engine-vs-fp32-oracle differences measure the KERNELS' arithmetic, not the
+    weight quantisation (which accounts for half of the bf16-vs-fp32 noise of a random network:
+    tools/noise_floor.py).  The engine's outputs are bit-identical with and without this rounding."""
+    import torch
+    for k, v in sd.items():
+        if v.dim() >= 2 and "embed_positions" not in k and not k.endswith("encoder.conv1.weight"):
+            sd[k] = v.to(torch.float32).to(torch.bfloat16).to(torch.float32)
+    return sd
+
+
+def script_tokens(seed, n_segments, ts_step=25, n_allowed_digits=4):
+    """A seeded, grammar-valid token script `<|on|> cluster <|off|>` x n_segments + EOS with increasing times."""
+    rng = np.random.default_rng(7000 + seed)
+    n_ts = TOTAL_SPEC_COLUMNS // ts_step + 1
+    times = np.sort(rng.choice(n_ts, size=2 * n_segments, replace=False))
+    toks = []
+    for k in range(n_segments):
+        toks += [ID_TS0 + int(times[2 * k]) * ts_step, ID_DIGIT0 + int(rng.integers(0, n_allowed_digits)),
+                 ID_TS0 + int(times[2 * k + 1]) * ts_step]
+    return toks + [ID_EOT]
+
+
+def script_vectors(emb, boost, seed, n_segments, prompt_len=3, ts_step=25, n_allowed_digits=4):
+    """[448, d] term added to the decoder position table of the "confident" recipe: at decoder position p
+    (p >= prompt_len - 1) `boost` along the unit embedding of the scripted NEXT token; after the script, EOS.
+    Like the EOS ramp it rides the residual stream into the tied output projection, where it lifts the scripted
+    token's logit by boost / rms(h) * |E| -- about `boost / rms(h)` standard deviations of the random logits.  The
+    greedy decode then follows the script except where the audio-dependent random part of the logits beats the boost
+    (a tail event whose probability the boost sets): most positions carry a wide top-1/top-2 margin, as a trained
+    segmenter's do, and the remaining ones depend on the audio through the whole encoder/decoder stack."""
+    import torch
+    toks = script_tokens(seed, n_segments, ts_step, n_allowed_digits)
+    out = torch.zeros(448, emb.shape[1], dtype=torch.float32)
+    for p in range(prompt_len - 1, 448):
+        j = min(p - (prompt_len - 1), len(toks) - 1)
+        u = emb[toks[j]].float()
+        out[p] = boost * u / u.norm()
+    return out
+
+
+# "confident" recipe constants: script boost = z * (rms of the final pre-LayerNorm hidden state, measured with the fp32
+# oracle: tiny 4.68, base 5.53, large 13.1), z chosen so that ~1 % of the positions leave the script
+ARCH_SCRIPT_BOOST = {"tiny": 14.0, "base": 16.5, "large": 35.0}
+
 GELU_MEAN = 0.28209479177387814       # E[gelu(h)], h ~ N(0,1)
 DEFAULT_CODEBOOK = {"vocal": 0, "b": 1, "c": 2, "d": 3}
 
@@ -117,6 +164,9 @@ def make_hf_model(arch="tiny", seed=0, shaped=True, cluster_codebook=None,
     if shaped:
         ts_step = shape_kw.pop("ts_step", 25)
         n_allowed_digits = shape_kw.pop("n_allowed_digits", 4)
+        script_boost = shape_kw.pop("script_boost", None)
+        script_segments = shape_kw.pop("script_segments", 8)
+        confident = shape_kw.pop("confident", False)
         shape_weights_(model, seed, **shape_kw)
         allowed = set(allowed_token_ids(ts_step, n_allowed_digits))
         if getattr(model, "_wsb_calibrate", True):
@@ -124,6 +174,13 @@ def make_hf_model(arch="tiny", seed=0, shaped=True, cluster_codebook=None,
             calibrate_output_bias_(sd, H, L, sorted(allowed), seed)
             with torch.no_grad():
                 model.model.decoder.layer_norm.bias.copy_(sd["model.decoder.layer_norm.bias"])
+        if confident and script_boost is None:
+            script_boost = ARCH_SCRIPT_BOOST[arch]
+        if script_boost:
+            with torch.no_grad():
+                model.model.decoder.embed_positions.weight.add_(script_vectors(
+                    model.model.decoder.embed_tokens.weight.detach(), script_boost, seed, script_segments,
+                    ts_step=ts_step, n_allowed_digits=n_allowed_digits))
         sup = [i for i in range(VOCAB_SIZE) if i not in allowed]
         model.generation_config.suppress_tokens = sup
         model.generation_config.begin_suppress_tokens = None
@@ -134,7 +191,7 @@ def make_hf_model(arch="tiny", seed=0, shaped=True, cluster_codebook=None,
 
 def shape_weights_(model, seed, n_digits=2, eos_scale=1.3, qk_cross=3.0, qk_self=2.0, emb_std=0.05,
                    digit_scale=1.0, conv_gain=2.0, bias_std=0.02, cancel_gelu_mean=True,
-                   dec_pos_std=2.0, cross_out_gain=2.0, calibrate=True):
+                   dec_pos_std=2.0, cross_out_gain=2.0, calibrate=True, bf16_exact=True):
     """SURVEY.md section 7.2-1 recipe (constants tuned so rows end with EOS at varied lengths)."""
     import torch
     g = torch.Generator().manual_seed(1000 + seed)
@@ -169,6 +226,10 @@ def shape_weights_(model, seed, n_digits=2, eos_scale=1.3, qk_cross=3.0, qk_self
         emb.copy_(torch.randn(emb.shape, generator=g) * emb_std)
         emb[ID_DIGIT0:ID_DIGIT0 + n_digits] *= digit_scale
         emb[ID_EOT] *= eos_scale
+        if bf16_exact:
+            for name, p in sd.items():
+                if p.dim() >= 2 and "embed_positions" not in name and not name.endswith("encoder.conv1.weight"):
+                    p.copy_(p.to(torch.bfloat16).to(torch.float32))
     model.tie_weights()
     model._wsb_calibrate = calibrate
 
@@ -255,7 +316,7 @@ ARCH_EOS_SCALE = {"tiny": 1.3, "base": 1.3, "small": 1.3, "large": 3.0}
 def make_state(arch="large", seed=0, n_digits=2, eos_scale=None, qk_cross=3.0, qk_self=2.0, emb_std=0.05,
                digit_scale=1.0, conv_gain=2.0, ts_step=25, n_allowed_digits=4, bias_std=0.02,
                cancel_gelu_mean=True, dec_pos_std=2.0, cross_out_gain=2.0, calibrate="auto", dtype=None,
-               eos_ramp=None, eos_ramp_start=10):
+               eos_ramp=None, eos_ramp_start=10, bf16_exact=True, confident=False, script_boost=None, script_segments=8):
     """(config dict, state dict, generation dict) of a shaped random checkpoint -- same recipe as
     shape_weights_, HF parameter names, drawn tensor by tensor from one seeded CPU generator."""
     import torch
@@ -321,6 +382,8 @@ def make_state(arch="large", seed=0, n_digits=2, eos_scale=None, qk_cross=3.0, q
         ln(p + "final_layer_norm")
         mlp(p)
     ln("model.decoder.layer_norm")
+    if bf16_exact:
+        round_weights_bf16_(sd)
     allowed = set(allowed_token_ids(ts_step, n_allowed_digits))
     gen = dict(suppress_tokens=[i for i in range(VOCAB_SIZE) if i not in allowed], begin_suppress_tokens=None)
     # calibrate: "file" = committed vector under tools/calibration/ only (bench.py's GPU arm: no oracle
@@ -336,6 +399,15 @@ def make_state(arch="large", seed=0, n_digits=2, eos_scale=None, qk_cross=3.0, q
             raise FileNotFoundError("no committed calibration vector for (%s, seed %d): %s" % (arch, seed, path))
         else:
             calibrate_output_bias_(sd, H, L, sorted(allowed), seed)
+    if confident:
+        # "confident" recipe: the scripted grammar replaces the EOS ramp (see script_vectors)
+        eos_ramp = 0.0
+        if script_boost is None:
+            script_boost = ARCH_SCRIPT_BOOST[arch]
+    if script_boost:
+        sd["model.decoder.embed_positions.weight"] = sd["model.decoder.embed_positions.weight"] + script_vectors(
+            sd["model.decoder.embed_tokens.weight"], script_boost, seed, script_segments, ts_step=ts_step,
+            n_allowed_digits=n_allowed_digits)
     if eos_ramp is None:
         eos_ramp = ARCH_EOS_RAMP.get(arch, 0.0)
     if eos_ramp:

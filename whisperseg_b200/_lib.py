@@ -26,6 +26,7 @@ EXPORTS = {
     "wsb_abi_version": (ctypes.c_int, []),
     "wsb_last_error": (ctypes.c_char_p, []),
     "wsb_launch_count": (ctypes.c_longlong, [ctypes.c_int]),
+    "wsb_set_sm_reserve": (ctypes.c_int, [ctypes.c_int]),
     "wsb_logmel_plan_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                               ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "wsb_logmel_plan_destroy": (None, [ctypes.c_void_p]),
@@ -74,13 +75,18 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.isfile(LIB_PATH):
+        # (re)build when the sources changed: build() compares a digest of csrc/ + include/ with the stamp next to
+        # the library and is a no-op when they match.  Without nvcc (a deployment box) the shipped .so is used as is.
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        if "WSB_LIB" not in os.environ and (os.path.isfile(nvcc) or not os.path.isfile(LIB_PATH)):
             try:
                 from .build import build
                 build()
             except Exception as e:  # noqa: BLE001
-                raise WsbError("libwsb.so is not built and could not be built here (%s); run "
-                               "`python -m whisperseg_b200.build`" % e) from e
+                if not os.path.isfile(LIB_PATH):
+                    raise WsbError("libwsb.so is not built and could not be built here (%s); run "
+                                   "`python -m whisperseg_b200.build`" % e) from e
+                raise WsbError("libwsb.so is out of date and rebuilding it failed (%s)" % e) from e
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(lib, name)            # AttributeError if the symbol is missing

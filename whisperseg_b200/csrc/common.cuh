@@ -39,6 +39,7 @@ void count_launch(int n = 1);
 // launched with programmaticStreamSerialization so the next kernel's launch + prologue overlaps the tail
 // of the previous one; every such kernel calls pdl_wait() before touching its inputs.
 extern thread_local bool g_use_pdl;
+extern thread_local int g_sm_reserve;     // SMs the persistent GEMMs launched by this thread leave free (wsb_set_sm_reserve)
 
 // Per-device one-time kernel setup (cudaFuncSetAttribute is per device; a process may drive several GPUs
 // from different threads -- reference model.py:169-184 fans out one thread per device).

@@ -27,6 +27,7 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* get_last_error() { return g_last_error.c_str(); }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 thread_local bool g_use_pdl = false;
+thread_local int g_sm_reserve = 0;
 
 // ---------------------------------------------------------------------------- event profiling
 // Optional CUDA-event bracketing of kernel classes on the launching stream (bench.py's roofline
@@ -204,7 +205,7 @@ static int model_layout(Model* m, bool assign) {
     m->dff = carve<__nv_bfloat16>(p, B * F);
     m->dpart_floats = 16 * B * std::max<size_t>(F, 3 * d);
     m->dpart = carve<float>(p, m->dpart_floats);
-    m->gv_stats = carve<float>(p, std::max<size_t>(160 * 64 * 2, static_cast<size_t>(c.d_model / 128 + 1) * B * 2));
+    m->gv_stats = carve<float>(p, std::max<size_t>(256 * 64 * 2, static_cast<size_t>(c.d_model / 128 + 1) * B * 2));
     m->am_val = carve<float>(p, B * m->am_tiles);
     m->am_idx = carve<int>(p, B * m->am_tiles);
     m->tokens = carve<int>(p, B * c.max_target_positions);
@@ -538,7 +539,7 @@ static int decode_layers_fused(const StepCtx& x) {
         ga.M = B;
         ga.N = d;
         ga.K = K;
-        parts = gemv16_parts(d);
+        parts = gemv16_parts(d, K);
         ProfScope ps(PROF_DEC_GEMM, 2.0 * B * d * K, s);
         return gemv16(ga, s);
     };
@@ -1060,6 +1061,11 @@ long long wsb_launch_count(int reset) {
     if (reset) g_launches.store(0);
     return v;
 }
+int wsb_set_sm_reserve(int n_sms) {
+    const int prev = g_sm_reserve;
+    g_sm_reserve = n_sms < 0 ? 0 : n_sms;
+    return prev;
+}
 
 int wsb_logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float* mel_filters, int n_freq,
                            wsb_logmel_plan** plan) {
@@ -1335,14 +1341,14 @@ int wsb_gemv16_bench(int M, int N, int K, int mode, int iters, int weight_copies
     if (mode <= 1) {
         g.x = x;
         g.stats = stats;
-        g.stats_parts = gemv16_parts(K);
+        g.stats_parts = gemv16_parts(K, K);
         g.gamma = gb;
         g.beta = gb + K;
     } else if (mode >= 3) {                             // folded LayerNorm: 3 -> fp32, 4 -> GELU bf16
         g.a = a;
         g.c1 = gb + 2 * K;
         g.stats = stats;
-        g.stats_parts = gemv16_parts(K);
+        g.stats_parts = gemv16_parts(K, K);
     } else {
         g.a = a;
     }

@@ -571,7 +571,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     // super-rows of 16 m-tiles so that B streams from HBM once per super-row instead of once per m-tile
     p.group_m = (static_cast<double>(a.N) * a.K * 2.0 > 64e6 && p.m_tiles > 1) ? 16 : 0;
     const int total = p.m_tiles * p.n_tiles * p.splits;
-    const int grid = std::min(total, num_sms);
+    const int grid = std::min(total, std::max(8, num_sms - g_sm_reserve));
     WSB_CHECK_CUDA(launch_kernel(gemm_kernel<BN, EPI, EPIW>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, tmA, tmB, p));
     count_launch();
     return 0;

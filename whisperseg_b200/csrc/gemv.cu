@@ -29,13 +29,21 @@
 
 namespace wsb {
 
-constexpr int kGvThreads = 512;
+// -DWSB_GV_THREADS=256 builds the two-CTAs-per-SM variant (half the registers and shared memory per CTA, so that under
+// programmatic dependent launch launch i+1 is resident next to launch i).  Measured in round 2 and rejected: the bench
+// decode went from 414 to 464 ms (profiles/r2_decode_gemv_256_vs_512_threads.txt) -- 8 warps keep half as many
+// activation loads in flight and the smaller tiles need more CTAs; 512 threads, one CTA per SM stays the default.
+#ifndef WSB_GV_THREADS
+#define WSB_GV_THREADS 512
+#endif
+constexpr int kGvThreads = WSB_GV_THREADS;
+constexpr int kGvMinBlocks = kGvThreads <= 256 ? 2 : 1;
 constexpr int kGvWarps = kGvThreads / 32;
 constexpr int kGvBatch = 3;             // k-blocks (of 32) per warp whose activation fragments are in flight
 constexpr int kGvMaxNT = 5;
 constexpr int kGvWPad = 64;             // bytes of padding per weight row in smem (row shift = 16 banks)
 constexpr int kGvMaxRows = 64;          // 4 m-tiles of 16 rows
-constexpr int kGvMaxSmem = 220 * 1024;
+constexpr int kGvMaxSmem = (kGvMinBlocks == 2 ? 112 : 220) * 1024;
 
 struct GvParams {
     const float* x;                     // LN input: fp32 [M][K] (IN_LN) ...
@@ -86,7 +94,7 @@ __device__ __forceinline__ uint4 ln_pack8(const float4& v0, const float4& v1, fl
 // k-blocks, the next batch in flight while the current one feeds the MMAs.  m-tiles whose rows are all
 // finished are skipped (no loads, no MMAs), finished rows of a live tile are not loaded.
 template <int IN_LN, int EPI, int NT, int MT>
-__global__ void __launch_bounds__(kGvThreads, 1) gemv16_kernel(const GvParams p) {
+__global__ void __launch_bounds__(kGvThreads, kGvMinBlocks) gemv16_kernel(const GvParams p) {
     constexpr int KS = kGvWarps / MT;                    // warps splitting K inside one m-tile
     constexpr int MP = 16 * MT;                          // padded row count (statistics layout [parts][MP][2])
     extern __shared__ __align__(128) unsigned char gv_smem[];
@@ -355,16 +363,24 @@ int row_stats_any(const float* x, int M, int K, float* stats, __nv_bfloat16* xb,
     return 0;
 }
 
-int gemv16_parts(int N) {                                // CTAs (= partial statistics) of a launch with N outputs
-    const int nt = std::min(kGvMaxNT, std::max(1, ceil_div(ceil_div(N, 8), 148)));
-    return ceil_div(N, 8 * nt);
+static size_t gv_smem_bytes(int nt, int K, int in_ln, int epi, int mt) {
+    return static_cast<size_t>(8 * nt) * (static_cast<size_t>(K) * 2 + kGvWPad) + (in_ln == 1 ? static_cast<size_t>(K) * 8 : 0) +
+           sizeof(float) * kGvWarps * nt * 128 + (epi == 2 ? sizeof(float) * nt * 16 * mt * 8 : 0);
+}
+// n-tiles (of 8 output features) per CTA: about one CTA per SM, fewer features per CTA when the tile would not fit
+static int gv_pick_nt(int N, int K, int in_ln, int epi, int mt) {
+    int nt = std::min(kGvMaxNT, std::max(1, ceil_div(ceil_div(N, 8), 148)));
+    while (nt > 1 && gv_smem_bytes(nt, K, in_ln, epi, mt) > static_cast<size_t>(kGvMaxSmem)) --nt;
+    return nt;
+}
+int gemv16_parts(int N, int K) {                         // CTAs (= partial statistics) of a residual-update launch
+    return ceil_div(N, 8 * gv_pick_nt(N, K, 0, 2, 4));
 }
 int gemv16_max_rows() { return kGvMaxRows; }
 
 template <int IN_LN, int EPI, int NT, int MT>
 static int launch_gemv(const GvParams& p, cudaStream_t stream) {
-    const size_t smem = static_cast<size_t>(8 * NT) * (static_cast<size_t>(p.K) * 2 + kGvWPad) + (IN_LN == 1 ? static_cast<size_t>(p.K) * 8 : 0) +
-                        sizeof(float) * kGvWarps * NT * 128 + (EPI == 2 ? sizeof(float) * NT * 16 * MT * 8 : 0);
+    const size_t smem = gv_smem_bytes(NT, p.K, IN_LN, EPI, MT);
     WSB_REQUIRE(smem <= kGvMaxSmem, "gemv16: weight tile does not fit in shared memory (K too large)");
     static PerDeviceOnce once;
     int dev = 0;
@@ -424,8 +440,10 @@ int gemv16(const Gemv16Args& a, cudaStream_t stream) {
     p.M = a.M;
     p.N = a.N;
     p.K = a.K;
-    const int nt = std::min(kGvMaxNT, std::max(1, ceil_div(ceil_div(a.N, 8), 148)));
     const int epi = a.out_f32 ? 0 : (a.out_bf16_gelu ? 1 : 2);
+    // (the residual-update form sizes its tiles for 64 rows whatever M is: the number of CTAs is the number of
+    // partial row statistics the consumer adds up, gemv16_parts)
+    const int nt = gv_pick_nt(a.N, a.K, a.x ? 1 : (a.c1 ? 2 : 0), epi, epi == 2 ? 4 : (a.M <= 16 ? 1 : (a.M <= 32 ? 2 : 4)));
     if (a.x) {
         if (epi == 0) return dispatch_mt<1, 0>(p, nt, stream);
         if (epi == 1) return dispatch_mt<1, 1>(p, nt, stream);

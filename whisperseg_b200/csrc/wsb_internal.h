@@ -104,7 +104,7 @@ struct Gemv16Args {
 };
 int gemv16(const Gemv16Args& a, cudaStream_t stream);
 int gemv16_max_rows();
-int gemv16_parts(int N);                                 // CTAs (= statistics partials) of a launch with N outputs
+int gemv16_parts(int N, int K);                                 // CTAs (= statistics partials) of a launch with N outputs
 int row_stats16(const float* x, int M, int K, float* stats, cudaStream_t stream,
                 __nv_bfloat16* xb = nullptr);            // exact statistics, 1 part (+ optional bf16 copy of x)
 

@@ -58,7 +58,7 @@ class LogmelRunner:
 class Engine:
     """One model replica on one GPU."""
 
-    def __init__(self, model_path, device="cuda:0", max_batch=64, state=None):
+    def __init__(self, model_path, device="cuda:0", max_batch=64, state=None, tensors=None, stream_priority=0):
         if not torch.cuda.is_available():
             raise _lib.WsbError("whisperseg_b200 needs a CUDA (sm_100) device; there is no CPU path")
         self.lib = _lib.load()
@@ -67,8 +67,10 @@ class Engine:
         self.hf_config = cfg
         self.max_batch = int(max_batch)
         with torch.cuda.device(self.device):
-            self.tensors = prepare_tensors(cfg, sd, gen, self.device)
-            self.stream = torch.cuda.Stream(self.device)
+            # `tensors`: prepared device weights of another Engine on the same device (chunk pipelining: several
+            # contexts -- workspaces, streams, CUDA graphs -- share one copy of the weights)
+            self.tensors = tensors if tensors is not None else prepare_tensors(cfg, sd, gen, self.device)
+            self.stream = torch.cuda.Stream(self.device, priority=stream_priority)
             mc = _lib.ModelConfig(cfg["d_model"], cfg["encoder_attention_heads"], cfg["encoder_layers"],
                                   cfg["encoder_ffn_dim"], cfg["vocab_size"], cfg["num_mel_bins"],
                                   2 * cfg["max_source_positions"], cfg["max_target_positions"], self.max_batch)
