@@ -74,6 +74,11 @@ int wsb_model_create(const wsb_model_config* cfg, const char* const* names, cons
                      int n_tensors, wsb_model** model);
 void wsb_model_destroy(wsb_model* model);
 size_t wsb_model_workspace_bytes(const wsb_model* model);
+/* 1 once the folded-LayerNorm guard has fired for this model: at <= 64 decode rows the LayerNorm is folded into the
+ * projection that consumes it (the kernel multiplies bf16(x), not bf16(LN(x))), which is only as accurate as the
+ * exact form while a row's |mean| stays below ~2 standard deviations; when a live row violates that, the engine
+ * switches this model to the exact on-the-fly LayerNorm for good (HF nn.LayerNorm semantics, modeling_whisper.py:417-506). */
+int wsb_model_fold_fallback(const wsb_model* model);
 
 /* Encoder (conv stem + n_layers pre-LN blocks + final LN); replaces HF WhisperEncoder.forward
  * reached from model.generate (reference model.py:655).  features_dev: float32 [batch][80][n_cols].

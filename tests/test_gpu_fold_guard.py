@@ -1,0 +1,77 @@
+"""Folded LayerNorm (decode at <= 64 rows, csrc/gemv.cu) against a checkpoint built to break it, and its guard.
+
+The fused small-batch linear kernels multiply bf16(x) with weights that have the LayerNorm affine folded in and apply
+rstd (acc - mean c1) + c2 afterwards (HF nn.LayerNorm + nn.Linear, modeling_whisper.py:417-506, algebraically).  That
+rounds x instead of LN(x): the error grows like sqrt(1 + mean^2/var) of the row.  `dec_common_mode` shifts every channel
+of the decoder's residual stream by a constant (|mean| ~ 10-20 std), which an exact LayerNorm removes without trace.
+Expected: the guard notices (|mean| > 2 std on a live row), the engine switches to the exact on-the-fly LayerNorm and
+agrees with the fp32 oracle as well as the exact path does; with the guard disabled the folded path is visibly worse.
+VERDICT r1 weak #2 / ADVICE r1 (engine.cu:699)."""
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _agreement(state, x, mode, monkeypatch, max_length=72):
+    import torch
+    from oracle.whisper_torch import WhisperOracle
+    from tools import synth
+    from whisperseg_b200.segmenter import WhisperSegmenter
+    monkeypatch.delenv("WSB_FOLD_GUARD", raising=False)
+    monkeypatch.delenv("WSB_NO_FOLD", raising=False)
+    if mode == "fold-forced":
+        monkeypatch.setenv("WSB_FOLD_GUARD", "0")
+    elif mode == "exact":
+        monkeypatch.setenv("WSB_NO_FOLD", "1")
+    cfg, sd, gen = state
+    tokdir = tempfile.mkdtemp()
+    synth.token_table_files(tokdir)
+    seg = WhisperSegmenter.from_state(state, tokdir, device="cuda", device_ids=[0], max_batch=16)
+    eng, tok = seg.engines[0], seg.tokenizer
+    orc = WhisperOracle(sd, cfg["encoder_attention_heads"], cfg["encoder_layers"])
+    enc = orc.encode(x)
+    ids, margins = orc.greedy(enc, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length,
+                              suppress_tokens=gen["suppress_tokens"], return_margins=True)
+    B, n_new = ids.shape
+    forced = torch.full((B, max_length), tok.pad_token_id, dtype=torch.int32)
+    forced[:, :3] = torch.tensor(tok.prompt_ids, dtype=torch.int32)
+    forced[:, 3:3 + n_new] = ids.to(torch.int32)
+    eng.encode(x.to(eng.device).contiguous())
+    got, _ = eng.generate(B, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length, forced=forced.to(eng.device),
+                          use_graph=False)
+    got = got.cpu()[:, :n_new].long()
+    valid = torch.ones_like(ids, dtype=torch.bool)
+    for b in range(B):
+        eos = (ids[b] == tok.eos_token_id).nonzero()
+        if len(eos):
+            valid[b, eos[0, 0] + 1:] = False
+    valid[:, :4] = False                         # positions decoded before the guard's second look do not count
+    raw = ((got == ids) & valid).sum().item() / max(1, valid.sum().item())
+    # free-running through the graph path as well: the fallback must survive graph capture
+    eng.encode(x.to(eng.device).contiguous())
+    eng.generate(B, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length)
+    return raw, int(valid.sum()), eng.fold_fallback
+
+
+def test_fold_guard_falls_back_on_common_mode_rows(monkeypatch):
+    import torch
+    from oracle import frontend_np as FO
+    from tools import synth
+    audio = synth.synth_audio(120.0, 16000, seed=41)
+    feats = FO.sliced_audio_features(audio, 16000, 0, 0.01, 1, dtype=np.float32)
+    x = torch.from_numpy(np.asarray([f[2] for f in feats]))
+    plain = synth.make_state("tiny", seed=0)
+    shifted = synth.make_state("tiny", seed=0, dec_common_mode=40.0)
+    raw_plain, n, fb_plain = _agreement(plain, x, "default", monkeypatch)
+    assert not fb_plain, "the guard must stay quiet on rows whose mean is small against their spread"
+    res = {mode: _agreement(shifted, x, mode, monkeypatch) for mode in ("default", "fold-forced", "exact")}
+    print("common-mode checkpoint, teacher-forced raw agreement over %d positions: guarded %.4f (fallback fired: %s), "
+          "folded forced %.4f, exact LayerNorm %.4f; unshifted checkpoint %.4f" %
+          (res["default"][1], res["default"][0], res["default"][2], res["fold-forced"][0], res["exact"][0], raw_plain))
+    assert res["default"][2], "the guard did not fire on |mean| >> std rows"
+    assert not res["fold-forced"][2] and not res["exact"][2]
+    assert res["default"][0] >= res["exact"][0] - 0.01
+    assert res["default"][0] >= res["fold-forced"][0]

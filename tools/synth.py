@@ -316,7 +316,8 @@ ARCH_EOS_SCALE = {"tiny": 1.3, "base": 1.3, "small": 1.3, "large": 3.0}
 def make_state(arch="large", seed=0, n_digits=2, eos_scale=None, qk_cross=3.0, qk_self=2.0, emb_std=0.05,
                digit_scale=1.0, conv_gain=2.0, ts_step=25, n_allowed_digits=4, bias_std=0.02,
                cancel_gelu_mean=True, dec_pos_std=2.0, cross_out_gain=2.0, calibrate="auto", dtype=None,
-               eos_ramp=None, eos_ramp_start=10, bf16_exact=True, confident=False, script_boost=None, script_segments=8):
+               eos_ramp=None, eos_ramp_start=10, bf16_exact=True, confident=False, script_boost=None, script_segments=8,
+               dec_common_mode=0.0):
     """(config dict, state dict, generation dict) of a shaped random checkpoint -- same recipe as
     shape_weights_, HF parameter names, drawn tensor by tensor from one seeded CPU generator."""
     import torch
@@ -408,6 +409,11 @@ def make_state(arch="large", seed=0, n_digits=2, eos_scale=None, qk_cross=3.0, q
         sd["model.decoder.embed_positions.weight"] = sd["model.decoder.embed_positions.weight"] + script_vectors(
             sd["model.decoder.embed_tokens.weight"], script_boost, seed, script_segments, ts_step=ts_step,
             n_allowed_digits=n_allowed_digits)
+    if dec_common_mode:
+        # a constant added to every channel of the decoder's residual stream: LayerNorm removes it exactly, but it makes
+        # |mean| >> std for every row -- the regime in which a LayerNorm folded into the next projection (csrc/gemv.cu)
+        # loses precision.  Parity case for the engine's fold guard (tests/test_gpu_fold_guard.py).
+        sd["model.decoder.embed_positions.weight"] = sd["model.decoder.embed_positions.weight"] + float(dec_common_mode)
     if eos_ramp is None:
         eos_ramp = ARCH_EOS_RAMP.get(arch, 0.0)
     if eos_ramp:

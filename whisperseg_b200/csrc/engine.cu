@@ -147,6 +147,8 @@ struct Model {
     bool use_cluster = false;           // 65..256 decode rows: cluster split-K linear layers with folded LayerNorm (skinny.cu);
                                         // opt-in (WSB_CLUSTER=1): parity-green, but measured 0-4 % slower than the split-K pair
     bool use_fold = true;               // ... with the LayerNorm folded into the projection when the folded tensors exist
+    bool fold_guard = true;             // fall back to the exact LayerNorm when a row's common mode dominates (WSB_FOLD_GUARD=0: off)
+    bool fold_disabled = false;         // sticky: the guard fired once for this model
     int gemv_rows = 64;                 // ... used up to this many rows (WSB_GEMV_ROWS, <= 64)
     std::vector<int> ladder{64, 32, 16};   // compaction levels, descending, all <= kCompactRows (override: WSB_LADDER=64,16)
     int* pinned_active = nullptr;
@@ -521,6 +523,7 @@ static int decode_layers_fused(const StepCtx& x) {
         ga.out_f32 = out_f32;
         ga.out_bf16_gelu = out_gelu;
         ga.row_skip = fin;
+        ga.fold_flag = (fold && m->fold_guard) ? m->n_active + 1 : nullptr;
         ga.M = B;
         ga.N = N;
         ga.K = d;
@@ -760,7 +763,11 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     m->use_pdl = (flags & 2) != 0;                      // bit1: programmatic dependent launch (GEMM weight tiles and gemv weight rows
                                                         // are fetched before the dependency wait)
     m->use_gemv = (flags & 8) == 0;                     // bit3: keep the tcgen05 split-K path for small batches too
-    m->use_fold = std::getenv("WSB_NO_FOLD") == nullptr;
+    {
+        const char* g = std::getenv("WSB_FOLD_GUARD");
+        m->fold_guard = !(g && g[0] == '0');
+    }
+    m->use_fold = std::getenv("WSB_NO_FOLD") == nullptr && !(m->fold_guard && m->fold_disabled);
     m->use_cluster = std::getenv("WSB_CLUSTER") != nullptr;
     if (const char* e = std::getenv("WSB_GEMV_ROWS")) m->gemv_rows = std::max(0, std::min(64, std::atoi(e)));
     if (const char* e = std::getenv("WSB_LADDER")) {
@@ -801,6 +808,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     }
     WSB_CHECK_CUDA(cudaMemsetAsync(m->step, 0, sizeof(int) * 4, s));
     WSB_CHECK_CUDA(cudaMemsetAsync(m->finished, 0, B, s));
+    WSB_CHECK_CUDA(cudaMemsetAsync(m->n_active, 0, sizeof(int) * 4, s));       // [0] live rows, [1] folded-LayerNorm guard flag
     WSB_CHECK_CUDA(cudaMemcpyAsync(m->n_active, &B, sizeof(int), cudaMemcpyHostToDevice, s));
     WSB_CHECK_CUDA(cudaStreamSynchronize(s));              // init_tok / B are stack/host temporaries
     {   // pad everything: rows that never get written (early stop) must read as pad
@@ -819,6 +827,15 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     st.row_map = nullptr;
     for (int pos = 0; pos + 1 < prompt_len; ++pos)
         WSB_RUN(decode_step(m, st, false, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
+    if (m->use_fold && m->fold_guard && m->use_gemv && B <= m->gemv_rows && prompt_len > 1) {
+        // folded-LayerNorm guard, first look: the prompt positions have run on the folded path
+        WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active, m->n_active, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+        WSB_CHECK_CUDA(cudaStreamSynchronize(s));
+        if (m->pinned_active[1] != 0) {
+            m->fold_disabled = true;
+            m->use_fold = false;
+        }
+    }
     // first generated token (begin-suppress mask active)
     WSB_RUN(decode_step(m, st, true, true, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
     int steps_done = 1;
@@ -827,7 +844,8 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     const bool allow_compaction = (flags & 4) == 0 && forced == nullptr;
     Model::GraphEntry* graph = nullptr;
     auto get_graph = [&](const DecState& cur, Model::GraphEntry** out) -> int {
-        const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 32 * m->gemv_rows + (m->use_fold ? 4096 : 0) : 16) + (m->use_cluster ? 8192 : 0), cur.row_map != nullptr ? 1 : 0, max_new,
+        const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 32 * m->gemv_rows + (m->use_fold ? 4096 : 0) : 16) + (m->use_cluster ? 8192 : 0) +
+                                                    (m->use_pdl ? 16384 : 0) + (m->use_fold && m->fold_guard ? 32768 : 0), cur.row_map != nullptr ? 1 : 0, max_new,
                                          prompt_len, eos_id, pad_id);
         auto it = m->graphs.find(key);
         if (it == m->graphs.end()) {
@@ -861,9 +879,16 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
             WSB_RUN(decode_step(m, st, true, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
         }
         ++steps_done;
-        if (!forced && (steps_done % check_every) == 0 && steps_done < max_new) {
-            WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active, m->n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+        if ((steps_done % check_every) == 0 && steps_done < max_new) {
+            WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active, m->n_active, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
             WSB_CHECK_CUDA(cudaStreamSynchronize(s));
+            if (m->pinned_active[1] != 0 && m->use_fold && m->fold_guard) {
+                // folded-LayerNorm guard: some live row's mean dominates its spread -> exact LayerNorm from here on
+                m->fold_disabled = true;
+                m->use_fold = false;
+                if (use_graph) WSB_RUN(get_graph(st, &graph));
+            }
+            if (forced) continue;
             const int active = m->pinned_active[0];
             if (active <= 0) break;
             // batch compaction ladder: every move goes to the other buffer set (main <-> alternate); the target is
@@ -931,6 +956,11 @@ static int generate_beam(Model* m, int B, int nb, const int* prompt, int prompt_
     const int d = c.d_model, L = c.n_layers, T = m->T, rows = B * T;
     const int max_new = max_length - prompt_len;
     m->use_pdl = false;
+    {
+        const char* g = std::getenv("WSB_FOLD_GUARD");
+        m->fold_guard = !(g && g[0] == '0');
+    }
+    m->use_fold = std::getenv("WSB_NO_FOLD") == nullptr && !(m->fold_guard && m->fold_disabled);
     if (!m->beam_ws) {
         m->beam_ldv = (c.vocab_size + 7) & ~7;
         const size_t logits_bytes = (static_cast<size_t>(c.max_batch) * m->beam_ldv * sizeof(float) + 255) & ~size_t(255);
@@ -972,6 +1002,7 @@ static int generate_beam(Model* m, int B, int nb, const int* prompt, int prompt_
     bs.n_active = m->n_active;
     WSB_CHECK_CUDA(cudaMemcpyAsync(m->prompt_dev, prompt, sizeof(int) * prompt_len, cudaMemcpyHostToDevice, s));
     WSB_CHECK_CUDA(cudaMemsetAsync(m->step, 0, sizeof(int) * 4, s));
+    WSB_CHECK_CUDA(cudaMemsetAsync(m->n_active, 0, sizeof(int) * 4, s));
     WSB_CHECK_CUDA(cudaMemcpyAsync(m->n_active, &B, sizeof(int), cudaMemcpyHostToDevice, s));
     WSB_RUN(beam_set_length_penalty(bs, length_penalty, max_length, s));      // synchronises: prompt / B are temporaries
     WSB_RUN(beam_init(bs, m->prompt_dev, s));
@@ -993,12 +1024,10 @@ static int generate_beam(Model* m, int B, int nb, const int* prompt, int prompt_
     int steps_done = 1;
     const bool use_graph = (flags & 1) != 0 && max_new > 2;
     Model::GraphEntry* graph = nullptr;
-    if (use_graph) {
-        int lp_bits;
-        static_assert(sizeof(int) == sizeof(float), "float bits");
-        memcpy(&lp_bits, &length_penalty, sizeof(int));
-        (void)lp_bits;                                      // the penalty lives in a device table, not in the launches
-        const auto key = std::make_tuple(B, nb, max_length, prompt_len, eos_id, pad_id, 0);
+    // (the length penalty lives in a device table, not in the launches)
+    auto get_graph = [&](Model::GraphEntry** out) -> int {
+        const auto key = std::make_tuple(B, nb, max_length, prompt_len, eos_id, pad_id,
+                                         (m->use_fold ? 1 : 0) | (m->use_gemv ? 2 : 0) | (m->fold_guard ? 4 : 0) | (m->gemv_rows << 3));
         auto it = m->beam_graphs.find(key);
         if (it == m->beam_graphs.end()) {
             cudaGraph_t g = nullptr;
@@ -1018,8 +1047,10 @@ static int generate_beam(Model* m, int B, int nb, const int* prompt, int prompt_
             cudaGraphDestroy(g);
             it = m->beam_graphs.emplace(key, entry).first;
         }
-        graph = &it->second;
-    }
+        *out = &it->second;
+        return 0;
+    };
+    if (use_graph) WSB_RUN(get_graph(&graph));
     const int check_every = 4;
     while (steps_done < max_new) {
         if (use_graph) {
@@ -1030,9 +1061,14 @@ static int generate_beam(Model* m, int B, int nb, const int* prompt, int prompt_
         }
         ++steps_done;
         if ((steps_done % check_every) == 0 && steps_done < max_new) {
-            WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active, m->n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+            WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active, m->n_active, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
             WSB_CHECK_CUDA(cudaStreamSynchronize(s));
             if (m->pinned_active[0] <= 0) break;
+            if (m->pinned_active[1] != 0 && m->use_fold && m->fold_guard) {   // folded-LayerNorm guard (see generate)
+                m->fold_disabled = true;
+                m->use_fold = false;
+                if (use_graph) WSB_RUN(get_graph(&graph));
+            }
         }
     }
     WSB_RUN(beam_output(bs, tokens_out, scores_out, max_new, s));
@@ -1102,6 +1138,7 @@ void wsb_model_destroy(wsb_model* model) {
     model_destroy(model->impl);
     delete model;
 }
+int wsb_model_fold_fallback(const wsb_model* model) { return (model && model->impl && model->impl->fold_disabled) ? 1 : 0; }
 size_t wsb_model_workspace_bytes(const wsb_model* model) { return model ? model->impl->ws_bytes : 0; }
 
 int wsb_encode(wsb_model* model, const float* features_dev, int batch, float* hidden_f32_dev, void* stream) {

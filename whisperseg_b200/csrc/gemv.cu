@@ -62,6 +62,7 @@ struct GvParams {
     float* stats_out;                   // EPI 2: [gridDim.x][MP][2] partial row statistics of the updated rows
     __nv_bfloat16* xb_out;              // EPI 2, optional: bf16 copy of the updated rows (input of a folded-LayerNorm consumer)
     const unsigned char* row_skip;      // [M] or null: rows not stored
+    int* fold_flag;                     // IN_LN 2, optional: set to 1 when a live row has |mean| > 2 std (folded-LayerNorm guard)
     int M, N, K;
 };
 
@@ -208,6 +209,14 @@ __global__ void __launch_bounds__(kGvThreads, kGvMinBlocks) gemv16_kernel(const 
                 const float var = fmaxf(sq / p.K - mean * mean, 0.0f);
                 s_mean[r] = mean;
                 s_rstd[r] = rsqrtf(var + 1e-5f);
+                if constexpr (IN_LN == 2) {
+                    // Folded LayerNorm rounds x, not LN(x), to bf16: its error relative to the exact path grows like
+                    // sqrt(1 + mean^2 / var).  A row whose common mode dominates its spread raises the flag and the
+                    // engine falls back to the exact on-the-fly LayerNorm (engine.cu: fold guard).
+                    if (p.fold_flag != nullptr && blockIdx.x == 0 && r < p.M && !(p.row_skip && p.row_skip[r]) &&
+                        mean * mean > 4.0f * var)
+                        *p.fold_flag = 1;
+                }
             }
         }
         __syncthreads();                                 // also publishes gam_s / bet_s
@@ -437,6 +446,7 @@ int gemv16(const Gemv16Args& a, cudaStream_t stream) {
     p.resid = a.resid;
     p.stats_out = a.stats_out;
     p.row_skip = a.row_skip;
+    p.fold_flag = a.fold_flag;
     p.M = a.M;
     p.N = a.N;
     p.K = a.K;

@@ -100,6 +100,7 @@ struct Gemv16Args {
     __nv_bfloat16* out_bf16_gelu = nullptr;
     float* resid = nullptr;
     const unsigned char* row_skip = nullptr;
+    int* fold_flag = nullptr;            // folded LayerNorm guard: set to 1 when a live row has |mean| > 2 std
     int M = 0, N = 0, K = 0;
 };
 int gemv16(const Gemv16Args& a, cudaStream_t stream);

@@ -1,12 +1,15 @@
-"""Multi-GPU: one process per GPU (torchrun), windows sharded by index, one small all-gather.
+"""Multi-GPU: one process per GPU (torchrun), windows sharded by index, one small all-gather of segment lists.
 
 The reference fans windows out to one Python *thread* per GPU inside a single process and
 concatenates the per-thread text lists (reference model.py:169-189); there is no collective.
 Here every rank computes the same window plan, takes a contiguous shard of the window list
 (the reference's `ceil(n / n_devices)` split, model.py:172-173), uploads only the samples its
-windows touch, runs front-end + encoder + decode locally, and the generated token ids are
-exchanged with ONE all-gather of a padded int32 [windows_per_rank, max_new] tensor (NCCL over
-NVLink on GPUs, gloo in the CPU tests).  Post-processing then runs identically on every rank.
+windows touch, runs front-end + encoder + decode locally, decodes ITS OWN token rows to text and
+extracts their `<|on|>id<|off|>` triples (postprocess.extract_table), and the ranks exchange those
+segment tables with ONE all-gather of a fixed-size float64 buffer (NCCL over NVLink on GPUs, gloo in
+the CPU tests).  Only the cheap second half of the post-processing (stitching across window
+boundaries, trial consolidation: postprocess.parse_table) runs on every rank.  (Round 1 gathered
+the padded token ids and every rank decoded and parsed ALL windows: 8x redundant host work at N=8.)
 `segment_many_sharded` does the same for folder mode: the windows of all clips, flattened in clip order, are
 sharded, and the gathered token ids are regrouped per clip.
 """
@@ -34,6 +37,45 @@ def all_gather_tokens(local_ids, per, max_new, pad_id, group=None):
     out = torch.empty((world * per, max_new), dtype=torch.int32, device=local_ids.device)
     dist.all_gather_into_tensor(out, buf, group=group)
     return out
+
+
+def all_gather_tables(table, per, max_new, device, group=None):
+    """table = (counts, onset, offset, cluster_id) of this rank's windows (postprocess.extract_table).  ONE all-gather
+    of a float64 buffer [1 + per + 3 * cap] per rank -- n_segments | counts (padded to `per` windows) | onsets |
+    offsets | cluster ids, cap = per * (max_new // 3) being the most triples `per` windows can hold.  Returns the
+    table of all windows in rank order (the caller trims each rank's counts to its real shard length)."""
+    world = dist.get_world_size(group)
+    counts, on, off, cid = table
+    cap = max(1, per * max(1, max_new // 3))
+    n = len(on)
+    assert n <= cap and len(counts) <= per
+    buf = np.zeros(1 + per + 3 * cap, dtype=np.float64)
+    buf[0] = n
+    buf[1:1 + len(counts)] = counts
+    base = 1 + per
+    buf[base:base + n] = on
+    buf[base + cap:base + cap + n] = off
+    buf[base + 2 * cap:base + 2 * cap + n] = cid
+    send = torch.from_numpy(buf).to(device)
+    out = torch.empty((world, buf.shape[0]), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out.view(-1), send, group=group)
+    rows = out.cpu().numpy()
+    tables = []
+    for r in range(world):
+        k = int(rows[r, 0])
+        tables.append((rows[r, 1:1 + per].astype(np.int32), rows[r, base:base + k].copy(), rows[r, base + cap:base + cap + k].copy(),
+                       rows[r, base + 2 * cap:base + 2 * cap + k].astype(np.int32)))
+    return tables
+
+
+def _merge_tables(tables, n_items, world):
+    """Per-rank tables -> one table over all `n_items` windows (each rank's counts trimmed to its shard length)."""
+    counts = []
+    for r, t in enumerate(tables):
+        a, b, _ = shard_bounds(n_items, world, r)
+        counts.append(t[0][:b - a])
+    return (np.concatenate(counts) if counts else np.zeros(0, np.int32), np.concatenate([t[1] for t in tables]),
+            np.concatenate([t[2] for t in tables]), np.concatenate([t[3] for t in tables]))
 
 
 def local_slice(audio, windows, clip_len):
@@ -79,15 +121,11 @@ def segment_sharded(segmenter, audio, sr, min_frequency=None, spec_time_step=Non
         local_ids = _engine_generate(segmenter, plan, mine, piece, s0, len(audio), max_length, num_beams, length_penalty)
     else:
         local_ids = generate_fn(mine, plan, piece, s0)
-    gathered = all_gather_tokens(local_ids, per, max_new, tok.pad_token_id, group)
-    rows = gathered.cpu().numpy()
-    texts = []
-    for r in range(world):
-        a, b, _ = shard_bounds(len(wins), world, r)
-        texts += tok.batch_decode(rows[r * per:r * per + (b - a)])
-    pred = pp.parse_generation(texts, [w.as_tuple() for w in wins], min_segment_length, len(audio) / sr, spec_time_step,
-                               num_trials, eps, time_per_frame_for_voting, consolidation_method,
-                               segmenter.cluster_codebook, segmenter.precision_bits)
+    texts = tok.batch_decode(local_ids.cpu().numpy()) if len(mine) else []
+    table = pp.extract_table(texts, [w.as_tuple() for w in mine], spec_time_step, segmenter.cluster_codebook)
+    counts, on, off, cid = _merge_tables(all_gather_tables(table, per, max_new, local_ids.device, group), len(wins), world)
+    pred = pp.parse_table(counts, on, off, cid, [w.trial_id for w in wins], min_segment_length, len(audio) / sr, num_trials, eps,
+                          time_per_frame_for_voting, consolidation_method, segmenter.cluster_codebook, segmenter.precision_bits)
     return pp.correct_fft_blur_and_dedupe(pred, sr, get_n_fft_given_sr(sr))
 
 
@@ -200,18 +238,18 @@ def segment_many_sharded(segmenter, audios, sr, min_frequency=None, spec_time_st
         local_ids = _engine_generate_folder(segmenter, plan, piece, descs, max_length, num_beams, length_penalty)
     else:
         local_ids = generate_fn(lo, descs, plan, piece)
-    gathered = all_gather_tokens(local_ids, per, max_new, tok.pad_token_id, group)
-    rows = gathered.cpu().numpy()
-    texts = []
-    for r in range(world):
-        a, b, _ = shard_bounds(len(owners), world, r)
-        texts += tok.batch_decode(rows[r * per:r * per + (b - a)])
+    flat = [w for wins in per_clip for w in wins]
+    texts = tok.batch_decode(local_ids.cpu().numpy()) if hi > lo else []
+    table = pp.extract_table(texts, [w.as_tuple() for w in flat[lo:hi]], spec_time_step, segmenter.cluster_codebook)
+    counts, on, off, cid = _merge_tables(all_gather_tables(table, per, max_new, local_ids.device, group), len(owners), world)
+    seg_start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     n_fft = get_n_fft_given_sr(sr)
     results = []
     for ci, (a, b) in enumerate(spans):
-        pred = pp.parse_generation(texts[a:b], [w.as_tuple() for w in per_clip[ci]], min_segment_length, lengths[ci] / sr,
-                                   spec_time_step, num_trials, eps, time_per_frame_for_voting, consolidation_method,
-                                   segmenter.cluster_codebook, segmenter.precision_bits)
+        s0, s1 = int(seg_start[a]), int(seg_start[b])
+        pred = pp.parse_table(counts[a:b], on[s0:s1], off[s0:s1], cid[s0:s1], [w.trial_id for w in per_clip[ci]],
+                              min_segment_length, lengths[ci] / sr, num_trials, eps, time_per_frame_for_voting,
+                              consolidation_method, segmenter.cluster_codebook, segmenter.precision_bits)
         results.append(pp.correct_fft_blur_and_dedupe(pred, sr, n_fft))
     return results
 

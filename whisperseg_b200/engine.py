@@ -91,6 +91,11 @@ class Engine:
     def workspace_bytes(self):
         return int(self.lib.wsb_model_workspace_bytes(self.handle))
 
+    @property
+    def fold_fallback(self):
+        """True once the folded-LayerNorm guard switched this replica to the exact LayerNorm (csrc/engine.cu)."""
+        return bool(self.lib.wsb_model_fold_fallback(self.handle))
+
     def _enter(self):
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
 

@@ -195,36 +195,91 @@ def consolidate_trials_by_voting(trials, time_per_frame, cluster_codebook):
     return {"onset": ons, "offset": offs, "cluster": names}
 
 
-def parse_generation(texts, windows, min_segment_length, audio_duration, spec_time_step, num_trials, eps,
-                     time_per_frame_for_voting, consolidation_method, cluster_codebook, precision_bits=3):
-    """model.py:210-281.  `windows[i]` = (trial_id, offset_time, ...) in generation order."""
+def extract_table(texts, windows, spec_time_step, cluster_codebook):
+    """First half of model.py:210-232 for a run of windows: every window's text -> its `<|on|>id<|off|>` triples with
+    the window's offset_time added (float64, `int * sts * 2` then `+ offset_time`, the reference's order).
+    Returns (counts int32 [n_windows], onset f64 [n], offset f64 [n], cluster_id int32 [n]) -- plain arrays, so that a
+    rank can compute the table of its own shard of windows and ranks exchange tables instead of token ids
+    (distributed.py); `parse_table` finishes the job."""
     inverse = {v: k for k, v in cluster_codebook.items()}
-    by_trial = {}
-    for text, win in zip(texts, windows):
-        trial_id, offset_time = win[0], win[1]
-        segs = segments_from_text(text, spec_time_step, inverse)
-        for s in segs:
-            s[0] += offset_time
-            s[1] += offset_time
-        by_trial.setdefault(trial_id, []).append(segs)
+    counts = np.zeros(len(texts), dtype=np.int32)
+    ons, offs, cids = [], [], []
+    for i, (text, win) in enumerate(zip(texts, windows)):
+        offset_time = win[1]
+        n = 0
+        for on_s, cid_s, off_s in _SEGMENT_RE.findall(text):
+            on = int(on_s) * spec_time_step * RATIO_DECODING_TIME_STEP_TO_SPEC_TIME_STEP
+            off = int(off_s) * spec_time_step * RATIO_DECODING_TIME_STEP_TO_SPEC_TIME_STEP
+            cid = int(cid_s)
+            if cid not in inverse or off - on <= 0:
+                continue
+            ons.append(on + offset_time)
+            offs.append(off + offset_time)
+            cids.append(cid)
+            n += 1
+        counts[i] = n
+    return counts, np.asarray(ons, dtype=np.float64), np.asarray(offs, dtype=np.float64), np.asarray(cids, dtype=np.int32)
+
+
+def _stitch_clip_filter(on, off, cid, first, audio_duration, min_segment_length):
+    """One trial, vectorised (model.py:235-258).  `first[i]`: segment i opens its window.  The reference fuses a
+    window's first segment into the last accumulated one when `prev offset == onset` and the clusters agree; the
+    accumulated segment's offset is then the fused segment's own offset, so the test only ever involves raw
+    neighbours and a chain of fusions is a run of flags."""
+    n = len(on)
+    if n == 0:
+        return on, off, cid
+    fuse = np.zeros(n, dtype=bool)
+    fuse[1:] = first[1:] & (off[:-1] == on[1:]) & (cid[:-1] == cid[1:])
+    heads = np.flatnonzero(~fuse)
+    last = np.concatenate([heads[1:], [n]]) - 1
+    on, off, cid = on[heads], off[last], cid[heads]
+    on = np.where(on <= 0, 0.0, on)                      # max(0, onset)
+    off = np.minimum(off, audio_duration)                # min(offset, audio_duration)
+    order = np.argsort(on, kind="stable")                # sorted(..., key=onset) is stable
+    on, off, cid = on[order], off[order], cid[order]
+    keep = off - on >= min_segment_length
+    return on[keep], off[keep], cid[keep]
+
+
+def parse_table(counts, on, off, cid, trial_ids, min_segment_length, audio_duration, num_trials, eps,
+                time_per_frame_for_voting, consolidation_method, cluster_codebook, precision_bits=3):
+    """Second half of model.py:210-281 on the table of ALL windows (generation order): per-trial stitching across
+    window boundaries, clipping, sorting, minimum length, trial consolidation, rounding."""
+    inverse = {v: k for k, v in cluster_codebook.items()}
+    counts = np.asarray(counts, dtype=np.int64)
+    trial_ids = np.asarray(trial_ids)
+    seg_trial = np.repeat(trial_ids, counts)
+    first = np.zeros(len(on), dtype=bool)
+    starts = np.cumsum(counts) - counts
+    first[starts[counts > 0]] = True
+    seen = []
+    for t in trial_ids.tolist():                         # trials in order of first appearance (dict insertion order)
+        if t not in seen:
+            seen.append(t)
     trials = []
-    for per_window in by_trial.values():
-        segs = _stitch_trial(per_window)
-        for s in segs:
-            s[0] = max(0, s[0])
-            s[1] = min(s[1], audio_duration)
-        segs.sort(key=lambda s: s[0])
-        segs = [s for s in segs if s[1] - s[0] >= min_segment_length]
-        trials.append({"onset": [s[0] for s in segs], "offset": [s[1] for s in segs], "cluster": [s[2] for s in segs]})
+    for t in seen:
+        sel = seg_trial == t
+        a, b, c = _stitch_clip_filter(on[sel], off[sel], cid[sel], first[sel], audio_duration, min_segment_length)
+        trials.append({"onset": a.tolist(), "offset": b.tolist(), "cluster": [inverse[k] for k in c.tolist()]})
     if num_trials == 1:
-        final = trials[0]
+        final = trials[0] if trials else {"onset": [], "offset": [], "cluster": []}
     elif consolidation_method == "clustering":
         final = consolidate_trials_by_clustering(trials, eps, max(2, int(ceil(num_trials * 0.5))))
     else:
         final = consolidate_trials_by_voting(trials, time_per_frame_for_voting, cluster_codebook)
-    final["onset"] = [float(np.round(t, precision_bits)) for t in final["onset"]]
-    final["offset"] = [float(np.round(t, precision_bits)) for t in final["offset"]]
+    # np.round rounds arrays and scalars alike (x * 1000 -> rint -> / 1000); one call instead of one per segment
+    final["onset"] = np.round(np.asarray(final["onset"], dtype=np.float64), precision_bits).tolist()
+    final["offset"] = np.round(np.asarray(final["offset"], dtype=np.float64), precision_bits).tolist()
     return final
+
+
+def parse_generation(texts, windows, min_segment_length, audio_duration, spec_time_step, num_trials, eps,
+                     time_per_frame_for_voting, consolidation_method, cluster_codebook, precision_bits=3):
+    """model.py:210-281.  `windows[i]` = (trial_id, offset_time, ...) in generation order."""
+    counts, on, off, cid = extract_table(texts, windows, spec_time_step, cluster_codebook)
+    return parse_table(counts, on, off, cid, [w[0] for w in windows][:len(texts)], min_segment_length, audio_duration,
+                       num_trials, eps, time_per_frame_for_voting, consolidation_method, cluster_codebook, precision_bits)
 
 
 def correct_fft_blur_and_dedupe(prediction, sr, n_fft):
