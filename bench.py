@@ -33,15 +33,31 @@ sys.path.insert(0, ROOT)
 SR, STS, MIN_FREQ = 48000, 0.0025, 0
 SECONDS_PER_GPU = 600.0
 PROMPT_LEN = 3
-# Decode positions the REFERENCE executes per generate() call on this workload: it decodes batch_size=4
-# windows together (segment() default, reference model.py:407) until the longest row emits EOS or hits
-# max_length.  Measured with this seed/recipe on the GPU path (bench JSON key
-# decode_row_lengths.mean_positions_per_batch_of_4, identical tokens by construction): 50.3 (the whole
-# 240-window batch runs 136 positions, its longest row).  The GPU arm's cpu_baseline leg uses the value
-# it has just measured; `--impl reference` (no GPU pass) uses this constant.
-REF_POSITIONS_PER_BATCH4 = {"large": 50.3}
 CATS = ["conv1", "enc_gemm", "enc_attn", "enc_ln", "crosskv_gemm", "dec_gemm", "dec_logits", "dec_self_attn",
-        "dec_cross_attn", "dec_ln", "misc"]
+        "dec_cross_attn", "dec_ln", "misc", "dec_graph", "dec_compact"]
+# `ncu --set full` summaries (tools/ncu_summary.py) of one representative launch of the roofline kernel class (the qkv
+# projection: exactly the class-average FLOPs per launch), newest first: roofline.traffic is read from the first that exists
+NCU_TRAFFIC_FILES = ["profiles/r2_ncu_full_gemm_qkv.txt", "profiles/r1b_ncu_full_gemm_qkv.txt", "profiles/r1_ncu_full_gemm_qkv2.txt"]
+
+
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the cited capture (MB in the summary files)."""
+    for rel in NCU_TRAFFIC_FILES:
+        path = os.path.join(ROOT, rel)
+        if not os.path.isfile(path):
+            continue
+        vals = {}
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 2 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[0] not in vals:
+                try:
+                    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(f[2] if len(f) > 2 else "Mbyte", 1e6)
+                    vals[f[0]] = float(f[1]) * scale
+                except ValueError:
+                    pass
+        if len(vals) == 2:
+            return sum(vals.values()), rel
+    return None, None
 
 
 def peaks():
@@ -110,67 +126,142 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_sample(state, arch, max_length, n_windows=2, decode_steps=12, threads=None, positions=None):
-    """Oracle port of the reference path (front-end -> HF-equivalent fp32 Whisper -> greedy) on the host
-    cores.  Measures front-end and encoder on `n_windows` windows and `decode_steps` greedy steps, and
-    scales the decode to the full budget (the per-step cost is constant: weight streaming)."""
+def cpu_reference_sample(state, arch, max_length, n_windows=4, threads=None, **_ignored):
+    """The reference path on the host cores, ONE WHOLE reference batch: segment()'s default batch_size=4 windows
+    (reference model.py:407) through front-end -> fp32 Whisper encoder -> greedy decode until the longest of the four
+    rows emits EOS (or max_length) -- every position is executed and timed, nothing is extrapolated inside the sample.
+    kind "reference": the unmodified /root/reference WhisperSegmenterForEval (container only, oracle/ref_shim.py);
+    kind "port": the oracle restatement (oracle/frontend_np.py + oracle/whisper_torch.py), which is what exists on the
+    GPU box."""
     import torch
-    from oracle import frontend_np as FO
     from tools import synth
-    from oracle.whisper_torch import WhisperOracle
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     cfg, sd, gen = state
     audio = make_audio(n_windows * 1000 * STS, SR, seed=2)
+    audio_s = n_windows * 1000 * STS
+    real = None
+    if os.environ.get("WSB_BENCH_REAL_REFERENCE", "1") != "0":
+        try:
+            real = _real_reference_segmenter(state)
+        except Exception:  # noqa: BLE001
+            real = None
+    if real is not None:
+        t0 = time.perf_counter()
+        real.segment(audio, SR, min_frequency=MIN_FREQ, spec_time_step=STS, num_trials=1, num_beams=1, batch_size=n_windows,
+                     max_length=max_length)
+        total = time.perf_counter() - t0
+        return dict(value=audio_s / total, unit="audio-s/s", cores=threads, kind="reference", seconds=total,
+                    sample="%d windows = one reference batch (%s arch) through the unmodified reference's "
+                           "WhisperSegmenterForEval.segment (num_beams=1, max_length=%d): %.2f s" %
+                           (n_windows, arch, max_length, total))
+    from oracle import frontend_np as FO
+    from oracle import postprocess_ref as PR
+    from oracle.whisper_torch import WhisperOracle
+    from whisperseg_b200.frontend import get_n_fft_given_sr
+    orc = _oracle_cache.get(id(sd))
+    if orc is None:
+        orc = _oracle_cache[id(sd)] = WhisperOracle(sd, cfg["encoder_attention_heads"], cfg["encoder_layers"])
     t0 = time.perf_counter()
     feats = FO.sliced_audio_features(audio, SR, MIN_FREQ, STS, 1, dtype=np.float32)
     t_front = time.perf_counter() - t0
-    orc = WhisperOracle(sd, cfg["encoder_attention_heads"], cfg["encoder_layers"])
     x = torch.from_numpy(np.asarray([f[2] for f in feats]))
     t0 = time.perf_counter()
     enc = orc.encode(x)
     t_enc = time.perf_counter() - t0
     t0 = time.perf_counter()
-    orc.greedy(enc, [synth.ID_SOT, synth.ID_EN, synth.ID_NOTIMESTAMPS], -1, synth.ID_EOT, PROMPT_LEN + decode_steps,
-               suppress_tokens=gen["suppress_tokens"])
-    t_dec = time.perf_counter() - t0                     # includes cross-K/V and the 3 prompt positions
-    n = len(feats)
-    per_step = t_dec / (decode_steps + PROMPT_LEN - 1)
-    if positions is None:
-        positions = REF_POSITIONS_PER_BATCH4.get(arch, float(max_length - PROMPT_LEN)) if max_length == 448 else float(max_length - PROMPT_LEN)
-    total = t_front + t_enc + per_step * (positions + PROMPT_LEN - 1)
-    audio_s = n * 1000 * STS
-    return dict(value=audio_s / total, unit="audio-s/s", cores=threads, kind="port",
-                sample="%d windows = one reference batch (%s arch): front-end %.2fs + encoder %.2fs measured, %d greedy "
-                       "steps measured (%.3fs/step at batch %d) and scaled to the %.0f decode positions the reference "
-                       "runs per batch of 4 on this workload (max_length=%d)" %
-                       (n, arch, t_front, t_enc, decode_steps, per_step, n, positions, max_length),
-                frontend_s=t_front, encoder_s=t_enc, decode_s_per_step=per_step)
+    ids = orc.greedy(enc, [synth.ID_SOT, synth.ID_EN, synth.ID_NOTIMESTAMPS], synth.ID_EOT, synth.ID_EOT, max_length,
+                     suppress_tokens=gen["suppress_tokens"])
+    t_dec = time.perf_counter() - t0                     # cross-K/V + the prompt positions + every generated position
+    t0 = time.perf_counter()
+    tok = _token_table()
+    texts = tok.batch_decode(ids.numpy())
+    PR.segment_from_texts(texts, [(f[0], f[1], None, f[3]) for f in feats], len(audio), SR, STS, cfg["cluster_codebook"],
+                          get_n_fft_given_sr(SR))
+    t_post = time.perf_counter() - t0
+    total = t_front + t_enc + t_dec + t_post
+    return dict(value=audio_s / total, unit="audio-s/s", cores=threads, kind="port", seconds=total,
+                sample="%d windows = one WHOLE reference batch (%s arch, oracle port, fp32, %d threads): front-end %.2f s + "
+                       "encoder %.2f s + cross-K/V and %d greedy positions %.2f s (decoded until the longest row ended, "
+                       "max_length=%d) + post-processing %.3f s; throughput = %.1f audio-s / %.2f s" %
+                       (len(feats), arch, threads, t_front, t_enc, ids.shape[1] + PROMPT_LEN - 1, t_dec, max_length, t_post,
+                        audio_s, total),
+                frontend_s=t_front, encoder_s=t_enc, decode_s=t_dec, positions=int(ids.shape[1]))
+
+
+_oracle_cache = {}
+_tok_cache = []
+
+
+def _token_table():
+    if not _tok_cache:
+        from tools import synth
+        from whisperseg_b200.tokens import TokenTable
+        d = tempfile.mkdtemp(prefix="wsb_tok_")
+        synth.token_table_files(d)
+        _tok_cache.append(TokenTable.from_pretrained(d))
+    return _tok_cache[0]
+
+
+_real_cache = {}
+
+
+def _real_reference_segmenter(state):
+    """The unmodified reference class over an HF model holding the same weights (only where /root/reference exists)."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        return None
+    key = id(state[1])
+    if key in _real_cache:
+        return _real_cache[key]
+    import torch
+    from tools import synth
+    from transformers import WhisperConfig, WhisperForConditionalGeneration
+    ref_model, _ = ref_shim.import_reference()
+    cfg, sd, gen = state
+    hf_cfg = WhisperConfig(**{k: v for k, v in cfg.items() if k not in ("model_type",)})
+    with torch.device("meta"):
+        hf = WhisperForConditionalGeneration(hf_cfg)
+    hf = hf.to_empty(device="cpu")
+    full = dict(sd)
+    full["proj_out.weight"] = sd["model.decoder.embed_tokens.weight"]
+    hf.load_state_dict({k: v.float() for k, v in full.items()}, strict=False)
+    hf.tie_weights()
+    hf.eval()
+    hf.generation_config.suppress_tokens = gen["suppress_tokens"]
+    hf.generation_config.begin_suppress_tokens = None
+    hf.config.suppress_tokens = gen["suppress_tokens"]
+    hf.config.begin_suppress_tokens = None
+    seg = ref_model.WhisperSegmenterForEval(model=ref_shim.GenerateAdapter(hf), tokenizer=synth.build_tokenizer())
+    _real_cache[key] = seg
+    return seg
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port; /root/reference does not exist on the
-    GPU box and the reference is pure Python + third-party transformers)."""
+    """--impl reference: the reference's CPU path on the box's host cores, all threads, one whole reference batch per
+    step (see cpu_reference_sample); `value` = sample audio-seconds / measured step time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from tools import synth
     state = synth.make_state(args.arch, seed=0)
-    vals = []
+    secs = []
     last = None
     for i in range(args.warmup + args.steps):
-        r = cpu_reference_sample(state, args.arch, args.max_length, n_windows=args.ref_windows,
-                                 decode_steps=args.ref_decode_steps)
+        r = cpu_reference_sample(state, args.arch, args.max_length, n_windows=args.ref_windows)
         if i >= args.warmup:
-            vals.append(r["value"])
+            secs.append(r["seconds"])
         last = r
-    v = float(np.mean(vals))
+    sample_audio_s = args.ref_windows * 1000 * STS
+    step_s = float(np.mean(secs))
+    v = sample_audio_s / step_s
     n_win = int(SECONDS_PER_GPU / (1000 * STS))
+    cfg = workload_config(args, n_win)
+    cfg["reference_step"] = "%d windows (%.1f audio-s) of the workload per step, measured in full" % (args.ref_windows, sample_audio_s)
     line = dict(metric="audio-sec/sec", value=v, unit="audio-s/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1000.0 * SECONDS_PER_GPU / v, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic", impl="reference",
-                config=workload_config(args, n_win),
-                cpu_baseline=dict(value=v, unit="audio-s/s", cores=last["cores"], kind="port", sample=last["sample"]),
+                ms_per_step=1000.0 * step_s, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference", config=cfg,
+                cpu_baseline=dict(value=v, unit="audio-s/s", cores=last["cores"], kind=last["kind"], sample=last["sample"]),
                 e2e=dict(value=v, unit="audio-s/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
 
@@ -333,11 +424,12 @@ def run_ours(args):
                                    launches=dg_cnt, algorithmic_bytes_per_launch=dec_weight_bytes / (6 * L),
                                    note="weight streaming at batch %d" % n_win)
     shares = {k: v[0] for k, v in prof.items() if v[1]}
-    # DRAM traffic of one representative launch of the class (the qkv projection: exactly the class-average
-    # FLOPs per launch) from `ncu --set full`: profiles/r1_ncu_full_gemm_qkv2.txt (read 318 MB + write 876 MB;
-    # algorithmic: A 307 MB + W 10 MB + C 922 MB)
+    shares["logmel"] = lm_ms * args.steps
+    # DRAM traffic of one representative launch of the class (the qkv projection: exactly the class-average FLOPs per
+    # launch; algorithmic: A 307 MB + W 10 MB + C 922 MB) read from the committed `ncu --set full` summary
+    traffic, traffic_src = ncu_traffic_bytes() if args.arch == "large" else (None, None)
     roofline = dict(bound="tensor", achieved=roof["achieved"], peak=roof["peak"], unit="TFLOP/s", frac=roof["frac"],
-                    traffic=1.194e9 if args.arch == "large" else None, kernel="gemm_kernel<BN> (encoder GEMM class: conv2, qkv, out-proj, fc1, fc2)",
+                    traffic=traffic, traffic_source=traffic_src, kernel="gemm_kernel<BN> (encoder GEMM class: conv2, qkv, out-proj, fc1, fc2)",
                     ms_per_launch=roof["ms_per_launch"], launches=roof["launches"],
                     algorithmic_flops_per_launch=roof["algorithmic_flops_per_launch"],
                     peak_source="%s cuBLAS bf16, sustained figure (kernel timed inside a long step)" % pk["source"])
@@ -418,6 +510,20 @@ def run_ours(args):
         beam_ms = float(tb.item())
     h2d = len(piece) * 4 + n_win * 24
     d2h = n_win * max_new * 4
+    # ---- the decode phase as a whole (graph replays are bracketed as one class): algorithmic HBM bytes = the decoder
+    # weights once per position + the cross-attention K/V blocks of every LIVE row at every position it runs
+    ids_rank = (ids[rank * n_win:(rank + 1) * n_win] if world > 1 else ids).cpu().numpy()
+    live_positions = float(((ids_rank != tok.eos_token_id).sum(axis=1) + 1 + (PROMPT_LEN - 1)).clip(max=max_new + PROMPT_LEN - 1).sum())
+    cross_bytes_per_row = 2.0 * L * 2 * H * eng.T * 64
+    n_positions = float(np.mean(steps_done)) + PROMPT_LEN - 1
+    dec_bytes = dec_weight_bytes * n_positions + cross_bytes_per_row * live_positions
+    dec_ms = sum(prof[k][0] for k in ("dec_gemm", "dec_logits", "dec_self_attn", "dec_cross_attn", "dec_ln", "dec_graph", "dec_compact")) / args.steps
+    if dec_ms > 0:
+        kernels["decode_phase"] = dict(bound="hbm", achieved=dec_bytes / dec_ms / 1e6, peak=pk["hbm"], unit="GB/s",
+                                       frac=dec_bytes / dec_ms / 1e6 / pk["hbm"], ms_per_step=dec_ms, positions=n_positions,
+                                       live_row_positions=live_positions, algorithmic_bytes_per_step=dec_bytes,
+                                       note="all decoder positions of a step (eager prompt positions + CUDA-graph replays + "
+                                            "compaction); bytes = decoder weights x positions + cross-K/V x live row-positions")
 
     ids_host = (ids[rank * n_win:(rank + 1) * n_win] if world > 1 else ids).cpu().numpy()
     row_len = (ids_host != tok.eos_token_id).sum(axis=1)
@@ -426,7 +532,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_reference_sample(state, args.arch, args.max_length, n_windows=args.ref_windows,
-                                       decode_steps=args.ref_decode_steps, positions=per_batch4)
+                                       )
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = dict(metric="audio-sec/sec", value=value, unit="audio-s/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=dt_ms / args.steps, higher_is_better=True, scaling="weak",
@@ -450,6 +556,105 @@ def run_ours(args):
                                             mean_positions_per_batch_of_4=per_batch4),
                     step_share_ms={k: v / args.steps for k, v in shares.items()})
         emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The other BASELINE.json configurations, end to end through the public API with HOST audio (python bench.py
+# --config cfg3|cfg4|cfg5 [--gpus N]); the default (cfg2) above is what the driver runs.
+CONFIGS = {
+    # name: (description, sr, sts, seconds, seed, num_trials, segment kwargs)
+    "cfg3": ("configs[2]: zebra-finch parameters, 600 s synthetic 32 kHz audio, spec_time_step 0.0025, num_trials=3 "
+             "(multi-trial consolidation by clustering included)", 32000, 0.0025, 600.0, 3, 3, dict(eps=0.02, min_segment_length=0.01)),
+    "cfg4": ("configs[3]: 1 h synthetic 16 kHz human-VAD-like audio, spec_time_step 0.01, windows sharded across the ranks, "
+             "one all-gather of segment tables", 16000, 0.01, 3600.0, 4, 1, dict(min_segment_length=0.1)),
+    "cfg5": ("configs[4]: folder mode, variable-length clips U(0.5, 30) s at 32 kHz, spec_time_step 0.0025, windows of all "
+             "clips flattened into shared batches and sharded across the ranks", 32000, 0.0025, 600.0, 5, 1, dict()),
+}
+
+
+def run_config(args):
+    import torch
+    import torch.distributed as dist
+    from tools import synth
+    from whisperseg_b200 import _lib
+    from whisperseg_b200.distributed import LazyClips, segment_many_sharded, segment_sharded
+    from whisperseg_b200.frontend import FrontendPlan
+    from whisperseg_b200.segmenter import WhisperSegmenter
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    desc, sr, sts, seconds, seed, num_trials, kw = CONFIGS[args.config]
+    state = synth.make_state(args.arch, seed=0, calibrate="file" if args.arch == "large" else "auto")
+    tokdir = tempfile.mkdtemp(prefix="wsb_tok_")
+    synth.token_table_files(tokdir)
+    seg = WhisperSegmenter.from_state(state, tokdir, device="cuda", device_ids=[local_rank], max_batch=args.max_batch)
+    base = make_audio(seconds, sr, seed=seed)
+    plan = FrontendPlan(sr, sts, MIN_FREQ)
+    common = dict(min_frequency=MIN_FREQ, spec_time_step=sts, max_length=args.max_length, num_trials=num_trials, num_beams=1, **kw)
+    if args.config == "cfg5":
+        rng = np.random.default_rng(seed)
+        durations = rng.uniform(0.5, 30.0, size=args.clips)
+        lengths = (durations * sr).astype(np.int64)
+        offsets = rng.integers(0, len(base) - lengths.max() - 1, size=args.clips)
+        load = lambda k: np.ascontiguousarray(base[offsets[k]:offsets[k] + lengths[k]])      # noqa: E731
+        audio_seconds = float(lengths.sum()) / sr
+        n_windows = int(sum(len(plan.windows(int(n), num_trials)) for n in lengths))
+
+        def step():
+            if world > 1:
+                return segment_many_sharded(seg, LazyClips(lengths, load), sr, **common)
+            return seg.segment_many([load(k) for k in range(args.clips)], sr, **common)
+    else:
+        audio_seconds = seconds
+        n_windows = len(plan.windows(len(base), num_trials))
+
+        def step():
+            if world > 1:
+                return segment_sharded(seg, base, sr, **common)
+            return seg.segment(base, sr, **common)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        res = step()
+    barrier()
+    lib.wsb_launch_count(1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step()
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    n_seg = sum(len(r["onset"]) for r in res) if isinstance(res, list) else len(res["onset"])
+    if rank == 0:
+        value = audio_seconds * args.steps / dt
+        emit(dict(metric="audio-sec/sec", value=value, unit="audio-s/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                  ms_per_step=1000.0 * dt / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
+                  data="synthetic", config=dict(workload=desc, config=args.config, arch=args.arch, windows=n_windows,
+                                                audio_seconds=audio_seconds, max_length=args.max_length, max_batch=args.max_batch,
+                                                clips=args.clips if args.config == "cfg5" else None,
+                                                weights="seeded shaped random-init (stress recipe)",
+                                                timing="wall clock around synchronised public-API calls, host audio in, segments out"),
+                  e2e=dict(value=value, unit="audio-s/s", h2d_bytes_per_step=int(audio_seconds * sr * 4 / world),
+                           d2h_bytes_per_step=int(n_windows * (args.max_length - PROMPT_LEN) * 4 / world), segments=n_seg),
+                  gpu_launches=int(lib.wsb_launch_count(0)), clocks=clocks))
     if world > 1:
         dist.destroy_process_group()
 
@@ -481,12 +686,16 @@ def main():
     ap.add_argument("--arch", default="large")
     ap.add_argument("--max-length", type=int, default=448, dest="max_length")
     ap.add_argument("--ref-windows", type=int, default=4, dest="ref_windows")
-    ap.add_argument("--ref-decode-steps", type=int, default=12, dest="ref_decode_steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-beam", action="store_true", dest="no_beam")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--clips", type=int, default=10000, help="cfg5: number of clips in the folder")
+    ap.add_argument("--max-batch", type=int, default=240, dest="max_batch")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "cfg2":
+        run_config(args)
     else:
         run_ours(args)
 

@@ -74,6 +74,9 @@ int wsb_model_create(const wsb_model_config* cfg, const char* const* names, cons
                      int n_tensors, wsb_model** model);
 void wsb_model_destroy(wsb_model* model);
 size_t wsb_model_workspace_bytes(const wsb_model* model);
+/* Workspace a model of this configuration would allocate (no device needed): lets the host pick max_batch from the
+ * free device memory when the caller -- e.g. the reference's unchanged scripts/segment.py -- does not give one. */
+size_t wsb_workspace_bytes_for(const wsb_model_config* cfg);
 /* 1 once the folded-LayerNorm guard has fired for this model: at <= 64 decode rows the LayerNorm is folded into the
  * projection that consumes it (the kernel multiplies bf16(x), not bf16(LN(x))), which is only as accurate as the
  * exact form while a row's |mean| stays below ~2 standard deviations; when a live row violates that, the engine
@@ -124,7 +127,8 @@ int wsb_beam_selftest(int batch, int num_beams, int vocab, int n_steps, const fl
  * While enabled, every eagerly launched kernel is bracketed by CUDA events on its own stream.
  * categories: 0 conv1, 1 encoder GEMMs (conv2, qkv, out, fc1, fc2), 2 encoder attention,
  * 3 encoder LayerNorm, 4 cross-K/V GEMM, 5 decoder GEMMs, 6 logits+arg-max GEMM, 7 decode
- * self-attention, 8 decode cross-attention, 9 decoder LayerNorm, 10 misc.
+ * self-attention, 8 decode cross-attention, 9 decoder LayerNorm, 10 misc, 11 CUDA-graph replays of a whole decoder
+ * position (bracketed as one unit: `work` counts positions), 12 batch compaction.
  * wsb_profile_read: call after synchronising the stream; `work` = accumulated algorithmic FLOPs
  * (GEMMs, attention) or bytes (LayerNorm, decode cross-attention) of the bracketed launches.      */
 int wsb_profile_enable(int enable);

@@ -137,6 +137,38 @@ def test_segment_end_to_end(setup, golden_dir):
     print("free-running segments vs reference: TP %d pred %d ref %d F1 %.3f" % (tp, n_pred, n_lab, f1))
 
 
+def test_segments_match_unmodified_reference_on_confident_checkpoint(tmp_path, golden_dir):
+    """North-star bar against the REFERENCE ITSELF: tests/golden/model_tiny_confident.npz holds what the unmodified
+    /root/reference WhisperSegmenterForEval.segment returned (oracle/gen_golden.py, HF fp32 on the CPU) for a seeded
+    tiny checkpoint of the "confident" recipe; the same checkpoint directory through this repo's WhisperSegmenter on the
+    GPU must give segment-level F1 >= 0.99 with onsets/offsets within one spec_time_step (reference scorer,
+    model.py:493-516), for num_trials=1 and for the 3-trial consolidated output, and the same generated ids."""
+    from oracle import postprocess_ref as PR
+    from tools import synth
+    from whisperseg_b200.segmenter import WhisperSegmenter
+    hf = synth.make_hf_model("tiny", seed=0, confident=True, default_segmentation_config=dict(
+        sr=16000, min_frequency=0, spec_time_step=0.01, species="human"))
+    path = synth.save_checkpoint(hf, str(tmp_path / "ckpt"))
+    seg = WhisperSegmenter(path, device="cuda", device_ids=[0], max_batch=8)
+    g = np.load(golden_dir + "/model_tiny_confident.npz")
+    audio = synth.synth_audio(47.0, 16000, seed=11)
+    for key, trials in (("segments", 1), ("segments_trials3", 3)):
+        gold = json.loads(bytes(g[key]).decode())
+        res = seg.segment(audio, 16000, num_trials=trials, num_beams=1, batch_size=8, max_length=96)
+        tp, n_pred, n_lab, p, r, f1 = PR.segment_score(res, gold, tolerance=0.01)
+        print("confident tiny checkpoint, num_trials=%d: vs unmodified reference TP %d pred %d ref %d F1 %.4f" % (trials, tp, n_pred, n_lab, f1))
+        if trials == 1:
+            assert n_lab >= 20 and f1 >= 0.99
+        else:                      # the scripted segments sit at window-relative times, so shifted trials never agree: both empty
+            assert res == gold or f1 >= 0.99
+    sliced = seg.get_sliced_audios_features(audio, 16000, 0, 0.01, 1)
+    texts = seg.generate_segment_text(sliced, 8, 96, 1)
+    ref_texts = json.loads(bytes(g["texts"]).decode())
+    same = sum(a == b for a, b in zip(texts, ref_texts))
+    print("generated texts identical to the reference's for %d / %d windows" % (same, len(ref_texts)))
+    assert same >= len(ref_texts) - 1
+
+
 def test_segment_multi_trial_and_empty(setup):
     seg, audio = setup["seg"], setup["audio"]
     res = seg.segment(audio[:16000 * 12], 16000, num_trials=3, num_beams=1, max_length=48)

@@ -34,7 +34,7 @@ thread_local int g_sm_reserve = 0;
 // numbers).  Only eager launches are bracketed (never inside a graph capture).
 enum ProfCat : int {
     PROF_CONV1 = 0, PROF_ENC_GEMM, PROF_ENC_ATTN, PROF_ENC_LN, PROF_CROSSKV_GEMM, PROF_DEC_GEMM, PROF_DEC_LOGITS,
-    PROF_DEC_SELF_ATTN, PROF_DEC_CROSS_ATTN, PROF_DEC_LN, PROF_DEC_MISC, PROF_NCAT
+    PROF_DEC_SELF_ATTN, PROF_DEC_CROSS_ATTN, PROF_DEC_LN, PROF_DEC_MISC, PROF_DEC_GRAPH, PROF_DEC_COMPACT, PROF_NCAT
 };
 struct ProfRec {
     cudaEvent_t a, b;
@@ -873,6 +873,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     const int check_every = 4;
     while (steps_done < max_new) {
         if (use_graph) {
+            ProfScope ps(PROF_DEC_GRAPH, 1.0, s);           // one replayed decoder position (all its kernels) per bracket
             WSB_CHECK_CUDA(cudaGraphLaunch(graph->exec, s));
             count_launch(graph->kernels);
         } else {
@@ -931,7 +932,10 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
                 ca.n_layers = L;
                 ca.t_max = c.max_target_positions;
                 ca.cross_row_elems = static_cast<long long>(L) * 2 * c.n_heads * T * 64;
-                WSB_RUN(compact_decode_state(ca, s));
+                {
+                    ProfScope ps(PROF_DEC_COMPACT, 1.0, s);
+                    WSB_RUN(compact_decode_state(ca, s));
+                }
                 st = nx;
                 if (use_graph) WSB_RUN(get_graph(st, &graph));
             }
@@ -1054,6 +1058,7 @@ static int generate_beam(Model* m, int B, int nb, const int* prompt, int prompt_
     const int check_every = 4;
     while (steps_done < max_new) {
         if (use_graph) {
+            ProfScope ps(PROF_DEC_GRAPH, 1.0, s);
             WSB_CHECK_CUDA(cudaGraphLaunch(graph->exec, s));
             count_launch(graph->kernels);
         } else {
@@ -1137,6 +1142,15 @@ void wsb_model_destroy(wsb_model* model) {
     if (!model) return;
     model_destroy(model->impl);
     delete model;
+}
+size_t wsb_workspace_bytes_for(const wsb_model_config* cfg) {
+    if (!cfg || cfg->max_batch < 1) return 0;
+    Model m;
+    m.cfg = *cfg;
+    m.T = cfg->n_cols / 2;
+    m.am_tiles = gemm_n_tiles(cfg->vocab_size, 32);        // upper bound: every vocabulary tile of the narrowest block
+    model_layout(&m, false);
+    return m.ws_bytes;
 }
 int wsb_model_fold_fallback(const wsb_model* model) { return (model && model->impl && model->impl->fold_disabled) ? 1 : 0; }
 size_t wsb_model_workspace_bytes(const wsb_model* model) { return model ? model->impl->ws_bytes : 0; }

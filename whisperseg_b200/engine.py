@@ -55,6 +55,24 @@ class LogmelRunner:
             pass
 
 
+def _model_config(cfg, max_batch):
+    return _lib.ModelConfig(cfg["d_model"], cfg["encoder_attention_heads"], cfg["encoder_layers"], cfg["encoder_ffn_dim"],
+                            cfg["vocab_size"], cfg["num_mel_bins"], 2 * cfg["max_source_positions"], cfg["max_target_positions"],
+                            int(max_batch))
+
+
+def auto_max_batch(cfg, device, lib, limit=240, weights_resident=False):
+    """Largest batch of windows (<= `limit`) whose workspace fits in 80 % of the device's free memory after the
+    weights: an unchanged scripts/segment.py passes no max_batch and must still get the wide-batch configuration."""
+    free, _ = torch.cuda.mem_get_info(device)
+    n_params = 2 * cfg["encoder_layers"] * 12 * cfg["d_model"] ** 2 + cfg["vocab_size"] * cfg["d_model"]
+    budget = 0.8 * free - (0 if weights_resident else 4.5 * n_params)     # bf16 weights + folded copies + fp32 bits
+    for b in (limit, 192, 160, 128, 96, 64, 48, 32, 16, 8, 4, 2, 1):
+        if b <= limit and lib.wsb_workspace_bytes_for(ctypes.byref(_model_config(cfg, b))) <= budget:
+            return b
+    raise _lib.WsbError("not enough free device memory for a single window's workspace")
+
+
 class Engine:
     """One model replica on one GPU."""
 
@@ -65,15 +83,13 @@ class Engine:
         self.device = torch.device(device)
         cfg, sd, gen = state if state is not None else load_checkpoint(model_path)
         self.hf_config = cfg
-        self.max_batch = int(max_batch)
+        self.max_batch = int(max_batch) if max_batch else auto_max_batch(cfg, self.device, self.lib, weights_resident=tensors is not None)
         with torch.cuda.device(self.device):
             # `tensors`: prepared device weights of another Engine on the same device (chunk pipelining: several
             # contexts -- workspaces, streams, CUDA graphs -- share one copy of the weights)
             self.tensors = tensors if tensors is not None else prepare_tensors(cfg, sd, gen, self.device)
             self.stream = torch.cuda.Stream(self.device, priority=stream_priority)
-            mc = _lib.ModelConfig(cfg["d_model"], cfg["encoder_attention_heads"], cfg["encoder_layers"],
-                                  cfg["encoder_ffn_dim"], cfg["vocab_size"], cfg["num_mel_bins"],
-                                  2 * cfg["max_source_positions"], cfg["max_target_positions"], self.max_batch)
+            mc = _model_config(cfg, self.max_batch)
             names = list(self.tensors.keys())
             c_names = (ctypes.c_char_p * len(names))(*[n.encode() for n in names])
             c_ptrs = (ctypes.c_void_p * len(names))(*[self.tensors[n].data_ptr() for n in names])

@@ -20,8 +20,8 @@ Design differences (B200-first):
 """
 import json
 import os
+import tempfile
 import threading
-import warnings
 
 import numpy as np
 import torch
@@ -32,7 +32,34 @@ from .frontend import FrontendPlan, get_n_fft_given_sr
 from .tokens import TokenTable
 from .weights import load_checkpoint
 
-_warned_beams = False
+DEFAULT_MAX_BATCH = 240       # windows decoded together when the caller does not say (shrunk to what fits in free HBM)
+
+
+def resolve_model_path(model_path):
+    """A local checkpoint directory, or a Hugging Face hub id resolved the way the reference's download_model does
+    (reference model.py:37-56: snapshot_download into the local cache).  Accepts the CTranslate2 repo layout
+    (`<path>/hf_model/` holds the HF config + tokenizer + weights, model.py:694-702)."""
+    path = str(model_path)
+    if not os.path.isdir(path):
+        try:
+            from huggingface_hub import snapshot_download
+            path = snapshot_download(path, cache_dir=os.environ.get("WHISPERSEG_MODEL_CACHE"))
+        except Exception as e:  # noqa: BLE001
+            raise FileNotFoundError(
+                "model_path %r is neither a local directory nor a Hugging Face hub id that could be resolved here (%s: %s). "
+                "Offline: download the checkpoint once (huggingface_hub.snapshot_download) and pass the directory."
+                % (model_path, type(e).__name__, e)) from e
+    hf_dir = os.path.join(path, "hf_model")
+    has_weights = any(os.path.isfile(os.path.join(path, f)) for f in
+                      ("model.safetensors", "model.safetensors.index.json", "pytorch_model.bin", "pytorch_model.bin.index.json"))
+    if os.path.isdir(hf_dir) and not has_weights:
+        if not any(os.path.isfile(os.path.join(hf_dir, f)) for f in ("model.safetensors", "model.safetensors.index.json",
+                                                                      "pytorch_model.bin", "pytorch_model.bin.index.json")):
+            raise FileNotFoundError(
+                "%s is a CTranslate2 export (model.bin): its hf_model/ folder holds config and tokenizer but no HF weights. "
+                "whisperseg_b200 loads the HF checkpoint (e.g. nccratliri/whisperseg-large-ms, not the -ct2 repo)." % path)
+        return hf_dir
+    return path
 
 
 class SegmenterBase:
@@ -53,8 +80,7 @@ class SegmenterBase:
         if device == "cpu" or not torch.cuda.is_available():
             raise RuntimeError("whisperseg_b200 has no CPU path: a CUDA sm_100 (B200) device is required")
         if state is None:
-            hf_dir = os.path.join(model_path, "hf_model")
-            ckpt_dir = hf_dir if os.path.isdir(hf_dir) and not os.path.isfile(os.path.join(model_path, "config.json")) else model_path
+            ckpt_dir = resolve_model_path(model_path)
             state = load_checkpoint(ckpt_dir)
             tokenizer_dir = ckpt_dir
         else:
@@ -69,6 +95,7 @@ class SegmenterBase:
         self.tokenizer = TokenTable.from_pretrained(tokenizer_dir)
         self.device_list = [torch.device("cuda", int(g)) for g in device_ids]
         self.engines = [Engine(ckpt_dir, dev, max_batch=max_batch, state=state) for dev in self.device_list]
+        self.max_batch = min(e.max_batch for e in self.engines)
 
     def update_cluster_codebook(self, cluster_codebook):
         self.cluster_codebook = cluster_codebook
@@ -247,12 +274,14 @@ class SegmenterBase:
 
 
 class WhisperSegmenter(SegmenterBase):
-    def __init__(self, model_path, device=None, device_ids=[0, ], max_batch=64):
+    def __init__(self, model_path, device=None, device_ids=[0, ], max_batch=None):
+        """`max_batch` (not in the reference signature): windows encoded/decoded together; None = up to
+        DEFAULT_MAX_BATCH, shrunk to what fits in the device's free memory (engine.py: auto_max_batch)."""
         super().__init__()
         self._setup(model_path, device, device_ids, max_batch)
 
     @classmethod
-    def from_state(cls, state, tokenizer_dir, device=None, device_ids=(0,), max_batch=64):
+    def from_state(cls, state, tokenizer_dir, device=None, device_ids=(0,), max_batch=None):
         """Build from an in-memory (config dict, state dict, generation dict) triple -- what
         weights.load_checkpoint returns -- plus a directory holding the tokenizer files."""
         self = cls.__new__(cls)
@@ -266,13 +295,24 @@ class WhisperSegmenterFast(WhisperSegmenter):
 
 
 class WhisperSegmenterForEval(SegmenterBase):
-    def __init__(self, model_path=None, device=None, model=None, tokenizer=None, max_batch=64):
+    def __init__(self, model_path=None, device=None, model=None, tokenizer=None, max_batch=None):
+        """reference model.py:573-595: either a checkpoint path, or an in-memory HF `WhisperForConditionalGeneration`
+        plus its tokenizer (evaluate.py / train.py pass the model they are training).  The in-memory form snapshots
+        the model's weights, config and generation config into an engine: later updates of `model` are not seen."""
         super().__init__()
-        if model_path is None:
-            raise ValueError("whisperseg_b200.WhisperSegmenterForEval needs model_path (an in-memory HF model "
-                             "belongs to the training path, which is out of scope)")
         dev = torch.device(device) if device is not None else torch.device("cuda", 0)
-        self._setup(model_path, "cuda", [dev.index or 0], max_batch)
+        if model_path is not None:
+            self._setup(model_path, "cuda", [dev.index or 0], max_batch)
+        else:
+            if model is None or tokenizer is None:
+                raise ValueError("WhisperSegmenterForEval needs model_path, or model and tokenizer")
+            hf = getattr(model, "module", model)                      # nn.DataParallel wrapper (train.py:132)
+            cfg = hf.config.to_dict()
+            gen = hf.generation_config.to_dict() if getattr(hf, "generation_config", None) is not None else {}
+            sd = {k: v.detach().to("cpu") for k, v in hf.state_dict().items()}
+            tokdir = tempfile.mkdtemp(prefix="wsb_tok_")
+            tokenizer.save_pretrained(tokdir)
+            self._setup(None, "cuda", [dev.index or 0], max_batch, state=(cfg, sd, gen), tokenizer_dir=tokdir)
         self.device = self.device_list[0]
 
 
