@@ -164,7 +164,11 @@ def test_segments_match_unmodified_reference_on_confident_checkpoint(tmp_path, g
     sliced = seg.get_sliced_audios_features(audio, 16000, 0, 0.01, 1)
     texts = seg.generate_segment_text(sliced, 8, 96, 1)
     ref_texts = json.loads(bytes(g["texts"]).decode())
-    same = sum(a == b for a, b in zip(texts, ref_texts))
+    def strip(t):                  # the two sides pad finished rows differently (EOS runs / prompt tokens): compare the payload
+        for special in ("<|endoftext|>", "<|startoftranscript|>", "<|en|>", "<|notimestamps|>"):
+            t = t.replace(special, "")
+        return t
+    same = sum(strip(a) == strip(b) for a, b in zip(texts, ref_texts))
     print("generated texts identical to the reference's for %d / %d windows" % (same, len(ref_texts)))
     assert same >= len(ref_texts) - 1
 
