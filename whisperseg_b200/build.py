@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwsb.so")
-SOURCES = ["logmel.cu", "gemm.cu", "elementwise.cu", "attention.cu", "decode.cu", "beam.cu", "gemv.cu", "skinny.cu", "engine.cu"]
+SOURCES = ["logmel.cu", "gemm.cu", "elementwise.cu", "attention.cu", "decode.cu", "beam.cu", "gemv.cu", "skinny.cu", "mega.cu", "engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("WSB_NVCC_EXTRA", "").split()
 

@@ -74,6 +74,7 @@ struct Profiler {
 };
 static Profiler g_prof;
 static bool g_capturing = false;
+static std::mutex g_mega_mutex[64];
 struct ProfScope {
     cudaStream_t s;
     bool on;
@@ -147,6 +148,9 @@ struct Model {
     bool use_cluster = false;           // 65..256 decode rows: cluster split-K linear layers with folded LayerNorm (skinny.cu);
                                         // opt-in (WSB_CLUSTER=1): parity-green, but measured 0-4 % slower than the split-K pair
     bool use_fold = true;               // ... with the LayerNorm folded into the projection when the folded tensors exist
+    bool use_mega = true;               // <= 64 rows: one persistent kernel per decoder position (mega.cu; WSB_NO_MEGA=1: off)
+    void* mega_layers = nullptr;        // device table of the folded linear layers (null: folded tensors missing / unsupported width)
+    unsigned int* mega_sync = nullptr;  // device: grid-barrier arrivals, exits, watchdog flag
     bool fold_guard = true;             // fall back to the exact LayerNorm when a row's common mode dominates (WSB_FOLD_GUARD=0: off)
     bool fold_disabled = false;         // sticky: the guard fired once for this model
     int gemv_rows = 64;                 // ... used up to this many rows (WSB_GEMV_ROWS, <= 64)
@@ -332,6 +336,20 @@ static int model_create(const wsb_model_config* cfg, const char* const* names, c
     WSB_CHECK_CUDA(cudaMalloc(&m->ws, m->ws_bytes));
     model_layout(m, true);
     WSB_CHECK_CUDA(cudaMallocHost(&m->pinned_active, sizeof(int) * 4));
+    if (m->dec[0].sqkv_wf != nullptr && mega_supported(cfg->d_model, cfg->ffn_dim)) {
+        std::vector<char> host(mega_layer_table_bytes(cfg->n_layers));
+        for (int l = 0; l < cfg->n_layers; ++l) {
+            const DecLayer& e = m->dec[l];
+            const void* W[6] = {e.sqkv_wf, e.so_w, e.cq_wf, e.co_w, e.fc1_wf, e.fc2_w};
+            const float* bias[6] = {e.sqkv_c2, e.so_b, e.cq_c2, e.co_b, e.fc1_c2, e.fc2_b};
+            const float* c1[6] = {e.sqkv_c1, nullptr, e.cq_c1, nullptr, e.fc1_c1, nullptr};
+            mega_fill_layer(host.data(), l, W, bias, c1);
+        }
+        WSB_CHECK_CUDA(cudaMalloc(&m->mega_layers, host.size()));
+        WSB_CHECK_CUDA(cudaMemcpy(m->mega_layers, host.data(), host.size(), cudaMemcpyHostToDevice));
+        WSB_CHECK_CUDA(cudaMalloc(&m->mega_sync, sizeof(unsigned int) * 4));
+        WSB_CHECK_CUDA(cudaMemset(m->mega_sync, 0, sizeof(unsigned int) * 4));
+    }
     *out = m;
     return 0;
 }
@@ -341,6 +359,8 @@ static void model_destroy(Model* m) {
     for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
     for (auto& kv : m->beam_graphs) cudaGraphExecDestroy(kv.second.exec);
     cudaFree(m->beam_ws);
+    cudaFree(m->mega_layers);
+    cudaFree(m->mega_sync);
     cudaFree(m->ws);
     cudaFree(m->logit_tiles);
     cudaFreeHost(m->pinned_active);
@@ -696,17 +716,49 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
         ~PdlScope() { g_use_pdl = prev; }
     } pdl_scope(m->use_pdl || (m->use_gemv && B <= m->gemv_rows && c.d_model <= 1536));
     // (programmatic dependent launch: the linear-layer kernels fetch their weight tiles before the dependency wait)
-    WSB_RUN(embed_tokens_step(st.next_token, m->step, 0, m->dec_emb, m->dec_pos, m->dx, B, d, s));
     const long long cache_l = static_cast<long long>(B) * H * tmax * 64;
     const StepCtx x{m, st, B, d, F, L, H, T, tmax, fin, cache_l, with_logits, s};
     const bool folded = m->use_fold && m->dec[0].sqkv_wf != nullptr;
-    if (m->use_gemv && B <= m->gemv_rows && d <= 1536) {
-        WSB_RUN(decode_layers_fused(x));
-    } else if (m->use_cluster && folded && B <= 256 && skinny_cluster_supported(B, d, d) && skinny_cluster_supported(B, F, d) &&
-               skinny_cluster_supported(B, d, F)) {
-        WSB_RUN(decode_layers_cluster(x));
+    if (m->use_mega && m->mega_layers != nullptr && folded && m->use_gemv && B <= m->gemv_rows && st.anc == nullptr) {
+        // K5e: embedding + all decoder layers of this position in one persistent launch (mega.cu)
+        MegaArgs a;
+        a.layers_dev = m->mega_layers;
+        a.L = L; a.d = d; a.F = F; a.H = H; a.T = T; a.tmax = tmax; a.B = B;
+        a.next_token = st.next_token;
+        a.step_ptr = m->step;
+        a.emb = m->dec_emb;
+        a.pos_emb = m->dec_pos;
+        a.dx = m->dx;
+        a.dxn = m->dxn;
+        a.stats = m->gv_stats;
+        a.proj = m->dpart;
+        a.datt = m->datt;
+        a.dff = m->dff;
+        a.k_cache = st.k_cache;
+        a.v_cache = st.v_cache;
+        a.cross_kv = st.cross_kv;
+        a.finished = fin;
+        a.kv_div = st.kv_div;
+        a.sync = m->mega_sync;
+        a.fold_flag = m->fold_guard ? m->n_active + 1 : nullptr;
+        {
+            ProfScope ps(PROF_DEC_GEMM, 0.0, s);
+            WSB_RUN(decode_layers_mega(a, s));
+        }
+        if (with_logits) {
+            ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
+            WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec_ln_g, m->dec_ln_b, m->dxn, nullptr, B, d, s));
+        }
     } else {
-        WSB_RUN(decode_layers_splitk(x));
+        WSB_RUN(embed_tokens_step(st.next_token, m->step, 0, m->dec_emb, m->dec_pos, m->dx, B, d, s));
+        if (m->use_gemv && B <= m->gemv_rows && d <= 1536) {
+            WSB_RUN(decode_layers_fused(x));
+        } else if (m->use_cluster && folded && B <= 256 && skinny_cluster_supported(B, d, d) && skinny_cluster_supported(B, F, d) &&
+                   skinny_cluster_supported(B, d, F)) {
+            WSB_RUN(decode_layers_cluster(x));
+        } else {
+            WSB_RUN(decode_layers_splitk(x));
+        }
     }
     if (!with_logits) return prefill_advance(st.next_token, forced, forced_ld, m->prompt_dev, m->step, B, s);
     if (beam) {
@@ -769,6 +821,14 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     }
     m->use_fold = std::getenv("WSB_NO_FOLD") == nullptr && !(m->fold_guard && m->fold_disabled);
     m->use_cluster = std::getenv("WSB_CLUSTER") != nullptr;
+    m->use_mega = std::getenv("WSB_NO_MEGA") == nullptr;
+    // Two persistent decode kernels on one device could starve each other (each needs every SM to make progress):
+    // generate() calls that may launch them are serialised per device and drain their stream before returning.
+    int cur_dev = 0;
+    WSB_CHECK_CUDA(cudaGetDevice(&cur_dev));
+    std::unique_lock<std::mutex> mega_lock;
+    const bool mega_possible = m->use_mega && m->mega_layers != nullptr && m->use_gemv;
+    if (mega_possible) mega_lock = std::unique_lock<std::mutex>(g_mega_mutex[cur_dev & 63]);
     if (const char* e = std::getenv("WSB_GEMV_ROWS")) m->gemv_rows = std::max(0, std::min(64, std::atoi(e)));
     if (const char* e = std::getenv("WSB_LADDER")) {
         std::vector<int> lv;
@@ -845,7 +905,8 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     Model::GraphEntry* graph = nullptr;
     auto get_graph = [&](const DecState& cur, Model::GraphEntry** out) -> int {
         const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 32 * m->gemv_rows + (m->use_fold ? 4096 : 0) : 16) + (m->use_cluster ? 8192 : 0) +
-                                                    (m->use_pdl ? 16384 : 0) + (m->use_fold && m->fold_guard ? 32768 : 0), cur.row_map != nullptr ? 1 : 0, max_new,
+                                                    (m->use_pdl ? 16384 : 0) + (m->use_fold && m->fold_guard ? 32768 : 0) + (m->use_mega ? 65536 : 0),
+                                         cur.row_map != nullptr ? 1 : 0, max_new,
                                          prompt_len, eos_id, pad_id);
         auto it = m->graphs.find(key);
         if (it == m->graphs.end()) {
@@ -882,7 +943,14 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
         ++steps_done;
         if ((steps_done % check_every) == 0 && steps_done < max_new) {
             WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active, m->n_active, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+            if (mega_possible)
+                WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active + 2, m->mega_sync + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
             WSB_CHECK_CUDA(cudaStreamSynchronize(s));
+            if (mega_possible && m->pinned_active[2] != 0) {
+                cudaMemsetAsync(m->mega_sync, 0, sizeof(unsigned int) * 4, s);
+                set_last_error("persistent decode kernel: grid barrier watchdog fired (another kernel is holding SMs of this device?)");
+                return 6;
+            }
             if (m->pinned_active[1] != 0 && m->use_fold && m->fold_guard) {
                 // folded-LayerNorm guard: some live row's mean dominates its spread -> exact LayerNorm from here on
                 m->fold_disabled = true;
@@ -943,6 +1011,15 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     }
     WSB_CHECK_CUDA(cudaMemcpyAsync(tokens_out, m->tokens, sizeof(int) * static_cast<size_t>(B) * max_new,
                                    cudaMemcpyDeviceToDevice, s));
+    if (mega_possible) {
+        WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active + 2, m->mega_sync + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
+        WSB_CHECK_CUDA(cudaStreamSynchronize(s));          // nothing of this call is still running when the device lock drops
+        if (m->pinned_active[2] != 0) {
+            cudaMemsetAsync(m->mega_sync, 0, sizeof(unsigned int) * 4, s);
+            set_last_error("persistent decode kernel: grid barrier watchdog fired (another kernel is holding SMs of this device?)");
+            return 6;
+        }
+    }
     if (n_steps) *n_steps = steps_done;
     return 0;
 }
@@ -1274,7 +1351,7 @@ int wsb_gemv16(const float* x_f32_dev, const float* gamma_dev, const float* beta
         float*& p;
         ~Free() { cudaFree(p); }
     } guard{stats};
-    WSB_CHECK_CUDA(cudaMalloc(&stats, sizeof(float) * 160 * 128 * 2));
+    WSB_CHECK_CUDA(cudaMalloc(&stats, sizeof(float) * 640 * 128 * 2));
     __nv_bfloat16* xb = nullptr;
     struct FreeB {
         __nv_bfloat16*& p;
@@ -1303,7 +1380,7 @@ int wsb_gemv16(const float* x_f32_dev, const float* gamma_dev, const float* beta
     else if (out_mode == 1) g.out_bf16_gelu = static_cast<__nv_bfloat16*>(out_dev);
     else {
         g.resid = static_cast<float*>(out_dev);
-        g.stats_out = stats + 160 * 128;
+        g.stats_out = stats + 640 * 128;
     }
     g.M = M;
     g.N = N;
@@ -1376,13 +1453,13 @@ int wsb_gemv16_bench(int M, int N, int K, int mode, int iters, int weight_copies
     WSB_CHECK_CUDA(cudaMalloc(&a, static_cast<size_t>(64) * K * 2));
     WSB_CHECK_CUDA(cudaMalloc(&x, static_cast<size_t>(64) * K * 4));
     WSB_CHECK_CUDA(cudaMalloc(&gb, static_cast<size_t>(K) * 8 + static_cast<size_t>(N) * 4));
-    WSB_CHECK_CUDA(cudaMalloc(&stats, sizeof(float) * 160 * 128 * 2));
+    WSB_CHECK_CUDA(cudaMalloc(&stats, sizeof(float) * 640 * 128 * 2));
     WSB_CHECK_CUDA(cudaMalloc(&out, static_cast<size_t>(64) * N * 4));
     WSB_CHECK_CUDA(cudaMemset(w, 0, wn * 2 * weight_copies));
     WSB_CHECK_CUDA(cudaMemset(a, 0, static_cast<size_t>(64) * K * 2));
     WSB_CHECK_CUDA(cudaMemset(x, 0, static_cast<size_t>(64) * K * 4));
     WSB_CHECK_CUDA(cudaMemset(gb, 0, static_cast<size_t>(K) * 8 + static_cast<size_t>(N) * 4));
-    WSB_CHECK_CUDA(cudaMemset(stats, 0, sizeof(float) * 160 * 128 * 2));
+    WSB_CHECK_CUDA(cudaMemset(stats, 0, sizeof(float) * 640 * 128 * 2));
     WSB_CHECK_CUDA(cudaMemset(out, 0, static_cast<size_t>(64) * N * 4));
     cudaStream_t s = nullptr;
     cudaEvent_t e0, e1;
@@ -1408,7 +1485,7 @@ int wsb_gemv16_bench(int M, int N, int K, int mode, int iters, int weight_copies
     else if (mode == 1 || mode == 4) g.out_bf16_gelu = reinterpret_cast<__nv_bfloat16*>(out);
     else {
         g.resid = out;
-        g.stats_out = stats + 160 * 128;
+        g.stats_out = stats + 640 * 128;
     }
     g.M = M;
     g.N = N;

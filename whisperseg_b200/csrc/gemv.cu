@@ -311,17 +311,20 @@ __global__ void __launch_bounds__(kGvThreads, kGvMinBlocks) gemv16_kernel(const 
     if constexpr (EPI == 2) {
         if (p.stats_out) {
             __syncthreads();
-            if (tid < MP) {
-                float sm = 0.0f, sq = 0.0f;
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
+            // one (sum, sum of squares) partial per 8-feature n-tile and row -- independent of how many n-tiles a CTA
+            // owns, so every producer of the residual stream (this kernel, mega.cu) leaves the same partials
+            for (int idx = tid; idx < NT * MP; idx += kGvThreads) {
+                const int nt = idx / MP, row = idx - nt * MP;
+                if (n0 + nt * 8 < p.N) {
+                    float sm = 0.0f, sq = 0.0f;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const float v = new_s[(nt * MP + tid) * 8 + c];
+                        const float v = new_s[(nt * MP + row) * 8 + c];
                         sm += v;
                         sq = fmaf(v, v, sq);
                     }
-                *reinterpret_cast<float2*>(p.stats_out + (static_cast<long long>(blockIdx.x) * MP + tid) * 2) = make_float2(sm, sq);
+                    *reinterpret_cast<float2*>(p.stats_out + (static_cast<long long>(n0 / 8 + nt) * MP + row) * 2) = make_float2(sm, sq);
+                }
             }
         }
     }
@@ -382,8 +385,9 @@ static int gv_pick_nt(int N, int K, int in_ln, int epi, int mt) {
     while (nt > 1 && gv_smem_bytes(nt, K, in_ln, epi, mt) > static_cast<size_t>(kGvMaxSmem)) --nt;
     return nt;
 }
-int gemv16_parts(int N, int K) {                         // CTAs (= partial statistics) of a residual-update launch
-    return ceil_div(N, 8 * gv_pick_nt(N, K, 0, 2, 4));
+int gemv16_parts(int N, int K) {                         // partial statistics a residual-update launch leaves: one per 8 features
+    (void)K;
+    return ceil_div(N, 8);
 }
 int gemv16_max_rows() { return kGvMaxRows; }
 

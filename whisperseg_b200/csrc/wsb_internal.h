@@ -83,7 +83,7 @@ int embed_tokens(const int* tokens, const int* positions, const __nv_bfloat16* e
 // the consumer's LayerNorm (gamma, beta) fused in -- `stats` = [stats_parts][MP][2] partial (sum, sum of squares)
 // of every row, left by the producer of x -- or bf16 activations `a`.  Output: exactly one of fp32 `out_f32`,
 // bf16 `out_bf16_gelu` (GELU applied) or the in-place fp32 residual update `resid` (+=), which also writes the
-// updated rows' partial statistics to `stats_out` [gemv16_parts(N)][MP][2] when given.
+// updated rows' partial statistics to `stats_out` [N / 8][MP][2] (one partial per 8-feature n-tile) when given.
 struct Gemv16Args {
     const float* x = nullptr;
     const float* stats = nullptr;
@@ -108,6 +108,37 @@ int gemv16_max_rows();
 int gemv16_parts(int N, int K);                                 // CTAs (= statistics partials) of a launch with N outputs
 int row_stats16(const float* x, int M, int K, float* stats, cudaStream_t stream,
                 __nv_bfloat16* xb = nullptr);            // exact statistics, 1 part (+ optional bf16 copy of x)
+
+// ------------------------------------------------------------------ K5e persistent decode position for <= 64 rows (mega.cu)
+// One launch runs embedding + every decoder layer of one position (grid barriers between phases, weight tiles of the
+// next two linear-layer jobs in flight).  `layers_dev`: device table built with mega_fill_layer (per layer the six
+// linear layers qkv, self-out, cross-q, cross-out, fc1, fc2: W / bias / c1, the LayerNorm-consuming ones in folded form).
+// Leaves the updated residual stream in dx (+ bf16 copy, row statistics); the caller applies the final LayerNorm.
+struct MegaArgs {
+    const void* layers_dev = nullptr;
+    int L = 0, d = 0, F = 0, H = 0, T = 0, tmax = 0, B = 0;
+    const int* next_token = nullptr;
+    const int* step_ptr = nullptr;
+    const __nv_bfloat16* emb = nullptr;
+    const float* pos_emb = nullptr;
+    float* dx = nullptr;
+    __nv_bfloat16* dxn = nullptr;
+    float* stats = nullptr;
+    float* proj = nullptr;
+    __nv_bfloat16* datt = nullptr;
+    __nv_bfloat16* dff = nullptr;
+    __nv_bfloat16* k_cache = nullptr;
+    __nv_bfloat16* v_cache = nullptr;
+    const __nv_bfloat16* cross_kv = nullptr;
+    const unsigned char* finished = nullptr;
+    int kv_div = 1;
+    unsigned int* sync = nullptr;        // device, 4 words, zero before the first launch: arrivals, exits, watchdog flag
+    int* fold_flag = nullptr;
+};
+bool mega_supported(int d, int F);
+int decode_layers_mega(const MegaArgs& a, cudaStream_t stream);
+size_t mega_layer_table_bytes(int n_layers);
+void mega_fill_layer(void* host_table, int layer, const void* const W[6], const float* const bias[6], const float* const c1[6]);
 
 // ------------------------------------------------------------------ K5d skinny linear for 65..256 rows (skinny.cu)
 // One launch per linear layer: split-K across a thread-block cluster, partial tiles reduced through DSMEM, LayerNorm
