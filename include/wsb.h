@@ -82,6 +82,11 @@ size_t wsb_workspace_bytes_for(const wsb_model_config* cfg);
  * exact form while a row's |mean| stays below ~2 standard deviations; when a live row violates that, the engine
  * switches this model to the exact on-the-fly LayerNorm for good (HF nn.LayerNorm semantics, modeling_whisper.py:417-506). */
 int wsb_model_fold_fallback(const wsb_model* model);
+/* Diagnostics of the persistent decode kernel (csrc/mega.cu): out_host == NULL arms the trace and returns its length in
+ * words; otherwise copies the %globaltimer stamps (ns) CTA 0 took during the LAST decoder position into out_host:
+ * word 0 = start, word 2k-1 = phase k's work done, word 2k = grid barrier k passed.  Returns the words copied (> 0);
+ * unlike the other entry points a return value <= 0 is the error.                                                  */
+int wsb_mega_trace(wsb_model* model, unsigned long long* out_host, int n);
 
 /* Encoder (conv stem + n_layers pre-LN blocks + final LN); replaces HF WhisperEncoder.forward
  * reached from model.generate (reference model.py:655).  features_dev: float32 [batch][80][n_cols].

@@ -1,5 +1,5 @@
-"""K5e (csrc/mega.cu): the persistent one-launch-per-position decode kernel for <= 64 rows against the launch-per-layer
-fused path it replaces (gemv.cu + decode.cu, WSB_NO_MEGA=1).  Both run the same arithmetic in the same order, so the
+"""K5e (csrc/mega.cu, opt-in with WSB_MEGA=1): the persistent one-launch-per-position decode kernel for <= 64 rows against
+the launch-per-layer fused path (gemv.cu + decode.cu, the default).  Both run the same arithmetic in the same order, so the
 generated tokens must be BIT-IDENTICAL -- free-running, with and without CUDA graphs, across the 16 / 32 / 64-row
 variants and through batch compaction; parity against the fp32 oracle is asserted for both paths in test_gpu_model.py
 (test_decoder_teacher_forced) and test_gpu_parity_bar.py."""
@@ -27,9 +27,9 @@ def test_mega_tokens_identical_to_launch_per_layer_path(tiny_checkpoint, monkeyp
     outs = {}
     for mode in ("mega", "launches"):
         if mode == "launches":
-            monkeypatch.setenv("WSB_NO_MEGA", "1")
+            monkeypatch.delenv("WSB_MEGA", raising=False)
         else:
-            monkeypatch.delenv("WSB_NO_MEGA", raising=False)
+            monkeypatch.setenv("WSB_MEGA", "1")
         for graph in (False, True):
             eng.encode(feats)
             ids, steps = eng.generate(n, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, 120, use_graph=graph)
@@ -61,9 +61,9 @@ def test_mega_large_arch_small_batch(monkeypatch):
     outs = {}
     for mode in ("mega", "launches"):
         if mode == "launches":
-            monkeypatch.setenv("WSB_NO_MEGA", "1")
+            monkeypatch.delenv("WSB_MEGA", raising=False)
         else:
-            monkeypatch.delenv("WSB_NO_MEGA", raising=False)
+            monkeypatch.setenv("WSB_MEGA", "1")
         eng.encode(feats)
         ids, steps = eng.generate(len(wins), tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, 100)
         outs[mode] = (ids.cpu(), steps)

@@ -65,8 +65,8 @@ def test_decoder_teacher_forced(setup, monkeypatch, path):
     (WSB_NO_FOLD=1), and the tcgen05 split-K GEMM + reduce pair used above 64 rows (WSB_NO_GEMV=1)."""
     import torch
     from tools import synth
-    if path != "persistent-kernel":             # (default at <= 64 rows: csrc/mega.cu, one launch per position)
-        monkeypatch.setenv("WSB_NO_MEGA", "1")
+    if path == "persistent-kernel":             # opt-in: csrc/mega.cu, one launch per decoder position
+        monkeypatch.setenv("WSB_MEGA", "1")
     if path == "fused-exact-ln":
         monkeypatch.setenv("WSB_NO_FOLD", "1")
     elif path == "tcgen05-splitk":

@@ -38,6 +38,7 @@ EXPORTS = {
     "wsb_model_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p]),
     "wsb_workspace_bytes_for": (ctypes.c_size_t, [ctypes.POINTER(ModelConfig)]),
     "wsb_model_fold_fallback": (ctypes.c_int, [ctypes.c_void_p]),
+    "wsb_mega_trace": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]),
     "wsb_encode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "wsb_generate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int,
                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,

@@ -148,9 +148,11 @@ struct Model {
     bool use_cluster = false;           // 65..256 decode rows: cluster split-K linear layers with folded LayerNorm (skinny.cu);
                                         // opt-in (WSB_CLUSTER=1): parity-green, but measured 0-4 % slower than the split-K pair
     bool use_fold = true;               // ... with the LayerNorm folded into the projection when the folded tensors exist
-    bool use_mega = true;               // <= 64 rows: one persistent kernel per decoder position (mega.cu; WSB_NO_MEGA=1: off)
+    bool use_mega = false;              // <= 64 rows: one persistent kernel per decoder position (mega.cu); opt-in (WSB_MEGA=1):
+                                        // bit-identical tokens, but measured 3x SLOWER than the launch-per-layer path
     void* mega_layers = nullptr;        // device table of the folded linear layers (null: folded tensors missing / unsupported width)
     unsigned int* mega_sync = nullptr;  // device: grid-barrier arrivals, exits, watchdog flag
+    unsigned long long* mega_trace = nullptr;   // diagnostics (wsb_mega_trace): per-barrier timestamps of the last position
     bool fold_guard = true;             // fall back to the exact LayerNorm when a row's common mode dominates (WSB_FOLD_GUARD=0: off)
     bool fold_disabled = false;         // sticky: the guard fired once for this model
     int gemv_rows = 64;                 // ... used up to this many rows (WSB_GEMV_ROWS, <= 64)
@@ -347,8 +349,8 @@ static int model_create(const wsb_model_config* cfg, const char* const* names, c
         }
         WSB_CHECK_CUDA(cudaMalloc(&m->mega_layers, host.size()));
         WSB_CHECK_CUDA(cudaMemcpy(m->mega_layers, host.data(), host.size(), cudaMemcpyHostToDevice));
-        WSB_CHECK_CUDA(cudaMalloc(&m->mega_sync, sizeof(unsigned int) * 4));
-        WSB_CHECK_CUDA(cudaMemset(m->mega_sync, 0, sizeof(unsigned int) * 4));
+        WSB_CHECK_CUDA(cudaMalloc(&m->mega_sync, sizeof(unsigned int) * 64));
+        WSB_CHECK_CUDA(cudaMemset(m->mega_sync, 0, sizeof(unsigned int) * 64));
     }
     *out = m;
     return 0;
@@ -361,6 +363,7 @@ static void model_destroy(Model* m) {
     cudaFree(m->beam_ws);
     cudaFree(m->mega_layers);
     cudaFree(m->mega_sync);
+    cudaFree(m->mega_trace);
     cudaFree(m->ws);
     cudaFree(m->logit_tiles);
     cudaFreeHost(m->pinned_active);
@@ -741,6 +744,7 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
         a.kv_div = st.kv_div;
         a.sync = m->mega_sync;
         a.fold_flag = m->fold_guard ? m->n_active + 1 : nullptr;
+        a.trace = m->mega_trace;
         {
             ProfScope ps(PROF_DEC_GEMM, 0.0, s);
             WSB_RUN(decode_layers_mega(a, s));
@@ -821,7 +825,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     }
     m->use_fold = std::getenv("WSB_NO_FOLD") == nullptr && !(m->fold_guard && m->fold_disabled);
     m->use_cluster = std::getenv("WSB_CLUSTER") != nullptr;
-    m->use_mega = std::getenv("WSB_NO_MEGA") == nullptr;
+    m->use_mega = std::getenv("WSB_MEGA") != nullptr && std::getenv("WSB_NO_MEGA") == nullptr;
     // Two persistent decode kernels on one device could starve each other (each needs every SM to make progress):
     // generate() calls that may launch them are serialised per device and drain their stream before returning.
     int cur_dev = 0;
@@ -947,7 +951,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
                 WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active + 2, m->mega_sync + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
             WSB_CHECK_CUDA(cudaStreamSynchronize(s));
             if (mega_possible && m->pinned_active[2] != 0) {
-                cudaMemsetAsync(m->mega_sync, 0, sizeof(unsigned int) * 4, s);
+                cudaMemsetAsync(m->mega_sync, 0, sizeof(unsigned int) * 64, s);
                 set_last_error("persistent decode kernel: grid barrier watchdog fired (another kernel is holding SMs of this device?)");
                 return 6;
             }
@@ -1015,7 +1019,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
         WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active + 2, m->mega_sync + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
         WSB_CHECK_CUDA(cudaStreamSynchronize(s));          // nothing of this call is still running when the device lock drops
         if (m->pinned_active[2] != 0) {
-            cudaMemsetAsync(m->mega_sync, 0, sizeof(unsigned int) * 4, s);
+            cudaMemsetAsync(m->mega_sync, 0, sizeof(unsigned int) * 64, s);
             set_last_error("persistent decode kernel: grid barrier watchdog fired (another kernel is holding SMs of this device?)");
             return 6;
         }
@@ -1228,6 +1232,25 @@ size_t wsb_workspace_bytes_for(const wsb_model_config* cfg) {
     m.am_tiles = gemm_n_tiles(cfg->vocab_size, 32);        // upper bound: every vocabulary tile of the narrowest block
     model_layout(&m, false);
     return m.ws_bytes;
+}
+int wsb_mega_trace(wsb_model* model, unsigned long long* out_host, int n) {
+    WSB_REQUIRE(model != nullptr && model->impl != nullptr, "null model");
+    Model* m = model->impl;
+    const int cap = 2 * (2 + 10 * m->cfg.n_layers) + 2 + 64;
+    if (out_host == nullptr) {                              // arm (n != 0) or disarm (n == 0) the trace buffer
+        if (n != 0 && m->mega_trace == nullptr) {
+            WSB_CHECK_CUDA(cudaMalloc(&m->mega_trace, sizeof(unsigned long long) * cap));
+            WSB_CHECK_CUDA(cudaMemset(m->mega_trace, 0, sizeof(unsigned long long) * cap));
+            for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);     // the pointer is baked into captured launches
+            m->graphs.clear();
+        }
+        return cap;
+    }
+    WSB_REQUIRE(m->mega_trace != nullptr, "trace not armed");
+    WSB_CHECK_CUDA(cudaDeviceSynchronize());
+    WSB_CHECK_CUDA(cudaMemcpy(out_host, m->mega_trace, sizeof(unsigned long long) * std::min(n, cap), cudaMemcpyDeviceToHost));
+    WSB_CHECK_CUDA(cudaMemset(m->mega_trace + (cap - 64), 0, sizeof(unsigned long long) * 64));      // stage accumulators restart
+    return std::min(n, cap);
 }
 int wsb_model_fold_fallback(const wsb_model* model) { return (model && model->impl && model->impl->fold_disabled) ? 1 : 0; }
 size_t wsb_model_workspace_bytes(const wsb_model* model) { return model ? model->impl->ws_bytes : 0; }

@@ -132,8 +132,9 @@ struct MegaArgs {
     const __nv_bfloat16* cross_kv = nullptr;
     const unsigned char* finished = nullptr;
     int kv_div = 1;
-    unsigned int* sync = nullptr;        // device, 4 words, zero before the first launch: arrivals, exits, watchdog flag
+    unsigned int* sync = nullptr;        // device, 64 words, zero before the first launch: arrivals, exits, watchdog flag, ..., generation
     int* fold_flag = nullptr;
+    unsigned long long* trace = nullptr; // diagnostics: device buffer of 2 * (2 + 10 L) timestamps (wsb_mega_trace)
 };
 bool mega_supported(int d, int F);
 int decode_layers_mega(const MegaArgs& a, cudaStream_t stream);
