@@ -25,6 +25,7 @@ def test_mega_tokens_identical_to_launch_per_layer_path(tiny_checkpoint, monkeyp
     assert n <= max_batch
     feats = eng.features(plan, audio, wins)
     outs = {}
+    monkeypatch.setenv("WSB_ATTN_THREADS", "128")     # the persistent kernel's attention units are decode.cu's 128-thread form
     for mode in ("mega", "launches"):
         if mode == "launches":
             monkeypatch.delenv("WSB_MEGA", raising=False)
@@ -59,6 +60,7 @@ def test_mega_large_arch_small_batch(monkeypatch):
     wins = plan.windows(len(audio), 1)
     feats = eng.features(plan, audio, wins)
     outs = {}
+    monkeypatch.setenv("WSB_ATTN_THREADS", "128")
     for mode in ("mega", "launches"):
         if mode == "launches":
             monkeypatch.delenv("WSB_MEGA", raising=False)

@@ -201,6 +201,7 @@ def test_batch_compaction_equals_uncompacted(tiny_checkpoint, monkeypatch):
     feats = eng.features(plan, audio, wins)
     outs = {}
     monkeypatch.setenv("WSB_NO_GEMV", "1")       # same linear-layer kernels on both sides: this test is about the gather
+    monkeypatch.setenv("WSB_ATTN_THREADS", "128")  # ... and the same attention variant whatever the row count
     for mode in ("compact", "plain"):
         if mode == "plain":
             monkeypatch.setenv("WSB_NO_COMPACT", "1")

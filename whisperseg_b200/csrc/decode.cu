@@ -12,10 +12,21 @@
 #include "wsb_internal.h"
 #include "decode.h"
 
+#include <cstdlib>
+
 namespace wsb {
 
 constexpr int kDaThreads = 128;
+constexpr int kDaWideThreads = 512;
 constexpr int kDaMaxKeys = 512;
+
+// 512 threads per (row, head) unit while all units fit on the device at once (4 such CTAs per SM); WSB_ATTN_THREADS=128
+// pins the narrow variant (the two variants reduce in different orders: tests that compare batch sizes bit for bit pin it)
+static bool decode_attention_wide(int B, int n_heads) {
+    const char* e = std::getenv("WSB_ATTN_THREADS");
+    const bool pinned = e != nullptr && std::atoi(e) == 128;
+    return !pinned && static_cast<long long>(B) * n_heads <= 592;
+}
 
 // q: bf16 [B][q_ld] (+ head*64), already scaled.  K/V blocks: bf16 [n_keys][64] contiguous per (b, head).
 // mode 0 (cross): K at kv + ((b*kv_heads_total + k_slot)*T)*64, n_keys = T, fixed.
@@ -52,8 +63,13 @@ struct DaParams {
     long long anc_buf_stride;
 };
 
-template <bool kAnc>
-__global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaParams p) {
+// kThreads = 128, or 512 when there are so few (row, head) units that a 128-thread CTA per unit leaves the HBM pipe
+// empty: a unit streams its 128 KB of K/V with (threads x 64 B) in flight, i.e. ~8 GB/s per 128-thread CTA at ~1 us
+// of latency -- 16-20 us per launch at <= 16 rows whatever the row count (r2 mega trace: cross-attention was 37 us of a
+// 110 us layer at 8 rows).  Four times the threads per unit = four times the bytes in flight.
+template <bool kAnc, int kThreads>
+__global__ void __launch_bounds__(kThreads) decode_attention_kernel(const DaParams p) {
+    constexpr int kDaThreads = kThreads;
     const int h = blockIdx.x, b = blockIdx.y;
     pdl_wait();
     pdl_launch_dependents();
@@ -87,7 +103,7 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const DaPa
         if (tid < 64) {
             const float kv = proj(p.d + h * 64 + tid, p.new_k);
             p.k_cache[blk + static_cast<long long>(pos) * 64 + tid] = __float2bfloat16(kv);
-        } else {
+        } else if (tid < 128) {
             const int e = tid - 64;
             const float vv = proj(2 * p.d + h * 64 + e, p.new_v);
             p.v_cache[blk + static_cast<long long>(pos) * 64 + e] = __float2bfloat16(vv);
@@ -227,11 +243,14 @@ int decode_self_attention(const __nv_bfloat16* qkv, const SplitkInput* part, int
     p.anc_ld = anc_ld;
     p.anc_buf_stride = static_cast<long long>(B) * anc_ld;
     if (anc) {
-        WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel<true>, dim3(n_heads, B), dim3(kDaThreads), 0, stream, p));
+        WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel<true, kDaThreads>, dim3(n_heads, B), dim3(kDaThreads), 0, stream, p));
         count_launch();
         return 0;
     }
-    WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel<false>, dim3(n_heads, B), dim3(kDaThreads), 0, stream, p));
+    if (decode_attention_wide(B, n_heads))
+        WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel<false, kDaWideThreads>, dim3(n_heads, B), dim3(kDaWideThreads), 0, stream, p));
+    else
+        WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel<false, kDaThreads>, dim3(n_heads, B), dim3(kDaThreads), 0, stream, p));
     count_launch();
     return 0;
 }
@@ -270,7 +289,10 @@ int decode_cross_attention(const __nv_bfloat16* q, const SplitkInput* part, int 
     p.anc = nullptr;
     p.anc_ld = 0;
     p.anc_buf_stride = 0;
-    WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel<false>, dim3(n_heads, B), dim3(kDaThreads), 0, stream, p));
+    if (decode_attention_wide(B, n_heads))
+        WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel<false, kDaWideThreads>, dim3(n_heads, B), dim3(kDaWideThreads), 0, stream, p));
+    else
+        WSB_CHECK_CUDA(launch_kernel(decode_attention_kernel<false, kDaThreads>, dim3(n_heads, B), dim3(kDaThreads), 0, stream, p));
     count_launch();
     return 0;
 }

@@ -909,7 +909,8 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     Model::GraphEntry* graph = nullptr;
     auto get_graph = [&](const DecState& cur, Model::GraphEntry** out) -> int {
         const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 32 * m->gemv_rows + (m->use_fold ? 4096 : 0) : 16) + (m->use_cluster ? 8192 : 0) +
-                                                    (m->use_pdl ? 16384 : 0) + (m->use_fold && m->fold_guard ? 32768 : 0) + (m->use_mega ? 65536 : 0),
+                                                    (m->use_pdl ? 16384 : 0) + (m->use_fold && m->fold_guard ? 32768 : 0) + (m->use_mega ? 65536 : 0) +
+                                                    (std::getenv("WSB_ATTN_THREADS") ? 131072 : 0),
                                          cur.row_map != nullptr ? 1 : 0, max_new,
                                          prompt_len, eos_id, pad_id);
         auto it = m->graphs.find(key);

@@ -140,15 +140,45 @@ __global__ void __launch_bounds__(kGvThreads, kGvMinBlocks) gemv16_kernel(const 
             reinterpret_cast<float4*>(bet_s)[j] = __ldg(reinterpret_cast<const float4*>(p.beta) + j);
         }
     }
+    // epilogue operands of this thread's output elements: the constants (bias, c1) are fetched before the dependency
+    // wait, the residual rows right after it -- every global load of the launch is in flight at once and the kernel
+    // pays ONE L2 round trip (~1 us), not one per stage (measured with mega.cu's stage trace)
+    constexpr int kEpi = (MT * NT * 128 + kGvThreads - 1) / kGvThreads;
+    float pre_bias[kEpi], pre_c1[IN_LN == 2 ? kEpi : 1], pre_res[EPI == 2 ? kEpi : 1];
+#pragma unroll
+    for (int e = 0; e < kEpi; ++e) {
+        const int idx = tid + e * kGvThreads;
+        const int rem = idx % (NT * 128);
+        const int n = n0 + (rem >> 7) * 8 + (rem & 7);
+        const bool ok = idx < MT * NT * 128 && n < p.N;
+        pre_bias[e] = (ok && p.bias) ? __ldg(p.bias + n) : 0.0f;
+        if constexpr (IN_LN == 2) pre_c1[e] = ok ? __ldg(p.c1 + n) : 0.0f;
+    }
     pdl_wait();
 
-    // which of this lane's two rows are loaded (inside M and not finished), and is the tile live at all
+    // A fragments are loaded for every row inside M -- also finished ones, whose results are never stored: gating the
+    // loads on the finished flags would put a dependent round trip in front of them.  An m-tile whose rows have all
+    // finished is still skipped (no MMAs, no further loads).
     const int r_lo = rb + g, r_hi = rb + g + 8;
-    const bool use_lo = r_lo < p.M && !(p.row_skip && p.row_skip[r_lo]);
-    const bool use_hi = r_hi < p.M && !(p.row_skip && p.row_skip[r_hi]);
-    const bool tile_live = __any_sync(0xffffffffu, use_lo || use_hi);
-    const int my_blocks = (tile_live && kw < nkb) ? (nkb - kw + KS - 1) / KS : 0;      // k-blocks kw, kw + KS, ...
-    const int n_batches = (my_blocks + kGvBatch - 1) / kGvBatch;
+    const bool use_lo = r_lo < p.M, use_hi = r_hi < p.M;
+    const int all_blocks = kw < nkb ? (nkb - kw + KS - 1) / KS : 0;                   // k-blocks kw, kw + KS, ...
+    int my_blocks = all_blocks;
+    int n_batches = (my_blocks + kGvBatch - 1) / kGvBatch;
+    unsigned char skip_lo = 0, skip_hi = 0;
+    if (p.row_skip) {
+        if (use_lo) skip_lo = p.row_skip[r_lo];
+        if (use_hi) skip_hi = p.row_skip[r_hi];
+    }
+    if constexpr (EPI == 2) {
+#pragma unroll
+        for (int e = 0; e < kEpi; ++e) {
+            const int idx = tid + e * kGvThreads;
+            const int m = idx / (NT * 128), rem = idx - m * (NT * 128);
+            const int row = m * 16 + ((rem & 127) >> 3);
+            const int n = n0 + (rem >> 7) * 8 + (rem & 7);
+            pre_res[e] = (idx < MT * NT * 128 && row < p.M && n < p.N) ? p.resid[static_cast<long long>(row) * p.N + n] : 0.0f;
+        }
+    }
 
     // raw activation fragments of one batch: fp32 (LayerNorm path) or bf16
     float4 xl[IN_LN == 1 ? kGvBatch : 1][2], xh[IN_LN == 1 ? kGvBatch : 1][2];
@@ -183,6 +213,13 @@ __global__ void __launch_bounds__(kGvThreads, kGvMinBlocks) gemv16_kernel(const 
         }
     };
     if (n_batches > 0) load_batch(0);
+    {
+        const bool tile_live = __any_sync(0xffffffffu, (use_lo && !skip_lo) || (use_hi && !skip_hi));
+        if (!tile_live) {
+            my_blocks = 0;
+            n_batches = 0;
+        }
+    }
 
     float m_lo = 0.f, rs_lo = 0.f, m_hi = 0.f, rs_hi = 0.f;
     if constexpr (IN_LN != 0) {
@@ -193,10 +230,21 @@ __global__ void __launch_bounds__(kGvThreads, kGvMinBlocks) gemv16_kernel(const 
             const int r = tid / TPR, sub = tid % TPR;
             float sm = 0.0f, sq = 0.0f;
             if (r < p.M) {
-                for (int pp = sub; pp < p.stats_parts; pp += TPR) {
-                    const float2 v = *reinterpret_cast<const float2*>(p.stats + (static_cast<long long>(pp) * MP + r) * 2);
-                    sm += v.x;
-                    sq += v.y;
+                // 8 partials per thread in flight at a time, added in ascending order (adding the zero of a missing
+                // partial changes nothing, so the sum is the sequential one)
+                for (int base = sub; base < p.stats_parts; base += 8 * TPR) {
+                    float2 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int pp = base + i * TPR;
+                        v[i] = pp < p.stats_parts ? *reinterpret_cast<const float2*>(p.stats + (static_cast<long long>(pp) * MP + r) * 2)
+                                                  : make_float2(0.0f, 0.0f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        sm += v[i].x;
+                        sq += v[i].y;
+                    }
                 }
             }
 #pragma unroll
@@ -275,7 +323,10 @@ __global__ void __launch_bounds__(kGvThreads, kGvMinBlocks) gemv16_kernel(const 
         red_w[nt * 128 + (g + 8) * 8 + 2 * t + 1] = acc[nt][3];
     }
     __syncthreads();
-    for (int idx = tid; idx < MT * NT * 128; idx += kGvThreads) {
+#pragma unroll
+    for (int e = 0; e < kEpi; ++e) {
+        const int idx = tid + e * kGvThreads;
+        if (idx >= MT * NT * 128) break;
         const int m = idx / (NT * 128), rem = idx - m * (NT * 128);
         const int nt = rem >> 7, r = (rem & 127) >> 3, c = rem & 7;
         const int row = m * 16 + r;
@@ -285,9 +336,9 @@ __global__ void __launch_bounds__(kGvThreads, kGvMinBlocks) gemv16_kernel(const 
         for (int w = 0; w < KS; ++w) v += red_s[(m * KS + w) * (NT * 128) + nt * 128 + r * 8 + c];
         const bool valid = row < p.M && n < p.N;
         if constexpr (IN_LN == 2) {
-            if (valid) v = s_rstd[row] * (v - s_mean[row] * __ldg(p.c1 + n));
+            if (valid) v = s_rstd[row] * (v - s_mean[row] * pre_c1[e]);
         }
-        if (valid && p.bias) v += __ldg(p.bias + n);
+        if (valid && p.bias) v += pre_bias[e];
         const bool store = valid && !(p.row_skip && p.row_skip[row]);
         const long long o = static_cast<long long>(row) * p.N + n;
         if constexpr (EPI == 0) {
@@ -299,7 +350,7 @@ __global__ void __launch_bounds__(kGvThreads, kGvMinBlocks) gemv16_kernel(const 
         if constexpr (EPI == 2) {
             float xn = 0.0f;
             if (valid) {
-                xn = p.resid[o] + (store ? v : 0.0f);
+                xn = pre_res[e] + (store ? v : 0.0f);
                 if (store) {
                     p.resid[o] = xn;
                     if (p.xb_out) p.xb_out[o] = __float2bfloat16(xn);
