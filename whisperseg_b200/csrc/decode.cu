@@ -73,7 +73,6 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const DaPara
     const int h = blockIdx.x, b = blockIdx.y;
     pdl_wait();
     pdl_launch_dependents();
-    if (p.finished && p.finished[b]) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     __shared__ float s_q[64];
     __shared__ int s_src[kAnc ? kDaMaxKeys : 1];
@@ -85,34 +84,44 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const DaPara
     const __nv_bfloat16* K = p.k_base + blk;
     const __nv_bfloat16* V = p.v_base + blk;
     int n_keys;
-    // value of column `col` of this row's projection output: bf16 activation, or bias + split-K planes
+    // value of column `col` of this row's projection output: bf16 activation, or bias + split-K planes.  The planes are
+    // fetched together (one L2 round trip, not one per plane) and added in plane order.
     auto proj = [&](int col, const __nv_bfloat16* act) -> float {
         if (p.part == nullptr) return __bfloat162float(act[static_cast<long long>(b) * p.q_ld + h * 64 + (col & 63)]);
-        float acc = p.bias ? __ldg(p.bias + col) : 0.0f;
         const float* src = p.part + static_cast<long long>(b) * p.part_ld + col;
-        for (int sp = 0; sp < p.splits; ++sp) acc += src[sp * p.split_stride];
+        float t[16];
+#pragma unroll
+        for (int sp = 0; sp < 16; ++sp) t[sp] = sp < p.splits ? src[sp * p.split_stride] : 0.0f;
+        float acc = p.bias ? __ldg(p.bias + col) : 0.0f;
+#pragma unroll
+        for (int sp = 0; sp < 16; ++sp)
+            if (sp < p.splits) acc += t[sp];
         return acc;
     };
+    // the projection inputs are requested together with the finished flag; a finished row leaves before it writes anything
+    const bool fin = p.finished && p.finished[b];
+    float new_kv = 0.0f, new_q = 0.0f;
+    int pos = 0;
     if (p.self_mode) {
-        const int pos = p.pos_offset + *p.step_ptr;
+        pos = p.pos_offset + *p.step_ptr;
+        if (tid < 64) new_kv = proj(p.d + h * 64 + tid, p.new_k);
+        else if (tid < 128) new_kv = proj(2 * p.d + h * 64 + (tid - 64), p.new_v);
+    }
+    if (tid < 64) new_q = proj(h * 64 + tid, p.q);
+    if (fin) return;
+    if (p.self_mode) {
         n_keys = pos + 1;
         if constexpr (kAnc) {
             const int* a = p.anc + (pos & 1) * p.anc_buf_stride + static_cast<long long>(b) * p.anc_ld;
             for (int j = tid; j <= pos; j += kDaThreads) s_src[j] = (j == pos) ? b : a[j];
         }
-        if (tid < 64) {
-            const float kv = proj(p.d + h * 64 + tid, p.new_k);
-            p.k_cache[blk + static_cast<long long>(pos) * 64 + tid] = __float2bfloat16(kv);
-        } else if (tid < 128) {
-            const int e = tid - 64;
-            const float vv = proj(2 * p.d + h * 64 + e, p.new_v);
-            p.v_cache[blk + static_cast<long long>(pos) * 64 + e] = __float2bfloat16(vv);
-        }
+        if (tid < 64) p.k_cache[blk + static_cast<long long>(pos) * 64 + tid] = __float2bfloat16(new_kv);
+        else if (tid < 128) p.v_cache[blk + static_cast<long long>(pos) * 64 + (tid - 64)] = __float2bfloat16(new_kv);
     } else {
         n_keys = p.n_keys_fixed;
     }
     // q is rounded to bf16 like the stand-alone second phase would, so both paths give identical results
-    if (tid < 64) s_q[tid] = __bfloat162float(__float2bfloat16(proj(h * 64 + tid, p.q)));
+    if (tid < 64) s_q[tid] = __bfloat162float(__float2bfloat16(new_q));
     __syncthreads();                                   // also orders the cache append before the reads below
 
     // Single pass over the keys with an online softmax: a warp covers 4 keys per step (lane = (key % 4) * 8 +

@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(kRedThreads) splitk_reduce_bf16_kernel(const f
     const int nvec = N >> 2;
     pdl_wait();
     pdl_launch_dependents();
-    if (row_skip && row_skip[row]) return;
+    // (the finished flag is requested together with the first planes: a dependent round trip less per launch)
+    const bool skip = row_skip && row_skip[row];
     const float4* base = reinterpret_cast<const float4*>(partial + static_cast<long long>(row) * N);
     const long long sv = split_stride >> 2;
     for (int j = threadIdx.x; j < nvec; j += kRedThreads) {
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(kRedThreads) splitk_reduce_bf16_kernel(const f
 #pragma unroll
         for (int sp = 0; sp < kRedMaxSplits; ++sp)
             if (sp < splits) t[sp] = base[sp * sv + j];
+        if (skip) return;
         float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int sp = 0; sp < kRedMaxSplits; ++sp)
@@ -132,13 +134,25 @@ __global__ void __launch_bounds__(kRedThreads) splitk_reduce_resid_ln_kernel(con
     pdl_wait();
     pdl_launch_dependents();
     const int row = blockIdx.x;
-    if (row_skip && row_skip[row]) return;
+    const bool skip = row_skip && row_skip[row];          // requested together with the planes below
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nvec = N >> 2;
     const float4* base = reinterpret_cast<const float4*>(partial + static_cast<long long>(row) * N);
     const long long sv = split_stride >> 2;
     float4* xr = reinterpret_cast<float4*>(x + static_cast<long long>(row) * N);
     float4 v[kRedLnVec];
+    // the LayerNorm affine of this thread's elements: constants, fetched now instead of after the two reductions
+    float4 gm[kRedLnVec], bt_[kRedLnVec];
+    if (gamma != nullptr) {
+#pragma unroll
+        for (int i = 0; i < kRedLnVec; ++i) {
+            const int j = tid + kRedThreads * i;
+            if (j < nvec) {
+                gm[i] = __ldg(reinterpret_cast<const float4*>(gamma) + j);
+                bt_[i] = __ldg(reinterpret_cast<const float4*>(beta) + j);
+            }
+        }
+    }
     float sum = 0.0f;
 #pragma unroll
     for (int i = 0; i < kRedLnVec; ++i) {
@@ -149,6 +163,7 @@ __global__ void __launch_bounds__(kRedThreads) splitk_reduce_resid_ln_kernel(con
             for (int sp = 0; sp < kRedMaxSplits; ++sp)
                 if (sp < splits) t[sp] = base[sp * sv + j];
             float4 acc = xr[j];
+            if (skip) return;
             if (bias) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + j);
                 acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
@@ -191,8 +206,8 @@ __global__ void __launch_bounds__(kRedThreads) splitk_reduce_resid_ln_kernel(con
     for (int i = 0; i < kRedLnVec; ++i) {
         const int j = tid + kRedThreads * i;
         if (j < nvec) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + j);
-            const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + j);
+            const float4 g = gm[i];
+            const float4 bt = bt_[i];
             uint2 pk;
             pk.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + bt.x, (v[i].y - mean) * rstd * g.y + bt.y);
             pk.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + bt.z, (v[i].w - mean) * rstd * g.w + bt.w);
