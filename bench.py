@@ -590,15 +590,26 @@ def run_config(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    desc, sr, sts, seconds, seed, num_trials, kw = CONFIGS[args.config]
     state = synth.make_state(args.arch, seed=0, calibrate="file" if args.arch == "large" else "auto")
     tokdir = tempfile.mkdtemp(prefix="wsb_tok_")
     synth.token_table_files(tokdir)
     seg = WhisperSegmenter.from_state(state, tokdir, device="cuda", device_ids=[local_rank], max_batch=args.max_batch)
+    for name in args.config.split(","):                    # several configurations on one model build (one JSON line each)
+        _run_one_config(args, name, seg, lib, world, rank, local_rank, dev)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _run_one_config(args, config, seg, lib, world, rank, local_rank, dev):
+    import torch
+    import torch.distributed as dist
+    from whisperseg_b200.distributed import LazyClips, segment_many_sharded, segment_sharded
+    from whisperseg_b200.frontend import FrontendPlan
+    desc, sr, sts, seconds, seed, num_trials, kw = CONFIGS[config]
     base = make_audio(seconds, sr, seed=seed)
     plan = FrontendPlan(sr, sts, MIN_FREQ)
     common = dict(min_frequency=MIN_FREQ, spec_time_step=sts, max_length=args.max_length, num_trials=num_trials, num_beams=1, **kw)
-    if args.config == "cfg5":
+    if config == "cfg5":
         rng = np.random.default_rng(seed)
         durations = rng.uniform(0.5, 30.0, size=args.clips)
         lengths = (durations * sr).astype(np.int64)
@@ -647,16 +658,14 @@ def run_config(args):
         value = audio_seconds * args.steps / dt
         emit(dict(metric="audio-sec/sec", value=value, unit="audio-s/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                   ms_per_step=1000.0 * dt / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
-                  data="synthetic", config=dict(workload=desc, config=args.config, arch=args.arch, windows=n_windows,
+                  data="synthetic", config=dict(workload=desc, config=config, arch=args.arch, windows=n_windows,
                                                 audio_seconds=audio_seconds, max_length=args.max_length, max_batch=args.max_batch,
-                                                clips=args.clips if args.config == "cfg5" else None,
+                                                clips=args.clips if config == "cfg5" else None,
                                                 weights="seeded shaped random-init (stress recipe)",
                                                 timing="wall clock around synchronised public-API calls, host audio in, segments out"),
                   e2e=dict(value=value, unit="audio-s/s", h2d_bytes_per_step=int(audio_seconds * sr * 4 / world),
                            d2h_bytes_per_step=int(n_windows * (args.max_length - PROMPT_LEN) * 4 / world), segments=n_seg),
                   gpu_launches=int(lib.wsb_launch_count(0)), clocks=clocks))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 _REAL_STDOUT = None
@@ -688,7 +697,7 @@ def main():
     ap.add_argument("--ref-windows", type=int, default=4, dest="ref_windows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-beam", action="store_true", dest="no_beam")
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--config", default="cfg2", help="cfg2 (default, the driver's workload) or a comma-separated list of cfg3, cfg4, cfg5")
     ap.add_argument("--clips", type=int, default=10000, help="cfg5: number of clips in the folder")
     ap.add_argument("--max-batch", type=int, default=240, dest="max_batch")
     args = ap.parse_args()

@@ -164,10 +164,18 @@ def segment_files(segmenter, paths, workers=4, group_seconds=1800.0, **segment_k
             per_file[path] = pred
 
     with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
-        futures = [pool.submit(load_audio, p) for p in paths]
+        # bounded decode-ahead: at most 2 x workers files are decoded (or being decoded) beyond the one being consumed,
+        # so host memory holds one group plus that window -- not the whole folder (the reference streams file by file,
+        # scripts/segment.py:48-55)
+        ahead = max(2, 2 * max(1, workers))
+        pending = {}
+        next_submit = 0
         group, group_sr, seconds = [], None, 0.0
-        for path, fut in zip(paths, futures):
-            audio, sr = fut.result()
+        for k, path in enumerate(paths):
+            while next_submit < len(paths) and next_submit < k + ahead:
+                pending[next_submit] = pool.submit(load_audio, paths[next_submit])
+                next_submit += 1
+            audio, sr = pending.pop(k).result()
             if group and (sr != group_sr or seconds + len(audio) / sr > group_seconds):
                 flush(group, group_sr)
                 group, seconds = [], 0.0
