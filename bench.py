@@ -335,6 +335,8 @@ def run_ours(args):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.lean:
+        torch.cuda.profiler.start()                      # ncu --profile-from-start off: only the timed steps are captured
     ev0.record()
     steps_done = []
     for _ in range(args.steps):
@@ -342,6 +344,8 @@ def run_ours(args):
         steps_done.append(n_steps)
     ev1.record()
     barrier()
+    if args.lean:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop()
     launches = int(lib.wsb_launch_count(0))
     dt_ms = ev0.elapsed_time(ev1)
