@@ -148,6 +148,8 @@ struct Model {
     bool use_cluster = false;           // 65..256 decode rows: cluster split-K linear layers with folded LayerNorm (skinny.cu);
                                         // opt-in (WSB_CLUSTER=1): parity-green, but measured 0-4 % slower than the split-K pair
     bool use_fold = true;               // ... with the LayerNorm folded into the projection when the folded tensors exist
+    int wide_direct_bn = 128;           // > 64 rows: qkv / cross-q / fc1 as single full-K launches with this block_n (one fp32 plane, or
+                                        // bias + GELU in the GEMM epilogue) instead of split-K planes + a second phase; WSB_WIDE_DIRECT=0: off
     bool use_mega = false;              // <= 64 rows: one persistent kernel per decoder position (mega.cu); opt-in (WSB_MEGA=1):
                                         // bit-identical tokens, but measured 3x SLOWER than the launch-per-layer path
     void* mega_layers = nullptr;        // device table of the folded linear layers (null: folded tensors missing / unsupported width)
@@ -455,9 +457,14 @@ static int encode(Model* m, const float* feats, int B, float* hidden_f32, cudaSt
 //   mode 0: out_bf16 = act(sum + bias)         mode 1: x += sum + bias; xn = LayerNorm(x) (if gamma)
 static int skinny_linear(Model* m, const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, int B, int N, int K,
                          int gelu, __nv_bfloat16* out_bf16, float* x, const float* gamma, const float* beta,
-                         __nv_bfloat16* xn, cudaStream_t s, const unsigned char* row_skip, SplitkInput* planes_only = nullptr) {
+                         __nv_bfloat16* xn, cudaStream_t s, const unsigned char* row_skip, SplitkInput* planes_only = nullptr,
+                         int force_bn = 0) {
     int bn = 128, splits = 1;
     gemm_pick_skinny(B, N, K, &bn, &splits);
+    if (force_bn > 0) {                                 // one full-K tile per CTA: a single fp32 plane, no cross-CTA sum
+        bn = force_bn;
+        splits = 1;
+    }
     const int64_t plane = static_cast<int64_t>(B) * N;
     WSB_REQUIRE(static_cast<size_t>(plane) * splits <= m->dpart_floats, "split-K workspace too small");
     {
@@ -685,20 +692,42 @@ static int decode_layers_splitk(const StepCtx& x) {
         const float* next_g = (l + 1 < L) ? m->dec[l + 1].ln1_g : m->dec_ln_g;
         const float* next_b = (l + 1 < L) ? m->dec[l + 1].ln1_b : m->dec_ln_b;
         SplitkInput part;
-        WSB_RUN(skinny_linear(m, m->dxn, e.sqkv_w, e.sqkv_b, B, 3 * d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, fin, &part));
+        WSB_RUN(skinny_linear(m, m->dxn, e.sqkv_w, e.sqkv_b, B, 3 * d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, fin, &part,
+                              m->wide_direct_bn));
         {
             ProfScope ps(PROF_DEC_SELF_ATTN, 0.0, s);
             WSB_RUN(decode_self_attention(nullptr, &part, d, st.k_cache + l * cache_l, st.v_cache + l * cache_l, tmax, m->step, 0,
                                           fin, m->datt, B, H, s, st.anc, st.anc_ld));
         }
         WSB_RUN(skinny_linear(m, m->datt, e.so_w, e.so_b, B, d, d, 0, nullptr, m->dx, e.ln2_g, e.ln2_b, m->dxn, s, fin));
-        WSB_RUN(skinny_linear(m, m->dxn, e.cq_w, e.cq_b, B, d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, fin, &part));
+        WSB_RUN(skinny_linear(m, m->dxn, e.cq_w, e.cq_b, B, d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, fin, &part,
+                              m->wide_direct_bn ? 32 : 0));
         {
             ProfScope ps(PROF_DEC_CROSS_ATTN, 4.0 * B * H * T * 64.0, s);   // bytes: K and V blocks, bf16
             WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s, st.kv_div));
         }
         WSB_RUN(skinny_linear(m, m->datt, e.co_w, e.co_b, B, d, d, 0, nullptr, m->dx, e.ln3_g, e.ln3_b, m->dxn, s, fin));
-        WSB_RUN(skinny_linear(m, m->dxn, e.fc1_w, e.fc1_b, B, F, d, 1, m->dff, nullptr, nullptr, nullptr, nullptr, s, fin));
+        if (m->wide_direct_bn) {
+            // fc1 as ONE launch: full-K tiles, bias + GELU + bf16 in the GEMM epilogue (no split-K planes, no second phase)
+            ProfScope ps(PROF_DEC_GEMM, 2.0 * B * F * d, s);
+            GemmArgs g;
+            g.A = m->dxn;
+            g.lda = d;
+            g.W = e.fc1_w;
+            g.M = B;
+            g.N = F;
+            g.K = d;
+            g.bias = e.fc1_b;
+            g.act = GEMM_ACT_GELU;
+            g.out = m->dff;
+            g.ldc = F;
+            g.out_mode = GEMM_OUT_BF16;
+            g.block_n = m->wide_direct_bn;
+            g.row_skip = fin;
+            WSB_RUN(gemm_bf16(g, s));
+        } else {
+            WSB_RUN(skinny_linear(m, m->dxn, e.fc1_w, e.fc1_b, B, F, d, 1, m->dff, nullptr, nullptr, nullptr, nullptr, s, fin));
+        }
         WSB_RUN(skinny_linear(m, m->dff, e.fc2_w, e.fc2_b, B, d, F, 0, nullptr, m->dx, next_g, next_b, m->dxn, s, fin));
     }
     return 0;
@@ -826,6 +855,11 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     m->use_fold = std::getenv("WSB_NO_FOLD") == nullptr && !(m->fold_guard && m->fold_disabled);
     m->use_cluster = std::getenv("WSB_CLUSTER") != nullptr;
     m->use_mega = std::getenv("WSB_MEGA") != nullptr && std::getenv("WSB_NO_MEGA") == nullptr;
+    m->wide_direct_bn = 128;
+    if (const char* e = std::getenv("WSB_WIDE_DIRECT")) {
+        const int v = std::atoi(e);
+        m->wide_direct_bn = (v == 32 || v == 64 || v == 128 || v == 256) ? v : 0;
+    }
     // Two persistent decode kernels on one device could starve each other (each needs every SM to make progress):
     // generate() calls that may launch them are serialised per device and drain their stream before returning.
     int cur_dev = 0;
@@ -910,7 +944,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     auto get_graph = [&](const DecState& cur, Model::GraphEntry** out) -> int {
         const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 32 * m->gemv_rows + (m->use_fold ? 4096 : 0) : 16) + (m->use_cluster ? 8192 : 0) +
                                                     (m->use_pdl ? 16384 : 0) + (m->use_fold && m->fold_guard ? 32768 : 0) + (m->use_mega ? 65536 : 0) +
-                                                    (std::getenv("WSB_ATTN_THREADS") ? 131072 : 0),
+                                                    (std::getenv("WSB_ATTN_THREADS") ? 131072 : 0) + m->wide_direct_bn * 262144,
                                          cur.row_map != nullptr ? 1 : 0, max_new,
                                          prompt_len, eos_id, pad_id);
         auto it = m->graphs.find(key);
