@@ -150,6 +150,7 @@ struct Model {
     bool use_fold = true;               // ... with the LayerNorm folded into the projection when the folded tensors exist
     int wide_direct_bn = 128;           // > 64 rows: qkv / cross-q / fc1 as single full-K launches with this block_n (one fp32 plane, or
                                         // bias + GELU in the GEMM epilogue) instead of split-K planes + a second phase; WSB_WIDE_DIRECT=0: off
+    int wide_direct_resid = 0;          // > 64 rows: self-out / cross-out as one full-K launch (block_n) + LayerNorm kernel (WSB_WIDE_DIRECT_RESID)
     bool use_mega = false;              // <= 64 rows: one persistent kernel per decoder position (mega.cu); opt-in (WSB_MEGA=1):
                                         // bit-identical tokens, but measured 3x SLOWER than the launch-per-layer path
     void* mega_layers = nullptr;        // device table of the folded linear layers (null: folded tensors missing / unsupported width)
@@ -699,14 +700,27 @@ static int decode_layers_splitk(const StepCtx& x) {
             WSB_RUN(decode_self_attention(nullptr, &part, d, st.k_cache + l * cache_l, st.v_cache + l * cache_l, tmax, m->step, 0,
                                           fin, m->datt, B, H, s, st.anc, st.anc_ld));
         }
-        WSB_RUN(skinny_linear(m, m->datt, e.so_w, e.so_b, B, d, d, 0, nullptr, m->dx, e.ln2_g, e.ln2_b, m->dxn, s, fin));
+        if (m->wide_direct_resid) {
+            // out-projection as one full-K launch with the in-place residual epilogue, then a plain LayerNorm
+            WSB_RUN(linear(m->datt, e.so_w, e.so_b, B, d, d, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s, m->wide_direct_resid, PROF_DEC_GEMM));
+            ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
+            WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln2_g, e.ln2_b, m->dxn, nullptr, B, d, s));
+        } else {
+            WSB_RUN(skinny_linear(m, m->datt, e.so_w, e.so_b, B, d, d, 0, nullptr, m->dx, e.ln2_g, e.ln2_b, m->dxn, s, fin));
+        }
         WSB_RUN(skinny_linear(m, m->dxn, e.cq_w, e.cq_b, B, d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, fin, &part,
                               m->wide_direct_bn ? 32 : 0));
         {
             ProfScope ps(PROF_DEC_CROSS_ATTN, 4.0 * B * H * T * 64.0, s);   // bytes: K and V blocks, bf16
             WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s, st.kv_div));
         }
-        WSB_RUN(skinny_linear(m, m->datt, e.co_w, e.co_b, B, d, d, 0, nullptr, m->dx, e.ln3_g, e.ln3_b, m->dxn, s, fin));
+        if (m->wide_direct_resid) {
+            WSB_RUN(linear(m->datt, e.co_w, e.co_b, B, d, d, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s, m->wide_direct_resid, PROF_DEC_GEMM));
+            ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
+            WSB_RUN(layernorm_f32_to_bf16(m->dx, e.ln3_g, e.ln3_b, m->dxn, nullptr, B, d, s));
+        } else {
+            WSB_RUN(skinny_linear(m, m->datt, e.co_w, e.co_b, B, d, d, 0, nullptr, m->dx, e.ln3_g, e.ln3_b, m->dxn, s, fin));
+        }
         if (m->wide_direct_bn) {
             // fc1 as ONE launch: full-K tiles, bias + GELU + bf16 in the GEMM epilogue (no split-K planes, no second phase)
             ProfScope ps(PROF_DEC_GEMM, 2.0 * B * F * d, s);
@@ -855,6 +869,11 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     m->use_fold = std::getenv("WSB_NO_FOLD") == nullptr && !(m->fold_guard && m->fold_disabled);
     m->use_cluster = std::getenv("WSB_CLUSTER") != nullptr;
     m->use_mega = std::getenv("WSB_MEGA") != nullptr && std::getenv("WSB_NO_MEGA") == nullptr;
+    m->wide_direct_resid = 0;
+    if (const char* e = std::getenv("WSB_WIDE_DIRECT_RESID")) {
+        const int v = std::atoi(e);
+        m->wide_direct_resid = (v == 32 || v == 64 || v == 128) ? v : 0;
+    }
     m->wide_direct_bn = 128;
     if (const char* e = std::getenv("WSB_WIDE_DIRECT")) {
         const int v = std::atoi(e);
@@ -944,7 +963,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     auto get_graph = [&](const DecState& cur, Model::GraphEntry** out) -> int {
         const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 32 * m->gemv_rows + (m->use_fold ? 4096 : 0) : 16) + (m->use_cluster ? 8192 : 0) +
                                                     (m->use_pdl ? 16384 : 0) + (m->use_fold && m->fold_guard ? 32768 : 0) + (m->use_mega ? 65536 : 0) +
-                                                    (std::getenv("WSB_ATTN_THREADS") ? 131072 : 0) + m->wide_direct_bn * 262144,
+                                                    (std::getenv("WSB_ATTN_THREADS") ? 131072 : 0) + m->wide_direct_bn * 262144 + m->wide_direct_resid * 1000003,
                                          cur.row_map != nullptr ? 1 : 0, max_new,
                                          prompt_len, eos_id, pad_id);
         auto it = m->graphs.find(key);
