@@ -387,6 +387,28 @@ def run_ours(args):
                               algorithmic_bytes_per_launch=lm_bytes,
                               note="compute-co-limited: %.0f FLOP/B with a radix FFT (SURVEY 7.2-5)" %
                                    (plan.logmel_flops_per_window() / plan.logmel_bytes_per_window()))}
+    # the same kernel on the 16 kHz / hop-160 / n_fft-512 front-end (cfg1 / cfg4: 14 FLOP/B, the plausibly bandwidth-bound case)
+    try:
+        plan16 = FrontendPlan(16000, 0.01, MIN_FREQ)
+        a16 = torch.from_numpy(make_audio(600.0, 16000, seed=4)).to(dev)
+        w16 = plan16.windows(a16.numel(), 1)
+        d16 = eng.window_descriptors(w16, 0, a16.numel())
+        t16 = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(eng.stream)
+            eng.logmel.run(plan16, a16, d16, len(w16), eng.stream)
+            b.record(eng.stream)
+            eng.stream.synchronize()
+            t16.append(a.elapsed_time(b))
+        ms16 = float(np.median(t16[1:]))
+        by16 = plan16.logmel_bytes_per_window() * len(w16)
+        kernels["logmel_16k_hop160"] = dict(bound="hbm", achieved=by16 / ms16 / 1e6, peak=pk["hbm"], unit="GB/s",
+                                            frac=by16 / ms16 / 1e6 / pk["hbm"], ms_per_launch=ms16, launches=1,
+                                            algorithmic_bytes_per_launch=by16, note="%d windows of 160 000 samples" % len(w16))
+        del a16, d16
+    except Exception as e:  # noqa: BLE001
+        kernels["logmel_16k_hop160"] = dict(error=str(e))
     # decode kernel classes: eager (graph-free) teacher-forced pass so every row stays active
     lib.wsb_profile_enable(1)
     forced = torch.full((n_win, args.max_length), tok.eos_token_id, dtype=torch.int32, device=dev)

@@ -67,6 +67,44 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
+// ---- register-resident FFT for M = 256 / 512 complex points per frame (n_fft 512 / 1024: every configuration up to 80 kHz)
+// Cooley-Tukey M = 32 x R: lane n1 holds the R points x[n1 + 32 n2]; an R-point DIF in registers, one twiddle
+// W_M^(n1 k2), a 32-point DIF ACROSS the lanes with shuffles (5 stages), and the spectrum is written once, transposed and
+// padded, for the real-FFT untangle.  Two shared-memory exchanges per frame instead of the Stockham path's five passes
+// with two barriers each (round-1 ncu: 179 M shared-memory bank conflicts per launch, IPC 0.9).
+__device__ constexpr float kCos16[16] = {1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f, 0.0f,
+                                         -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f, -1.0f,
+                                         -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f, 0.0f,
+                                         0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f};
+__device__ constexpr float kSin16[16] = {0.0f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f, 1.0f,
+                                         0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f, 0.0f,
+                                         -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f, -1.0f,
+                                         -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f};
+__host__ __device__ constexpr int bitrev(int v, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+// in-register R-point DIF (radix 2): v[i] <- X[bitrev(i)]
+template <int R>
+__device__ __forceinline__ void fft_dif_registers(float2 (&v)[R]) {
+#pragma unroll
+    for (int h = R / 2; h >= 1; h >>= 1) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            if ((i & h) == 0) {
+                const float2 a = v[i], b = v[i + h];
+                v[i] = make_float2(a.x + b.x, a.y + b.y);
+                const float2 dlt = make_float2(a.x - b.x, a.y - b.y);
+                const int k16 = (i & (h - 1)) * (8 / h);            // exp(-2 pi i t / (2h)) = (cos, -sin)(2 pi k16 / 16)
+                if (k16 == 0) v[i + h] = dlt;
+                else if (k16 == 4) v[i + h] = make_float2(dlt.y, -dlt.x);
+                else v[i + h] = make_float2(dlt.x * kCos16[k16] + dlt.y * kSin16[k16], dlt.y * kCos16[k16] - dlt.x * kSin16[k16]);
+            }
+        }
+    }
+}
+
 // Compile-time shape of the per-frame FFT: M = n_fft/2 complex points handled by a group of G threads
 // (a warp up to n_fft 1024; larger groups beyond), NB radix-4 butterflies per thread and pass.
 template <int LOG2M>
@@ -190,6 +228,15 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
     float2* buf = reinterpret_cast<float2*>(s_fft + g * C::GROUP_FLOATS);
     float* power = reinterpret_cast<float*>(buf + C::MPAD);
     float vmax = -INFINITY, vmin = INFINITY;
+    // twiddles of the cross-lane DIF stages (register FFT path): exp(-2 pi i (lane mod h) / (2h)), h = 16, 8, 4, 2, 1
+    float2 lane_tw[5];
+#pragma unroll
+    for (int st = 0; st < 5; ++st) {
+        const int h = 16 >> st;
+        float sn, cs;
+        sincospif(static_cast<float>(gt & (h - 1)) / static_cast<float>(h), &sn, &cs);
+        lane_tw[st] = make_float2(cs, -sn);
+    }
     const int iters = (nf + C::NGROUPS - 1) / C::NGROUPS;
     constexpr int Q = M / 4;
 
@@ -197,105 +244,172 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
     for (int it = 0; it < iters; ++it) {
         const int fl = it * C::NGROUPS + g;              // frame index local to this CTA
         const bool active = fl < nf;
-        // window + pack: z[j] = x[2j] w[2j] + i x[2j+1] w[2j+1]
-        if (active) {
-            const float* x = s_samples + fl * p.hop;
-            const bool x_aligned = ((fl * p.hop) & 1) == 0;       // warp-uniform
-#pragma unroll
-            for (int i = 0; i < M / G; ++i) {
-                const int j = gt + i * G;
-                const float2 h = reinterpret_cast<const float2*>(hann)[j];
-                float2 xv;
-                if (x_aligned) {
-                    xv = reinterpret_cast<const float2*>(x)[j];
-                } else {
-                    xv = make_float2(x[2 * j], x[2 * j + 1]);
-                }
-                buf[fpad(j)] = make_float2(xv.x * h.x, xv.y * h.y);
-            }
-        }
-        group_sync<G>(g);
-        // In-place Stockham passes: every thread pulls the inputs of all its butterflies into registers,
-        // the group synchronises, then the outputs are scattered -- one M-point buffer per frame group.
-        if constexpr (LOG2M & 1) {                       // one radix-2 pass first when log2(M) is odd
-            float2 u[2 * NB][2];
+        if constexpr (LOG2M == 8 || LOG2M == 9) {
+            constexpr int R = M / 32, LOGR = LOG2M - 5;
+            // transposed, padded spectrum: Z[R k1 + k2] lives at zt[k2 * 33 + k1]
+            float2* zt = buf;
             if (active) {
+                const float* x = s_samples + fl * p.hop;
+                const bool x_aligned = ((fl * p.hop) & 1) == 0;       // warp-uniform
+                float2 v[R];
 #pragma unroll
-                for (int i = 0; i < 2 * NB; ++i) {
-                    const int j = gt + i * G;
-                    u[i][0] = buf[fpad(j)];
-                    u[i][1] = buf[fpad(j + M / 2)];
+                for (int n2 = 0; n2 < R; ++n2) {
+                    const int j = gt + 32 * n2;
+                    const float2 h = reinterpret_cast<const float2*>(hann)[j];
+                    const float2 xv = x_aligned ? reinterpret_cast<const float2*>(x)[j] : make_float2(x[2 * j], x[2 * j + 1]);
+                    v[n2] = make_float2(xv.x * h.x, xv.y * h.y);
                 }
-            }
-            group_sync<G>(g);
-            if (active) {
+                fft_dif_registers<R>(v);
 #pragma unroll
-                for (int i = 0; i < 2 * NB; ++i) {
-                    const int j = gt + i * G;
-                    buf[fpad(2 * j)] = make_float2(u[i][0].x + u[i][1].x, u[i][0].y + u[i][1].y);
-                    buf[fpad(2 * j + 1)] = make_float2(u[i][0].x - u[i][1].x, u[i][0].y - u[i][1].y);
+                for (int i = 1; i < R; ++i) {                          // W_M^(n1 k2), k2 = bitrev(i); tw[] holds W_(2M)^j, j < 3M/2
+                    constexpr int kk = 0;
+                    (void)kk;
+                    int e = gt * bitrev(i, LOGR);
+                    const bool neg = e >= M / 2;
+                    if (neg) e -= M / 2;
+                    float2 w = tw[2 * e];
+                    if (neg) w = make_float2(-w.x, -w.y);
+                    v[i] = cmul(v[i], w);
                 }
-            }
-            group_sync<G>(g);
-        }
 #pragma unroll
-        for (int lg = (LOG2M & 1); lg < LOG2M; lg += 2) {      // radix-4 passes, ns = 2^lg
-            const int ns = 1 << lg;
-            const int tw_stride = N_FFT / (ns * 4);
-            float2 v[NB][4];
-            if (active) {
+                for (int h = 16; h >= 1; h >>= 1) {                    // 32-point DIF across the lanes
+                    const bool upper = (gt & h) != 0;
+                    const float2 wl = lane_tw[h == 16 ? 0 : h == 8 ? 1 : h == 4 ? 2 : h == 2 ? 3 : 4];
 #pragma unroll
-                for (int i = 0; i < NB; ++i) {
-                    const int j = gt + i * G;
-                    v[i][0] = buf[fpad(j)];
-                    v[i][1] = buf[fpad(j + Q)];
-                    v[i][2] = buf[fpad(j + 2 * Q)];
-                    v[i][3] = buf[fpad(j + 3 * Q)];
-                }
-            }
-            group_sync<G>(g);
-            if (active) {
-#pragma unroll
-                for (int i = 0; i < NB; ++i) {
-                    const int j = gt + i * G;
-                    const int k = j & (ns - 1);
-                    float2 v1 = v[i][1], v2 = v[i][2], v3 = v[i][3];
-                    if (lg > 0) {                              // ns == 1: all twiddles are 1
-                        v1 = cmul(v1, tw[k * tw_stride]);
-                        v2 = cmul(v2, tw[2 * k * tw_stride]);
-                        v3 = cmul(v3, tw[3 * k * tw_stride]);
+                    for (int i = 0; i < R; ++i) {
+                        const float ox = __shfl_xor_sync(0xffffffffu, v[i].x, h);
+                        const float oy = __shfl_xor_sync(0xffffffffu, v[i].y, h);
+                        if (upper) {
+                            const float2 dlt = make_float2(ox - v[i].x, oy - v[i].y);
+                            v[i] = (h == 1) ? dlt : cmul(dlt, wl);
+                        } else {
+                            v[i] = make_float2(v[i].x + ox, v[i].y + oy);
+                        }
                     }
-                    const float2 v0 = v[i][0];
-                    const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
-                    const float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
-                    const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
-                    const float2 a3 = make_float2(v1.y - v3.y, v3.x - v1.x);       // (v1 - v3) * (-i)
-                    const int j0 = ((j - k) << 2) + k;
-                    buf[fpad(j0)] = make_float2(a0.x + a2.x, a0.y + a2.y);
-                    buf[fpad(j0 + ns)] = make_float2(a1.x + a3.x, a1.y + a3.y);
-                    buf[fpad(j0 + 2 * ns)] = make_float2(a0.x - a2.x, a0.y - a2.y);
-                    buf[fpad(j0 + 3 * ns)] = make_float2(a1.x - a3.x, a1.y - a3.y);
+                }
+                const int k1 = bitrev(gt, 5);
+#pragma unroll
+                for (int i = 0; i < R; ++i) zt[bitrev(i, LOGR) * 33 + k1] = v[i];
+            }
+            group_sync<G>(g);
+            if (active) {                                              // real-FFT untangle + power spectrum: P[k], k = 0..M
+#pragma unroll
+                for (int i = 0; i <= M / G; ++i) {
+                    const int k = gt + i * G;
+                    if (i < M / G || k == M) {
+                        const int ka = k & (M - 1), kb = (M - k) & (M - 1);
+                        const float2 zk = zt[(ka & (R - 1)) * 33 + (ka >> LOGR)];
+                        const float2 zm = zt[(kb & (R - 1)) * 33 + (kb >> LOGR)];
+                        const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                        const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));   // (zk - conj zm)/(2i)
+                        const float2 t = cmul(o, tw[k]);
+                        const float re = e.x + t.x, im = e.y + t.y;
+                        power[k] = re * re + im * im;
+                    }
+                }
+            }
+            group_sync<G>(g);
+        } else {
+            // window + pack: z[j] = x[2j] w[2j] + i x[2j+1] w[2j+1]
+            if (active) {
+                const float* x = s_samples + fl * p.hop;
+                const bool x_aligned = ((fl * p.hop) & 1) == 0;       // warp-uniform
+    #pragma unroll
+                for (int i = 0; i < M / G; ++i) {
+                    const int j = gt + i * G;
+                    const float2 h = reinterpret_cast<const float2*>(hann)[j];
+                    float2 xv;
+                    if (x_aligned) {
+                        xv = reinterpret_cast<const float2*>(x)[j];
+                    } else {
+                        xv = make_float2(x[2 * j], x[2 * j + 1]);
+                    }
+                    buf[fpad(j)] = make_float2(xv.x * h.x, xv.y * h.y);
+                }
+            }
+            group_sync<G>(g);
+            // In-place Stockham passes: every thread pulls the inputs of all its butterflies into registers,
+            // the group synchronises, then the outputs are scattered -- one M-point buffer per frame group.
+            if constexpr (LOG2M & 1) {                       // one radix-2 pass first when log2(M) is odd
+                float2 u[2 * NB][2];
+                if (active) {
+    #pragma unroll
+                    for (int i = 0; i < 2 * NB; ++i) {
+                        const int j = gt + i * G;
+                        u[i][0] = buf[fpad(j)];
+                        u[i][1] = buf[fpad(j + M / 2)];
+                    }
+                }
+                group_sync<G>(g);
+                if (active) {
+    #pragma unroll
+                    for (int i = 0; i < 2 * NB; ++i) {
+                        const int j = gt + i * G;
+                        buf[fpad(2 * j)] = make_float2(u[i][0].x + u[i][1].x, u[i][0].y + u[i][1].y);
+                        buf[fpad(2 * j + 1)] = make_float2(u[i][0].x - u[i][1].x, u[i][0].y - u[i][1].y);
+                    }
+                }
+                group_sync<G>(g);
+            }
+    #pragma unroll
+            for (int lg = (LOG2M & 1); lg < LOG2M; lg += 2) {      // radix-4 passes, ns = 2^lg
+                const int ns = 1 << lg;
+                const int tw_stride = N_FFT / (ns * 4);
+                float2 v[NB][4];
+                if (active) {
+    #pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        const int j = gt + i * G;
+                        v[i][0] = buf[fpad(j)];
+                        v[i][1] = buf[fpad(j + Q)];
+                        v[i][2] = buf[fpad(j + 2 * Q)];
+                        v[i][3] = buf[fpad(j + 3 * Q)];
+                    }
+                }
+                group_sync<G>(g);
+                if (active) {
+    #pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        const int j = gt + i * G;
+                        const int k = j & (ns - 1);
+                        float2 v1 = v[i][1], v2 = v[i][2], v3 = v[i][3];
+                        if (lg > 0) {                              // ns == 1: all twiddles are 1
+                            v1 = cmul(v1, tw[k * tw_stride]);
+                            v2 = cmul(v2, tw[2 * k * tw_stride]);
+                            v3 = cmul(v3, tw[3 * k * tw_stride]);
+                        }
+                        const float2 v0 = v[i][0];
+                        const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
+                        const float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+                        const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+                        const float2 a3 = make_float2(v1.y - v3.y, v3.x - v1.x);       // (v1 - v3) * (-i)
+                        const int j0 = ((j - k) << 2) + k;
+                        buf[fpad(j0)] = make_float2(a0.x + a2.x, a0.y + a2.y);
+                        buf[fpad(j0 + ns)] = make_float2(a1.x + a3.x, a1.y + a3.y);
+                        buf[fpad(j0 + 2 * ns)] = make_float2(a0.x - a2.x, a0.y - a2.y);
+                        buf[fpad(j0 + 3 * ns)] = make_float2(a1.x - a3.x, a1.y - a3.y);
+                    }
+                }
+                group_sync<G>(g);
+            }
+            // real-FFT untangle + power spectrum: P[k], k = 0..M
+            if (active) {
+    #pragma unroll
+                for (int i = 0; i <= M / G; ++i) {
+                    const int k = gt + i * G;
+                    if (i < M / G || k == M) {
+                        const float2 zk = buf[fpad(k & (M - 1))];
+                        const float2 zm = buf[fpad((M - k) & (M - 1))];
+                        const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                        const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));   // (zk - conj zm)/(2i)
+                        const float2 t = cmul(o, tw[k]);
+                        const float re = e.x + t.x, im = e.y + t.y;
+                        power[k] = re * re + im * im;
+                    }
                 }
             }
             group_sync<G>(g);
         }
-        // real-FFT untangle + power spectrum: P[k], k = 0..M
-        if (active) {
-#pragma unroll
-            for (int i = 0; i <= M / G; ++i) {
-                const int k = gt + i * G;
-                if (i < M / G || k == M) {
-                    const float2 zk = buf[fpad(k & (M - 1))];
-                    const float2 zm = buf[fpad((M - k) & (M - 1))];
-                    const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-                    const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));   // (zk - conj zm)/(2i)
-                    const float2 t = cmul(o, tw[k]);
-                    const float re = e.x + t.x, im = e.y + t.y;
-                    power[k] = re * re + im * im;
-                }
-            }
-        }
-        group_sync<G>(g);
         // sparse mel: each thread owns filters gt, gt+G, ... (<= 2 triangles per FFT bin, CSR rows)
         if (active) {
             for (int m = gt; m < kMels; m += G) {
