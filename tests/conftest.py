@@ -26,3 +26,15 @@ def tiny_checkpoint(tmp_path_factory):
         sr=16000, min_frequency=0, spec_time_step=0.01, species="human"))
     synth.save_checkpoint(hf, path)
     return path, hf
+
+
+@pytest.fixture(scope="session")
+def tiny_confident_checkpoint(tmp_path_factory):
+    """The same architecture with the "confident" recipe (peaked logits, tools/synth.py: script_vectors): comparisons
+    between two bf16 code paths are then about the kernels, not about which near-tie of a Gaussian logit vector flips."""
+    from tools import synth
+    path = str(tmp_path_factory.mktemp("ckpt_tiny_confident"))
+    hf = synth.make_hf_model("tiny", seed=0, confident=True, default_segmentation_config=dict(
+        sr=16000, min_frequency=0, spec_time_step=0.01, species="human"))
+    synth.save_checkpoint(hf, path)
+    return path, hf

@@ -215,7 +215,8 @@ def test_batch_compaction_equals_uncompacted(tiny_checkpoint, monkeypatch):
 
 
 @pytest.mark.parametrize("seconds,max_batch", [(13.0, 16), (29.0, 32), (45.0, 64), (85.0, 96)])
-def test_small_batch_linear_path_matches_tensor_core_path(tiny_checkpoint, monkeypatch, seconds, max_batch):
+@pytest.mark.parametrize("recipe", ["stress", "confident"])
+def test_small_batch_linear_path_matches_tensor_core_path(tiny_checkpoint, tiny_confident_checkpoint, monkeypatch, seconds, max_batch, recipe):
     """Batches of 65..256 rows can run one cluster split-K launch per linear layer (skinny.cu, opt-in with WSB_CLUSTER=1:
     the 85-window case) and
     batches of <= 64 rows (1, 2 or 4 m-tiles of 16) run the fused mma.sync linear kernels (gemv.cu) instead of the
@@ -224,12 +225,15 @@ def test_small_batch_linear_path_matches_tensor_core_path(tiny_checkpoint, monke
     noise of the same size.  Teacher-forced on the tensor-core path's own tokens, the per-position arg-max must agree
     on >= 98.5 % of the positions (near-ties of a random-init model flip; 99.0-99.1 % measured, 99.2-99.7 % with the
     exact on-the-fly LayerNorm, WSB_NO_FOLD=1), and the free-running outputs of most rows must be identical.  Parity
-    of this path against the fp32 oracle is asserted by the teacher-forced tests above (they run <= 64 rows)."""
+    of this path against the fp32 oracle is asserted by the teacher-forced tests above (they run <= 64 rows).
+    On the "confident" recipe (peaked logits) the two paths must agree on >= 99.9 % of the positions; on the "stress"
+    recipe (Gaussian logits: 10 % of the positions are near-ties) the agreement is a noise measurement, >= 97 %."""
     import torch
     from tools import synth
     from whisperseg_b200.frontend import FrontendPlan
     from whisperseg_b200.segmenter import WhisperSegmenter
-    seg = WhisperSegmenter(tiny_checkpoint[0], device="cuda", device_ids=[0], max_batch=max_batch)
+    ckpt = tiny_checkpoint if recipe == "stress" else tiny_confident_checkpoint
+    seg = WhisperSegmenter(ckpt[0], device="cuda", device_ids=[0], max_batch=max_batch)
     eng, tok = seg.engines[0], seg.tokenizer
     sr, sts = 16000, 0.001
     audio = synth.synth_audio(seconds, sr, seed=23)
@@ -256,6 +260,8 @@ def test_small_batch_linear_path_matches_tensor_core_path(tiny_checkpoint, monke
     tensor_core_path(True)
     tf_old, _ = eng.generate(n, tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length, forced=forced, use_graph=False)
     agree = (tf_new == tf_old).float().mean().item()
-    print("small-batch path: %d windows, free-running rows identical %.3f, teacher-forced arg-max agreement %.4f" % (n, same_rows, agree))
-    assert agree >= 0.985
-    assert same_rows >= 0.75
+    print("small-batch path [%s]: %d windows, free-running rows identical %.3f, teacher-forced arg-max agreement %.4f" % (recipe, n, same_rows, agree))
+    if recipe == "confident":
+        assert agree >= 0.999 and same_rows >= 0.95
+    else:
+        assert agree >= 0.97 and same_rows >= 0.6

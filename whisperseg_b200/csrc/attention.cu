@@ -17,12 +17,19 @@
 
 namespace wsb {
 
+#ifndef WSB_ATT_POLY_MASK
+#define WSB_ATT_POLY_MASK 2          // pairs whose index has these bits set use the polynomial exp2 (2 = every second pair; 64 = none)
+#endif
 constexpr int kAttThreads = 512;    // four warps per TMEM lane quarter: each owns a quarter of the key columns
 constexpr int kAttQ = 128;          // query rows per tile
 constexpr int kAttKeys = 512;       // padded key count
 constexpr int kHd = 64;
 constexpr int kAttChunk = 128;      // keys per P tile / PV MMA group
 constexpr int kAttSmem = (kAttQ * kHd + 2 * kAttKeys * kHd + 2 * kAttQ * kAttChunk) * 2 + 1024 + 128;
+
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    return (static_cast<unsigned long long>(__float_as_uint(hi)) << 32) | __float_as_uint(lo);
+}
 
 // One CTA per (head, window): K and V are loaded once and shared by all query tiles; Q tiles are
 // double-buffered; TMEM (512 columns) is allocated once.
@@ -37,11 +44,13 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     unsigned char* sP = sV + kAttKeys * kHd * 2;                // 2 x 32 KB (each: two 128x64 swizzled sub-tiles)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kAttQ * kAttChunk * 2);
     uint64_t* bar_kv = bars;
-    uint64_t* bar_q = bars + 1;                                 // (+1 spare)
+    uint64_t* bar_q = bars + 1;
+    uint64_t* bar_v = bars + 2;                                 // V arrives after K: S = Q K^T starts as soon as K and Q are in
     uint64_t* bar_s = bars + 3;
     uint64_t* bar_p = bars + 4;                                 // [2] P buffer consumed by the tensor core
     uint64_t* bar_o = bars + 6;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint64_t* bar_ready = bars + 7;                             // [2] every warp has written its part of the P buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int quarter = warp & 3, colgrp = warp >> 2;   // TMEM lanes 32*quarter.., key-column group (0..3)
@@ -54,11 +63,13 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         tma_prefetch_desc(&tm_kv);
         mbar_init(bar_kv, 1);
         mbar_init(&bar_q[0], 1);
-        mbar_init(&bar_q[1], 1);
+        mbar_init(bar_v, 1);
         mbar_init(bar_s, 1);
         mbar_init(&bar_p[0], 1);
         mbar_init(&bar_p[1], 1);
         mbar_init(bar_o, 1);
+        mbar_init(&bar_ready[0], kAttThreads / 32);
+        mbar_init(&bar_ready[1], kAttThreads / 32);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -68,15 +79,24 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     const uint32_t tmem = *tmem_slot;
 
     if (tid == 0) {
-        mbar_arrive_expect_tx(bar_kv, 2 * kAttKeys * kHd * 2);
+        mbar_arrive_expect_tx(bar_kv, kAttKeys * kHd * 2);
         tma_load_3d(sK, &tm_kv, bar_kv, d + h * kHd, 0, b);
         tma_load_3d(sK + 256 * kHd * 2, &tm_kv, bar_kv, d + h * kHd, 256, b);
-        tma_load_3d(sV, &tm_kv, bar_kv, 2 * d + h * kHd, 0, b);
-        tma_load_3d(sV + 256 * kHd * 2, &tm_kv, bar_kv, 2 * d + h * kHd, 256, b);
         mbar_arrive_expect_tx(bar_q, kAttQ * kHd * 2);
         tma_load_3d(sQ, &tm_q, bar_q, h * kHd, 0, b);
+        mbar_arrive_expect_tx(bar_v, kAttKeys * kHd * 2);
+        tma_load_3d(sV, &tm_kv, bar_v, 2 * d + h * kHd, 0, b);
+        tma_load_3d(sV + 256 * kHd * 2, &tm_kv, bar_v, 2 * d + h * kHd, 256, b);
     }
 
+#ifdef WSB_ATT_TRACE
+    unsigned long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    unsigned long long t_prev = now();
+#define ATT_STAMP(i) do { const unsigned long long t_ = now(); tr[i] += t_ - t_prev; t_prev = t_; } while (0)
+#else
+#define ATT_STAMP(i) do { } while (0)
+#endif
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
     constexpr float kLog2e = 1.4426950408889634f;
     const int row = tid & (kAttQ - 1);                     // query row within the tile == TMEM lane
@@ -98,8 +118,10 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             }
             umma_commit(bar_s);
         }
+        ATT_STAMP(0);                                       // loop top -> S MMAs issued (incl. K/V / Q load waits)
         mbar_wait(bar_s, qt & 1);
         tc_fence_after();
+        ATT_STAMP(1);                                       // S = Q K^T complete
         if (tid == 0 && qt + 1 < n_qt) {                   // S is in TMEM: the Q buffer is free, prefetch the next tile
             mbar_arrive_expect_tx(bar_q, kAttQ * kHd * 2);
             tma_load_3d(sQ, &tm_q, bar_q, h * kHd, (qt + 1) * kAttQ, b);
@@ -126,36 +148,77 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         __syncthreads();
         rmax = fmaxf(fmaxf(s_xchg[0][row], s_xchg[1][row]), fmaxf(s_xchg[2][row], s_xchg[3][row]));
         const float mscaled = rmax * kLog2e;
+        ATT_STAMP(2);                                       // pass 1 (row max)
 
-        // pass 2: P chunks + PV MMAs
-        float rsum = 0.0f;
-#pragma unroll 1
+        // pass 2: P chunks + PV MMAs.  The TMEM columns of chunk c + 1 are requested before chunk c is exponentiated, the
+        // scale and the row sum run as packed f32x2 instructions (FFMA2 / FADD2), and the warps hand their part of the P
+        // buffer over with an mbarrier arrive instead of a CTA-wide barrier (only the MMA-issuing thread waits for the slowest).
+        unsigned long long rsum2 = 0ull;                       // (sum of even columns, sum of odd columns)
+        uint32_t rnext[32];
+        tmem_ld_32x32(lane_base + colgrp * 32, rnext);
+        const float nm = -mscaled;
+        const unsigned long long scale2 = pack_f32x2(kLog2e, kLog2e), shift2 = pack_f32x2(nm, nm);
+        // every second pair of columns takes its exponential as a degree-3 polynomial (relative error 8e-4, below the bf16
+        // rounding of P) so that the MUFU pipe -- 16 ex2 per clock and SM, the floor of this pass -- carries half the load
+        constexpr int kPolyMask = WSB_ATT_POLY_MASK;
+        const unsigned long long kMagic2 = pack_f32x2(12582912.0f, 12582912.0f), kNegMagic2 = pack_f32x2(-12582912.0f, -12582912.0f);
+        const unsigned long long kNegOne2 = pack_f32x2(-1.0f, -1.0f), kOne2 = pack_f32x2(1.0f, 1.0f);
+        const unsigned long long kC3 = pack_f32x2(0.05550411f, 0.05550411f), kC2 = pack_f32x2(0.24022651f, 0.24022651f);
+        const unsigned long long kC1 = pack_f32x2(0.69314718f, 0.69314718f);
+#pragma unroll
         for (int c = 0; c < kAttKeys / kAttChunk; ++c) {
             const int buf = c & 1;
             const int use = qt * (kAttKeys / kAttChunk / 2) + (c >> 1);  // how many times this buffer was used before
-            if (use > 0) mbar_wait(&bar_p[buf], (use - 1) & 1);
             // this warp's 32 of the chunk's 128 keys: sub-tile (64 keys) colgrp>>1, 32-key half colgrp&1
             unsigned char* pbuf = sP + buf * kAttQ * kAttChunk * 2 + (colgrp >> 1) * kAttQ * kHd * 2 + row * 128;
             {
                 const int hlf = colgrp & 1;
                 uint32_t r[32];
-                tmem_ld_32x32(lane_base + c * kAttChunk + colgrp * 32, r);
                 tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = rnext[i];
+                if (c + 1 < kAttKeys / kAttChunk) tmem_ld_32x32(lane_base + (c + 1) * kAttChunk + colgrp * 32, rnext);
                 const int n0 = c * kAttChunk + colgrp * 32;
                 float pv[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float e;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(__uint_as_float(r[i]), kLog2e, -mscaled)));
-                    pv[i] = e;
+                for (int i = 0; i < 32; i += 2) {
+                    unsigned long long x2;
+                    const unsigned long long s2 = (static_cast<unsigned long long>(r[i + 1]) << 32) | r[i];
+                    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x2) : "l"(s2), "l"(scale2), "l"(shift2));
+                    float e0, e1;
+                    if ((i & kPolyMask) == kPolyMask) {
+                        // this pair on the FMA / integer pipes: 2^x = 2^n * p(f), n = round(x), f = x - n in [-0.5, 0.5]
+                        const float a0 = fmaxf(__uint_as_float(static_cast<uint32_t>(x2)), -125.0f);
+                        const float a1 = fmaxf(__uint_as_float(static_cast<uint32_t>(x2 >> 32)), -125.0f);
+                        const unsigned long long a2 = pack_f32x2(a0, a1);
+                        unsigned long long t2, n2, f2, p2;
+                        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t2) : "l"(a2), "l"(kMagic2));
+                        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(n2) : "l"(t2), "l"(kNegMagic2));
+                        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(f2) : "l"(n2), "l"(kNegOne2), "l"(a2));
+                        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(kC3), "l"(f2), "l"(kC2));
+                        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(p2), "l"(f2), "l"(kC1));
+                        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(p2), "l"(f2), "l"(kOne2));
+                        e0 = __int_as_float(static_cast<int>(static_cast<uint32_t>(p2)) + ((static_cast<int>(static_cast<uint32_t>(t2)) - 0x4B400000) << 23));
+                        e1 = __int_as_float(static_cast<int>(static_cast<uint32_t>(p2 >> 32)) + ((static_cast<int>(static_cast<uint32_t>(t2 >> 32)) - 0x4B400000) << 23));
+                    } else {
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(__uint_as_float(static_cast<uint32_t>(x2))));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(__uint_as_float(static_cast<uint32_t>(x2 >> 32))));
+                    }
+                    pv[i] = e0;
+                    pv[i + 1] = e1;
                 }
-                if (n0 + 32 > T) {
+                if (n0 + 32 > T) {                             // warp-uniform: only the warps that straddle T mask anything
+                    asm volatile("" ::: "memory");             // (keeps this a branch: if-converted it costs every warp 64 instructions per chunk)
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (n0 + i >= T) pv[i] = 0.0f;
                 }
 #pragma unroll
-                for (int i = 0; i < 32; ++i) rsum += pv[i];
+                for (int i = 0; i < 32; i += 2) {
+                    const unsigned long long p2 = pack_f32x2(pv[i], pv[i + 1]);
+                    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(rsum2) : "l"(p2));
+                }
+                if (use > 0) mbar_wait(&bar_p[buf], (use - 1) & 1);     // the tensor core is done with this P buffer
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {                  // four 16-byte chunks of this 32-key half
                     uint4 pk;
@@ -169,8 +232,11 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             }
             fence_proxy_async_smem();                          // generic-proxy smem writes -> visible to the MMA
             tc_fence_before();
-            __syncthreads();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&bar_ready[buf]);
             if (tid == 0) {
+                mbar_wait(&bar_ready[buf], use & 1);
+                if (qt == 0 && c == 0) mbar_wait(bar_v, 0);
                 tc_fence_after();
                 constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);     // B (= V) is MN-major
                 const uint64_t dv = umma_desc_mn_sw128(smem_u32(sV + c * kAttChunk * kHd * 2));
@@ -184,8 +250,11 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
                 if (c == kAttKeys / kAttChunk - 1) umma_commit(bar_o);
             }
         }
+        const float rsum = __uint_as_float(static_cast<uint32_t>(rsum2)) + __uint_as_float(static_cast<uint32_t>(rsum2 >> 32));
+        ATT_STAMP(3);                                       // pass 2 (exp, P, PV issue)
         mbar_wait(bar_o, qt & 1);
         tc_fence_after();
+        ATT_STAMP(4);                                       // last PV MMAs complete
 
         // epilogue: O / rowsum (row sums of the two column halves are combined through shared memory)
         __syncthreads();                                       // s_xchg was last read right after pass 1
@@ -214,7 +283,13 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         // the next tile's S MMA overwrites the TMEM columns O was just read from
         tc_fence_before();
         __syncthreads();
+        ATT_STAMP(5);                                       // epilogue
     }
+#ifdef WSB_ATT_TRACE
+    if (tid == 0 && blockIdx.x == 3 && blockIdx.y == 7)
+        printf("attention trace (ns, thread 0, 4 tiles): wait-loads+issue S %llu | S mma %llu | pass1 %llu | pass2 %llu | PV tail %llu | epilogue %llu\n",
+               tr[0], tr[1], tr[2], tr[3], tr[4], tr[5]);
+#endif
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
