@@ -169,6 +169,7 @@ struct Model {
     std::map<std::tuple<int, int, int, int, int, int, int>, GraphEntry> beam_graphs;
 };
 
+constexpr size_t kMaxCachedGraphs = 48;   // instantiated decode-step graphs kept per model (each distinct batch size x ladder level is one)
 constexpr int kCompactRows = 64;        // first compaction level; the second level (16 rows) reuses the main buffers
 
 // the per-row decode state a step works on (main buffers, or a compacted copy)
@@ -983,6 +984,11 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
             entry.kernels = kernels;
             WSB_CHECK_CUDA(cudaGraphInstantiate(&entry.exec, g, 0));
             cudaGraphDestroy(g);
+            if (m->graphs.size() >= kMaxCachedGraphs) {      // folder mode with many tail batch sizes: bound the cache
+                WSB_CHECK_CUDA(cudaStreamSynchronize(s));
+                for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
+                m->graphs.clear();
+            }
             it = m->graphs.emplace(key, entry).first;
         }
         *out = &it->second;

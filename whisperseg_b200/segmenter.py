@@ -111,23 +111,36 @@ class SegmenterBase:
         return [(w.trial_id, w.offset_time, feats[i], w.clip_seconds) for i, w in enumerate(wins)]
 
     def _generate_on(self, eng, feats, max_length, status_monitor, texts_out, slot, num_beams=1, length_penalty=1.0):
-        """feats: device tensor [n,80,cols] on eng.device -> list of decoded strings."""
+        """feats: device tensor [n,80,cols] on eng.device -> list of decoded strings.  The ids of chunk i are copied
+        to the host and turned into text on a worker thread while the GPU already runs chunk i + 1 (the reference
+        decodes text between two generate() calls, model.py:667-668)."""
+        from concurrent.futures import ThreadPoolExecutor
         tok = self.tokenizer
-        texts, n = [], feats.shape[0]
+        n = feats.shape[0]
         steps = 0
         per_call = eng.max_batch if num_beams == 1 else max(1, eng.max_batch // num_beams)
-        for pos in range(0, n, per_call):
-            chunk = feats[pos:pos + per_call].contiguous()
-            eng.encode(chunk)
-            if num_beams == 1:
-                ids, n_steps = eng.generate(chunk.shape[0], tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length)
-            else:
-                ids, n_steps = eng.generate_beam(chunk.shape[0], num_beams, tok.prompt_ids, tok.eos_token_id,
-                                                 tok.pad_token_id, max_length, length_penalty)
-            steps += n_steps
-            texts += tok.batch_decode(ids.cpu().numpy())
-            if status_monitor is not None:                                       # model.py:672-674
-                status_monitor["progress"] = int(100 * min(1, (pos + per_call) / max(n, 1)))
+
+        def to_text(ids, done):
+            done.synchronize()
+            return tok.batch_decode(ids.cpu().numpy())
+
+        pending = []
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            for pos in range(0, n, per_call):
+                chunk = feats[pos:pos + per_call].contiguous()
+                eng.encode(chunk)
+                if num_beams == 1:
+                    ids, n_steps = eng.generate(chunk.shape[0], tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, max_length)
+                else:
+                    ids, n_steps = eng.generate_beam(chunk.shape[0], num_beams, tok.prompt_ids, tok.eos_token_id,
+                                                     tok.pad_token_id, max_length, length_penalty)
+                steps += n_steps
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(eng.device))
+                pending.append(pool.submit(to_text, ids, done))
+                if status_monitor is not None:                                       # model.py:672-674
+                    status_monitor["progress"] = int(100 * min(1, (pos + per_call) / max(n, 1)))
+            texts = [t for fut in pending for t in fut.result()]
         texts_out[slot] = texts
         self.last_stats["decode_steps"] = self.last_stats.get("decode_steps", 0) + steps
 
