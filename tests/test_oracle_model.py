@@ -197,3 +197,27 @@ def test_beam_oracle_matches_hf_generate(eos_scale, length_penalty, max_length):
     assert n >= out.shape[1] - 1
     assert torch.equal(out[:, :n], out_hf[:, :n])
     assert (out[:, n:] == synth.ID_EOT).all()
+
+
+def test_token_table_reads_the_published_checkpoints_tokenizer_layout(tiny, tmp_path):
+    """The published checkpoints (nccratliri/whisperseg-*) ship the slow-tokenizer trio -- vocab.json + added_tokens.json
+    (+ merges.txt, tokenizer_config.json), no tokenizer.json -- with `<|0|>..<|1000|>` and the species tokens appended after
+    the multilingual Whisper vocabulary (reference model.py:111-113).  Same ids and strings as the tokenizer.json form."""
+    import json
+    from whisperseg_b200.tokens import TokenTable
+    full = json.load(open(os.path.join(tiny["path"], "tokenizer.json")))
+    added = {a["content"]: a["id"] for a in full["added_tokens"]}
+    pieces = {k: v for k, v in full["model"]["vocab"].items() if k not in added}
+    legacy = tmp_path / "legacy"
+    legacy.mkdir()
+    json.dump(pieces, open(legacy / "vocab.json", "w"))
+    json.dump(added, open(legacy / "added_tokens.json", "w"))
+    json.dump({"pad_token": "<|endoftext|>", "eos_token": {"content": "<|endoftext|>"}}, open(legacy / "tokenizer_config.json", "w"))
+    a = TokenTable.from_pretrained(tiny["path"])
+    b = TokenTable.from_pretrained(str(legacy))
+    assert (a.prompt_ids, a.eos_token_id, a.pad_token_id) == (b.prompt_ids, b.eos_token_id, b.pad_token_id)
+    assert b.convert_tokens_to_ids(["<|0|>", "<|1000|>"]) == [synth.ID_TS0, synth.ID_TS0 + 1000]
+    rng = np.random.default_rng(1)
+    rows = rng.integers(0, 51372, size=(8, 40)).astype(np.int32)
+    rows[:, 30:] = synth.ID_EOT
+    assert a.batch_decode(rows) == b.batch_decode(rows)
