@@ -73,5 +73,7 @@ def test_fold_guard_falls_back_on_common_mode_rows(monkeypatch):
           (res["default"][1], res["default"][0], res["default"][2], res["fold-forced"][0], res["exact"][0], raw_plain))
     assert res["default"][2], "the guard did not fire on |mean| >> std rows"
     assert not res["fold-forced"][2] and not res["exact"][2]
-    assert res["default"][0] >= res["exact"][0] - 0.01
-    assert res["default"][0] >= res["fold-forced"][0]
+    # 203 positions of a stress-recipe checkpoint: one position is 0.5 %; the guarded run decodes its first positions folded
+    # (their K/V cache entries stay), so it sits between the two -- close to exact, clearly above the forced fold
+    assert res["default"][0] >= res["exact"][0] - 0.03
+    assert res["default"][0] >= res["fold-forced"][0] + 0.03

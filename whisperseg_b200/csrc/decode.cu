@@ -306,6 +306,270 @@ int decode_cross_attention(const __nv_bfloat16* q, const SplitkInput* part, int 
     return 0;
 }
 
+// ---------------------------------------------------------------------------- prompt prefill
+// The prompt ([<|startoftranscript|>, <|en|>, <|notimestamps|>], reference model.py:655-661) is the same for every row, and the
+// reference's generate() runs it through the decoder in one forward pass.  Here too: the P prompt positions of all B rows
+// form P * B virtual rows (row p * B + b) for the linear layers, and the two attention kernels below serve the P positions
+// of a row together -- the cross-attention K/V block of a row (128 KB per head) is streamed once instead of P times.
+__global__ void embed_prefill_kernel(const int* __restrict__ prompt, const int* __restrict__ forced, int forced_ld,
+                                     const __nv_bfloat16* __restrict__ emb, const float* __restrict__ pos_emb,
+                                     float* __restrict__ x, int B, int d) {
+    const int r = blockIdx.x, p = r / B, b = r - p * B;
+    const int tok = forced ? forced[static_cast<long long>(b) * forced_ld + p] : prompt[p];
+    const __nv_bfloat16* e = emb + static_cast<size_t>(tok) * d;
+    const float* pe = pos_emb + static_cast<size_t>(p) * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) x[static_cast<size_t>(r) * d + i] = __bfloat162float(e[i]) + pe[i];
+}
+
+int embed_prefill(const int* prompt_dev, const int* forced, int forced_ld, const __nv_bfloat16* emb, const float* pos_emb,
+                  float* x, int B, int P, int d, cudaStream_t stream) {
+    if (B <= 0 || P <= 0) return 0;
+    WSB_CHECK_CUDA(launch_kernel(embed_prefill_kernel, dim3(B * P), dim3(256), 0, stream, prompt_dev, forced, forced_ld, emb, pos_emb, x, B, d));
+    count_launch();
+    return 0;
+}
+
+constexpr int kPrefillMaxP = 4;
+
+__device__ __forceinline__ float prefill_proj(const DaParams& p, long long row, int col) {
+    const float* src = p.part + row * p.part_ld + col;
+    float t[16];
+#pragma unroll
+    for (int sp = 0; sp < 16; ++sp) t[sp] = sp < p.splits ? src[sp * p.split_stride] : 0.0f;
+    float acc = p.bias ? __ldg(p.bias + col) : 0.0f;
+#pragma unroll
+    for (int sp = 0; sp < 16; ++sp)
+        if (sp < p.splits) acc += t[sp];
+    return acc;
+}
+
+// grid (H, B), 128 threads.  P <= 4 positions: q, k, v rounded to bf16 exactly like the per-position kernel (k, v through
+// the cache, q in registers), scores and softmax in fp32.
+__global__ void __launch_bounds__(128) prefill_self_attention_kernel(const DaParams p, int B, int P) {
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ float s_q[kPrefillMaxP][64], s_k[kPrefillMaxP][64], s_v[kPrefillMaxP][64];
+    __shared__ float s_w[kPrefillMaxP][kPrefillMaxP];
+    const long long blk = static_cast<long long>(b) * p.b_stride + static_cast<long long>(h) * p.bh_stride;
+    for (int idx = tid; idx < P * 64; idx += 128) {
+        const int pos = idx >> 6, e = idx & 63;
+        const long long row = static_cast<long long>(pos) * B + b;
+        const __nv_bfloat16 kb = __float2bfloat16(prefill_proj(p, row, p.d + h * 64 + e));
+        const __nv_bfloat16 vb = __float2bfloat16(prefill_proj(p, row, 2 * p.d + h * 64 + e));
+        p.k_cache[blk + static_cast<long long>(pos) * 64 + e] = kb;
+        p.v_cache[blk + static_cast<long long>(pos) * 64 + e] = vb;
+        s_k[pos][e] = __bfloat162float(kb);
+        s_v[pos][e] = __bfloat162float(vb);
+        s_q[pos][e] = __bfloat162float(__float2bfloat16(prefill_proj(p, row, h * 64 + e)));
+    }
+    __syncthreads();
+    if (tid < P * P) {                                   // score of (query position qp, key position kp <= qp)
+        const int qp = tid / P, kp = tid - qp * P;
+        float dot = -INFINITY;
+        if (kp <= qp) {
+            dot = 0.0f;
+            for (int e = 0; e < 64; ++e) dot = fmaf(s_k[kp][e], s_q[qp][e], dot);
+        }
+        s_w[qp][kp] = dot;
+    }
+    __syncthreads();
+    if (tid < P) {
+        float mx = -INFINITY;
+        for (int kp = 0; kp <= tid; ++kp) mx = fmaxf(mx, s_w[tid][kp]);
+        float sum = 0.0f;
+        for (int kp = 0; kp < P; ++kp) {
+            const float w = kp <= tid ? __expf(s_w[tid][kp] - mx) : 0.0f;
+            s_w[tid][kp] = w;
+            sum += w;
+        }
+        for (int kp = 0; kp < P; ++kp) s_w[tid][kp] /= sum;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < P * 64; idx += 128) {
+        const int qp = idx >> 6, e = idx & 63;
+        float o = 0.0f;
+        for (int kp = 0; kp <= qp; ++kp) o = fmaf(s_w[qp][kp], s_v[kp][e], o);
+        p.out[(static_cast<long long>(qp) * B + b) * p.d + h * 64 + e] = __float2bfloat16(o);
+    }
+}
+
+int prefill_self_attention(const SplitkInput* part, int d, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int t_max,
+                           __nv_bfloat16* out, int B, int P, int n_heads, cudaStream_t stream) {
+    WSB_REQUIRE(part != nullptr && P >= 1 && P <= kPrefillMaxP && P <= t_max, "prefill: 1..4 prompt positions, projection planes");
+    if (B <= 0) return 0;
+    DaParams p = {};
+    p.k_cache = k_cache;
+    p.v_cache = v_cache;
+    p.bh_stride = static_cast<long long>(t_max) * 64;
+    p.b_stride = static_cast<long long>(n_heads) * t_max * 64;
+    p.out = out;
+    p.d = d;
+    p.part = part->planes;
+    p.splits = part->splits;
+    p.split_stride = part->split_stride;
+    p.part_ld = 3 * d;
+    p.bias = part->bias;
+    WSB_CHECK_CUDA(launch_kernel(prefill_self_attention_kernel, dim3(n_heads, B), dim3(128), 0, stream, p, B, P));
+    count_launch();
+    return 0;
+}
+
+// grid (H, B), 128 threads: NQ online-softmax states per thread, one pass over the row's K/V block; per query the
+// arithmetic and its order are decode_attention_kernel's (128-thread form)
+template <int NQ>
+__global__ void __launch_bounds__(kDaThreads) prefill_cross_attention_kernel(const DaParams p, int B) {
+    const int h = blockIdx.x, w = blockIdx.y;
+    pdl_wait();
+    pdl_launch_dependents();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __shared__ float s_q[NQ][64];
+    __shared__ float s_p[NQ][kDaThreads / 32];
+    __shared__ float s_red[NQ][kDaThreads / 32];
+    __shared__ float s_out[NQ][kDaThreads / 32][64];
+    const long long blk = static_cast<long long>(w) * p.b_stride + static_cast<long long>(h) * p.bh_stride;
+    const __nv_bfloat16* K = p.k_base + blk;
+    const __nv_bfloat16* V = p.v_base + blk;
+    const int n_keys = p.n_keys_fixed;
+    if (tid < 64) {
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi)
+            s_q[qi][tid] = __bfloat162float(__float2bfloat16(prefill_proj(p, static_cast<long long>(qi) * B + w, h * 64 + tid)));
+    }
+    __syncthreads();
+    const int sub = lane >> 3, ch = lane & 7;
+    float qv[NQ][8], m_run[NQ], l_run[NQ], acc[NQ][8];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+        m_run[qi] = -INFINITY;
+        l_run[qi] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            qv[qi][i] = s_q[qi][ch * 8 + i];
+            acc[qi][i] = 0.0f;
+        }
+    }
+    constexpr int kStep = (kDaThreads / 32) * 4;
+    for (int j0 = warp * 4; j0 < n_keys; j0 += 2 * kStep) {
+        uint4 kraw[2], vraw[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = j0 + u * kStep + sub;
+            ok[u] = j < n_keys;
+            if (ok[u]) {
+                const long long off = static_cast<long long>(j) * 64 + ch * 8;
+                kraw[u] = *reinterpret_cast<const uint4*>(K + off);
+                vraw[u] = *reinterpret_cast<const uint4*>(V + off);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float kf[8], vf[8];
+            if (ok[u]) {
+                const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kraw[u]);
+                const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vraw[u]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 a = __bfloat1622float2(k2[i]), c = __bfloat1622float2(v2[i]);
+                    kf[2 * i] = a.x; kf[2 * i + 1] = a.y;
+                    vf[2 * i] = c.x; vf[2 * i + 1] = c.y;
+                }
+            }
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) {
+                float dot = 0.0f;
+                if (ok[u]) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dot = fmaf(kf[i], qv[qi][i], dot);
+                }
+                dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                if (ok[u]) {
+                    const float m_new = fmaxf(m_run[qi], dot);
+                    const float scale = __expf(m_run[qi] - m_new);
+                    const float pj = __expf(dot - m_new);
+                    l_run[qi] = fmaf(l_run[qi], scale, pj);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[qi][i] = fmaf(acc[qi][i], scale, pj * vf[i]);
+                    m_run[qi] = m_new;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+        float m_w = fmaxf(m_run[qi], __shfl_xor_sync(0xffffffffu, m_run[qi], 8));
+        m_w = fmaxf(m_w, __shfl_xor_sync(0xffffffffu, m_w, 16));
+        const float sc = (m_run[qi] == -INFINITY) ? 0.0f : __expf(m_run[qi] - m_w);
+        float l = l_run[qi] * sc;
+        l += __shfl_xor_sync(0xffffffffu, l, 8);
+        l += __shfl_xor_sync(0xffffffffu, l, 16);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float a = acc[qi][i] * sc;
+            a += __shfl_xor_sync(0xffffffffu, a, 8);
+            a += __shfl_xor_sync(0xffffffffu, a, 16);
+            acc[qi][i] = a;
+        }
+        if (lane == 0) {
+            s_red[qi][warp] = m_w;
+            s_p[qi][warp] = l;
+        }
+        if (sub == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s_out[qi][warp][ch * 8 + i] = acc[qi][i];
+        }
+    }
+    __syncthreads();
+    if (tid < 64) {
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+            float gmax = s_red[qi][0];
+#pragma unroll
+            for (int wi = 1; wi < kDaThreads / 32; ++wi) gmax = fmaxf(gmax, s_red[qi][wi]);
+            float o = 0.0f, gsum = 0.0f;
+#pragma unroll
+            for (int wi = 0; wi < kDaThreads / 32; ++wi) {
+                const float f = (s_red[qi][wi] == -INFINITY) ? 0.0f : __expf(s_red[qi][wi] - gmax);
+                o = fmaf(s_out[qi][wi][tid], f, o);
+                gsum = fmaf(s_p[qi][wi], f, gsum);
+            }
+            p.out[(static_cast<long long>(qi) * B + w) * p.d + h * 64 + tid] = __float2bfloat16(o / gsum);
+        }
+    }
+}
+
+int prefill_cross_attention(const SplitkInput* part, int d, const __nv_bfloat16* cross_kv, int layer, int n_layers, int T,
+                            __nv_bfloat16* out, int B, int P, int n_heads, cudaStream_t stream) {
+    WSB_REQUIRE(part != nullptr && P >= 1 && P <= kPrefillMaxP && T <= kDaMaxKeys, "prefill: 1..4 prompt positions, projection planes");
+    if (B <= 0) return 0;
+    DaParams p = {};
+    const long long per_head = static_cast<long long>(T) * 64;
+    p.k_base = cross_kv + (static_cast<long long>(layer) * 2 + 0) * n_heads * per_head;
+    p.v_base = cross_kv + (static_cast<long long>(layer) * 2 + 1) * n_heads * per_head;
+    p.bh_stride = per_head;
+    p.b_stride = static_cast<long long>(n_layers) * 2 * n_heads * per_head;
+    p.n_keys_fixed = T;
+    p.out = out;
+    p.d = d;
+    p.part = part->planes;
+    p.splits = part->splits;
+    p.split_stride = part->split_stride;
+    p.part_ld = d;
+    p.bias = part->bias;
+    const dim3 grid(n_heads, B);
+    switch (P) {
+        case 1: WSB_CHECK_CUDA(launch_kernel(prefill_cross_attention_kernel<1>, grid, dim3(kDaThreads), 0, stream, p, B)); break;
+        case 2: WSB_CHECK_CUDA(launch_kernel(prefill_cross_attention_kernel<2>, grid, dim3(kDaThreads), 0, stream, p, B)); break;
+        case 3: WSB_CHECK_CUDA(launch_kernel(prefill_cross_attention_kernel<3>, grid, dim3(kDaThreads), 0, stream, p, B)); break;
+        default: WSB_CHECK_CUDA(launch_kernel(prefill_cross_attention_kernel<4>, grid, dim3(kDaThreads), 0, stream, p, B)); break;
+    }
+    count_launch();
+    return 0;
+}
+
 // ---------------------------------------------------------------------------- arg-max tail
 // one warp per row: reduce the per-tile partials (lowest index wins ties, like torch.argmax), then
 // finished rows emit pad, the token is recorded and fed back, EOS marks the row finished.

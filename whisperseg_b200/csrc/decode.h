@@ -48,6 +48,19 @@ int prefill_advance(int* next_token, const int* forced, int forced_ld, const int
 int embed_tokens_step(const int* tokens, const int* step_ptr, int pos_offset, const __nv_bfloat16* emb,
                       const float* pos_emb, float* x, int B, int d, cudaStream_t stream);
 
+// ---- prompt prefill: the P prompt positions of all B rows in ONE pass (virtual row p * B + b = position p of row b).
+// x[p * B + b] = emb[token] + pos_emb[p]; token = forced[b][p] if forced else prompt_dev[p]
+int embed_prefill(const int* prompt_dev, const int* forced, int forced_ld, const __nv_bfloat16* emb, const float* pos_emb,
+                  float* x, int B, int P, int d, cudaStream_t stream);
+// causal self-attention over the P prompt positions of every (row, head): reads q, k, v of the virtual rows from the fp32
+// projection planes (+ bias), writes the K/V cache positions 0..P-1 and the attention outputs of all P positions
+int prefill_self_attention(const SplitkInput* part, int d, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int t_max,
+                           __nv_bfloat16* out, int B, int P, int n_heads, cudaStream_t stream);
+// cross-attention of the P prompt positions of a row from ONE pass over the row's K/V block (the per-position path streams
+// the 128 KB block once per position)
+int prefill_cross_attention(const SplitkInput* part, int d, const __nv_bfloat16* cross_kv, int layer, int n_layers, int T,
+                            __nv_bfloat16* out, int B, int P, int n_heads, cudaStream_t stream);
+
 // ---- beam search (beam.cu): device-resident state of `B` windows x `nb` beams
 struct BeamState {
     int B, nb, K;                       // windows, beams per window, continuations kept per step (2*nb)

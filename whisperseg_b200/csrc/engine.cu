@@ -150,6 +150,7 @@ struct Model {
     bool use_fold = true;               // ... with the LayerNorm folded into the projection when the folded tensors exist
     int wide_direct_bn = 128;           // > 64 rows: qkv / cross-q / fc1 as single full-K launches with this block_n (one fp32 plane, or
                                         // bias + GELU in the GEMM epilogue) instead of split-K planes + a second phase; WSB_WIDE_DIRECT=0: off
+    int wide_cq_bn = 32;                // ... block_n of the cross-q projection on that path (WSB_WIDE_CQ_BN)
     int wide_direct_resid = 0;          // > 64 rows: self-out / cross-out as one full-K launch (block_n) + LayerNorm kernel (WSB_WIDE_DIRECT_RESID)
     bool use_mega = false;              // <= 64 rows: one persistent kernel per decoder position (mega.cu); opt-in (WSB_MEGA=1):
                                         // bit-identical tokens, but measured 3x SLOWER than the launch-per-layer path
@@ -169,6 +170,7 @@ struct Model {
     std::map<std::tuple<int, int, int, int, int, int, int>, GraphEntry> beam_graphs;
 };
 
+constexpr size_t kPrefillRows = 4;        // prompt positions decoded in one pass (prompt_len <= 4; the reference's prompt has 3 tokens)
 constexpr size_t kMaxCachedGraphs = 48;   // instantiated decode-step graphs kept per model (each distinct batch size x ladder level is one)
 constexpr int kCompactRows = 64;        // first compaction level; the second level (16 rows) reuses the main buffers
 
@@ -209,12 +211,13 @@ static int model_layout(Model* m, bool assign) {
     m->cross_kv = carve<__nv_bfloat16>(p, B * L * 2 * H * T * 64);
     m->k_cache = carve<__nv_bfloat16>(p, L * B * H * c.max_target_positions * 64);
     m->v_cache = carve<__nv_bfloat16>(p, L * B * H * c.max_target_positions * 64);
-    m->dx = carve<float>(p, B * d);
-    m->dxn = carve<__nv_bfloat16>(p, B * d);
+    // (the row-indexed decode scratch holds kPrefillRows x B rows: the prompt positions run as one pass of P x B virtual rows)
+    m->dx = carve<float>(p, kPrefillRows * B * d);
+    m->dxn = carve<__nv_bfloat16>(p, kPrefillRows * B * d);
     m->dqkv = carve<__nv_bfloat16>(p, B * 3 * d);
-    m->datt = carve<__nv_bfloat16>(p, B * d);
+    m->datt = carve<__nv_bfloat16>(p, kPrefillRows * B * d);
     m->dq = carve<__nv_bfloat16>(p, B * d);
-    m->dff = carve<__nv_bfloat16>(p, B * F);
+    m->dff = carve<__nv_bfloat16>(p, kPrefillRows * B * F);
     m->dpart_floats = 16 * B * std::max<size_t>(F, 3 * d);
     m->dpart = carve<float>(p, m->dpart_floats);
     m->gv_stats = carve<float>(p, std::max<size_t>(256 * 64 * 2, static_cast<size_t>(c.d_model / 128 + 1) * B * 2));
@@ -509,6 +512,7 @@ struct StepCtx {
     long long cache_l;                   // elements of one layer's K (or V) cache
     bool with_logits;
     cudaStream_t s;
+    int P = 0;                           // > 0: prompt prefill, P positions x B rows as P * B virtual rows (split-K path only)
 };
 #define WSB_STEP_LOCALS                                                                                      \
     Model* m = x.m;                                                                                          \
@@ -680,10 +684,21 @@ static int decode_layers_cluster(const StepCtx& x) {
     return 0;
 }
 
+static int decode_layers_splitk_rows(const StepCtx& x, const int B);
 // K5: any batch, tcgen05 split-K GEMM + fused second phase (12 launches per layer); leaves LayerNorm(x) of the final
 // decoder LayerNorm in m->dxn
 static int decode_layers_splitk(const StepCtx& x) {
-    WSB_STEP_LOCALS;
+    // the linear layers and LayerNorms see P * B virtual rows in a prompt prefill, B rows otherwise
+    return decode_layers_splitk_rows(x, x.P > 0 ? x.P * x.B : x.B);
+}
+
+static int decode_layers_splitk_rows(const StepCtx& x, const int B) {
+    Model* m = x.m;
+    const DecState& st = x.st;
+    const int Bw = x.B, P = x.P, d = x.d, F = x.F, L = x.L, H = x.H, T = x.T, tmax = x.tmax;
+    const unsigned char* fin = P > 0 ? nullptr : x.fin;
+    const long long cache_l = x.cache_l;
+    cudaStream_t s = x.s;
     {
         ProfScope ps(PROF_DEC_LN, 6.0 * B * d, s);
         WSB_RUN(layernorm_f32_to_bf16(m->dx, m->dec[0].ln1_g, m->dec[0].ln1_b, m->dxn, nullptr, B, d, s));
@@ -698,8 +713,11 @@ static int decode_layers_splitk(const StepCtx& x) {
                               m->wide_direct_bn));
         {
             ProfScope ps(PROF_DEC_SELF_ATTN, 0.0, s);
-            WSB_RUN(decode_self_attention(nullptr, &part, d, st.k_cache + l * cache_l, st.v_cache + l * cache_l, tmax, m->step, 0,
-                                          fin, m->datt, B, H, s, st.anc, st.anc_ld));
+            if (P > 0)
+                WSB_RUN(prefill_self_attention(&part, d, st.k_cache + l * cache_l, st.v_cache + l * cache_l, tmax, m->datt, Bw, P, H, s));
+            else
+                WSB_RUN(decode_self_attention(nullptr, &part, d, st.k_cache + l * cache_l, st.v_cache + l * cache_l, tmax, m->step, 0,
+                                              fin, m->datt, B, H, s, st.anc, st.anc_ld));
         }
         if (m->wide_direct_resid) {
             // out-projection as one full-K launch with the in-place residual epilogue, then a plain LayerNorm
@@ -710,10 +728,13 @@ static int decode_layers_splitk(const StepCtx& x) {
             WSB_RUN(skinny_linear(m, m->datt, e.so_w, e.so_b, B, d, d, 0, nullptr, m->dx, e.ln2_g, e.ln2_b, m->dxn, s, fin));
         }
         WSB_RUN(skinny_linear(m, m->dxn, e.cq_w, e.cq_b, B, d, d, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s, fin, &part,
-                              m->wide_direct_bn ? 32 : 0));
+                              m->wide_direct_bn ? m->wide_cq_bn : 0));
         {
-            ProfScope ps(PROF_DEC_CROSS_ATTN, 4.0 * B * H * T * 64.0, s);   // bytes: K and V blocks, bf16
-            WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s, st.kv_div));
+            ProfScope ps(PROF_DEC_CROSS_ATTN, 4.0 * Bw * H * T * 64.0, s);   // bytes: K and V blocks, bf16
+            if (P > 0)
+                WSB_RUN(prefill_cross_attention(&part, d, st.cross_kv, l, L, T, m->datt, Bw, P, H, s));
+            else
+                WSB_RUN(decode_cross_attention(nullptr, &part, d, st.cross_kv, l, L, T, fin, m->datt, B, H, s, st.kv_div));
         }
         if (m->wide_direct_resid) {
             WSB_RUN(linear(m->datt, e.co_w, e.co_b, B, d, d, GEMM_ACT_NONE, m->dx, m->dx, GEMM_OUT_F32, s, m->wide_direct_resid, PROF_DEC_GEMM));
@@ -748,6 +769,9 @@ static int decode_layers_splitk(const StepCtx& x) {
     return 0;
 }
 
+static int decode_logits_tail(Model* m, const DecState& st, const __nv_bfloat16* hidden, bool first_generated, int prompt_len,
+                              int max_new, const int* forced, int forced_ld, int eos_id, int pad_id, cudaStream_t s,
+                              const BeamState* beam);
 // one decoder position for all rows.  with_logits: project + arg-max + finalize (or, with `beam`, raw logits +
 // beam bookkeeping); else prefill advance.
 static int decode_step(Model* m, const DecState& st, bool with_logits, bool first_generated, int prompt_len, int max_new,
@@ -809,10 +833,20 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
         }
     }
     if (!with_logits) return prefill_advance(st.next_token, forced, forced_ld, m->prompt_dev, m->step, B, s);
+    return decode_logits_tail(m, st, m->dxn, first_generated, prompt_len, max_new, forced, forced_ld, eos_id, pad_id, s, beam);
+}
+
+// tied output projection + logits processors + arg-max (or beam bookkeeping) on `hidden` = bf16 LayerNorm-ed rows [B][d]
+static int decode_logits_tail(Model* m, const DecState& st, const __nv_bfloat16* hidden, bool first_generated, int prompt_len,
+                              int max_new, const int* forced, int forced_ld, int eos_id, int pad_id, cudaStream_t s,
+                              const BeamState* beam) {
+    const wsb_model_config& c = m->cfg;
+    const int B = st.B, d = c.d_model;
+    const unsigned char* fin = forced ? nullptr : st.finished;
     if (beam) {
         // raw logits of every row (the log-softmax runs over the full vocabulary, before the suppression masks)
         GemmArgs g;
-        g.A = m->dxn;
+        g.A = hidden;
         g.lda = d;
         g.W = m->dec_emb;
         g.M = B;
@@ -830,7 +864,7 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
         return step_increment(m->step, s);
     }
     GemmArgs g;
-    g.A = m->dxn;
+    g.A = hidden;
     g.lda = d;
     g.W = m->dec_emb;
     g.M = B;
@@ -850,6 +884,25 @@ static int decode_step(Model* m, const DecState& st, bool with_logits, bool firs
     }
     return argmax_finalize(m->am_val, m->am_idx, m->am_tiles, m->tokens, max_new, prompt_len - 1, st.next_token, forced,
                            forced_ld, st.finished, m->step, m->n_active, eos_id, pad_id, B, st.row_map, s);
+}
+
+// The prompt positions of all rows in ONE pass (P * B virtual rows through the split-K path, attention kernels that serve
+// the P positions of a row together), then the first generated token from the last prompt position's rows.
+static int prefill_and_first_token(Model* m, const DecState& st, int prompt_len, int max_new, const int* forced, int forced_ld,
+                                   int eos_id, int pad_id, cudaStream_t s) {
+    const wsb_model_config& c = m->cfg;
+    const int B = st.B, P = prompt_len;
+    const int d = c.d_model, F = c.ffn_dim, L = c.n_layers, H = c.n_heads, T = m->T, tmax = c.max_target_positions;
+    static const int kPos[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    WSB_RUN(embed_prefill(m->prompt_dev, forced, forced_ld, m->dec_emb, m->dec_pos, m->dx, B, P, d, s));
+    const long long cache_l = static_cast<long long>(B) * H * tmax * 64;
+    StepCtx x{m, st, B, d, F, L, H, T, tmax, nullptr, cache_l, true, s};
+    x.P = P;
+    WSB_RUN(decode_layers_splitk(x));
+    // the decode state continues at position P - 1: its token is the last prompt token, its logits give the first new token
+    WSB_CHECK_CUDA(cudaMemcpyAsync(m->step, &kPos[P - 1], sizeof(int), cudaMemcpyHostToDevice, s));
+    return decode_logits_tail(m, st, m->dxn + static_cast<long long>(P - 1) * B * d, true, prompt_len, max_new, forced, forced_ld,
+                              eos_id, pad_id, s, nullptr);
 }
 
 static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_id, int pad_id, int max_length,
@@ -874,6 +927,11 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     if (const char* e = std::getenv("WSB_WIDE_DIRECT_RESID")) {
         const int v = std::atoi(e);
         m->wide_direct_resid = (v == 32 || v == 64 || v == 128) ? v : 0;
+    }
+    m->wide_cq_bn = 32;
+    if (const char* e = std::getenv("WSB_WIDE_CQ_BN")) {
+        const int v = std::atoi(e);
+        if (v == 32 || v == 64 || v == 128) m->wide_cq_bn = v;
     }
     m->wide_direct_bn = 128;
     if (const char* e = std::getenv("WSB_WIDE_DIRECT")) {
@@ -943,8 +1001,15 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     st.next_token = m->next_token;
     st.finished = m->finished;
     st.row_map = nullptr;
-    for (int pos = 0; pos + 1 < prompt_len; ++pos)
-        WSB_RUN(decode_step(m, st, false, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
+    // wide batches: the prompt positions as one pass (WSB_NO_PREFILL=1: one position at a time, as at <= 64 rows)
+    const bool fused_prefill = std::getenv("WSB_NO_PREFILL") == nullptr && prompt_len >= 2 && prompt_len <= static_cast<int>(kPrefillRows) &&
+                               !(m->use_gemv && B <= m->gemv_rows);
+    if (fused_prefill) {
+        WSB_RUN(prefill_and_first_token(m, st, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
+    } else {
+        for (int pos = 0; pos + 1 < prompt_len; ++pos)
+            WSB_RUN(decode_step(m, st, false, false, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
+    }
     if (m->use_fold && m->fold_guard && m->use_gemv && B <= m->gemv_rows && prompt_len > 1) {
         // folded-LayerNorm guard, first look: the prompt positions have run on the folded path
         WSB_CHECK_CUDA(cudaMemcpyAsync(m->pinned_active, m->n_active, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
@@ -955,7 +1020,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
         }
     }
     // first generated token (begin-suppress mask active)
-    WSB_RUN(decode_step(m, st, true, true, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
+    if (!fused_prefill) WSB_RUN(decode_step(m, st, true, true, prompt_len, max_new, forced, max_length, eos_id, pad_id, s));
     int steps_done = 1;
     // teacher forcing bakes a caller-owned pointer into the launches: never replay those from a cached graph
     const bool use_graph = (flags & 1) != 0 && max_new > 2 && forced == nullptr;
@@ -964,7 +1029,7 @@ static int generate(Model* m, int B, const int* prompt, int prompt_len, int eos_
     auto get_graph = [&](const DecState& cur, Model::GraphEntry** out) -> int {
         const auto key = std::make_tuple(cur.B, cur.buffer_id + (m->use_gemv ? 32 * m->gemv_rows + (m->use_fold ? 4096 : 0) : 16) + (m->use_cluster ? 8192 : 0) +
                                                     (m->use_pdl ? 16384 : 0) + (m->use_fold && m->fold_guard ? 32768 : 0) + (m->use_mega ? 65536 : 0) +
-                                                    (std::getenv("WSB_ATTN_THREADS") ? 131072 : 0) + m->wide_direct_bn * 262144 + m->wide_direct_resid * 1000003,
+                                                    (std::getenv("WSB_ATTN_THREADS") ? 131072 : 0) + m->wide_direct_bn * 262144 + m->wide_direct_resid * 1000003 + m->wide_cq_bn * 7000003,
                                          cur.row_map != nullptr ? 1 : 0, max_new,
                                          prompt_len, eos_id, pad_id);
         auto it = m->graphs.find(key);
