@@ -83,3 +83,52 @@ def test_reference_cli_calling_sequence(tmp_path, monkeypatch):
     # a hub id cannot be resolved offline: the error must say so instead of a bare missing-file error
     with pytest.raises(FileNotFoundError, match="Hugging Face hub id"):
         WhisperSegmenter("nccratliri/whisperseg-large-ms", device="cuda", device_ids=[0])
+
+
+def test_reference_service_calling_sequence(tmp_path, monkeypatch):
+    """The Flask handler of the reference's segment_service.py (:56-111), statement for statement, without Flask: a
+    base64 WAV (stereo here), `librosa.load(BytesIO, sr=sr, mono=False)`, channel pick, `segment(...)` with the request's
+    keys (num_trials defaults to 3 in the service, :72), result through json (jsonify) -- plain floats and strings."""
+    import base64
+    import json
+    from scipy.io import wavfile
+    from tools import synth
+    from whisperseg_b200 import audio_io
+    hf = synth.make_hf_model("tiny", seed=0, confident=True, default_segmentation_config=dict(
+        sr=16000, min_frequency=0, spec_time_step=0.01, species="human"))
+    model_path = synth.save_checkpoint(hf, str(tmp_path / "ckpt"))
+    left = synth.synth_audio(12.0, 16000, seed=81)
+    right = synth.synth_audio(12.0, 16000, seed=82)
+    wav = tmp_path / "stereo.wav"
+    wavfile.write(str(wav), 16000, (np.stack([left, right], axis=1) * 32767).astype(np.int16))
+    request_json = {"audio_file_base64_string": base64.b64encode(open(wav, "rb").read()).decode(), "sr": 16000,
+                    "min_frequency": None, "spec_time_step": None, "channel_id": 1}
+    librosa = types.ModuleType("librosa")
+    librosa.load = lambda src, sr=None, mono=True: audio_io.load_audio(src, sr=sr, mono=mono)
+    monkeypatch.setitem(sys.modules, "librosa", librosa)
+    monkeypatch.syspath_prepend(ROOT)
+    sys.modules.pop("model", None)
+    from model import WhisperSegmenter, WhisperSegmenterFast          # noqa: E402  (segment_service.py:10)
+    try:                                                              # segment_service.py:123-128
+        segmenter = WhisperSegmenterFast(model_path, device="cuda", device_ids=[0])
+    except Exception:  # noqa: BLE001
+        segmenter = WhisperSegmenter(model_path, device="cuda", device_ids=[0])
+    request_info = {k: v for k, v in request_json.items() if v is not None}
+    sr = request_info["sr"]
+    num_trials = request_info.get("num_trials", 3)
+    channel_id = request_info.get("channel_id", 0)
+    audio, _ = librosa.load(io.BytesIO(base64.b64decode(request_info["audio_file_base64_string"])), sr=sr, mono=False)
+    assert audio.ndim == 2 and audio.shape[0] == 2
+    audio = audio[channel_id]
+    prediction = segmenter.segment(audio, sr=sr, min_frequency=request_info.get("min_frequency"),
+                                   spec_time_step=request_info.get("spec_time_step"),
+                                   min_segment_length=request_info.get("min_segment_length"), eps=request_info.get("eps"),
+                                   num_trials=num_trials, batch_size=8)
+    body = json.loads(json.dumps(prediction))                         # jsonify(prediction)
+    assert set(body) == {"onset", "offset", "cluster"} and len(body["onset"]) == len(body["offset"]) == len(body["cluster"])
+    # same audio, same arguments, direct call: identical
+    again = segmenter.segment(np.ascontiguousarray(audio), sr, num_trials=3, batch_size=8)
+    assert again == prediction
+    # and the channel really was picked
+    other = segmenter.segment(np.ascontiguousarray(audio_io.load_audio(str(wav), sr=sr, mono=False)[0][0]), sr, num_trials=3)
+    assert isinstance(other["onset"], list)

@@ -265,3 +265,36 @@ def test_small_batch_linear_path_matches_tensor_core_path(tiny_checkpoint, tiny_
         assert agree >= 0.999 and same_rows >= 0.95
     else:
         assert agree >= 0.97 and same_rows >= 0.6
+
+
+def test_fused_prompt_prefill_matches_position_by_position(tiny_confident_checkpoint, monkeypatch):
+    """Above 64 rows the three prompt positions run as ONE pass (3 x B virtual rows, causal 3x3 self-attention, 3-query
+    cross-attention from one pass over a row's K/V block: engine.cu prefill_and_first_token) instead of three decoder
+    positions (WSB_NO_PREFILL=1).  Same network, different reduction orders in the two attention kernels: on the confident
+    checkpoint every generated token must be identical."""
+    import torch
+    from tools import synth
+    from whisperseg_b200.frontend import FrontendPlan
+    from whisperseg_b200.segmenter import WhisperSegmenter
+    seg = WhisperSegmenter(tiny_confident_checkpoint[0], device="cuda", device_ids=[0], max_batch=96)
+    eng, tok = seg.engines[0], seg.tokenizer
+    sr, sts = 16000, 0.001
+    audio = synth.synth_audio(90.0, sr, seed=37)
+    plan = FrontendPlan(sr, sts, 0)
+    wins = plan.windows(len(audio), 1)
+    assert len(wins) == 90
+    feats = eng.features(plan, audio, wins)
+    outs = {}
+    for mode in ("fused", "per-position"):
+        if mode == "per-position":
+            monkeypatch.setenv("WSB_NO_PREFILL", "1")
+        else:
+            monkeypatch.delenv("WSB_NO_PREFILL", raising=False)
+        eng.encode(feats)
+        ids, steps = eng.generate(len(wins), tok.prompt_ids, tok.eos_token_id, tok.pad_token_id, 64)
+        outs[mode] = (ids.cpu(), steps)
+    same_rows = (outs["fused"][0] == outs["per-position"][0]).all(dim=1).float().mean().item()
+    print("fused prefill vs position-by-position: %d windows, rows identical %.3f, positions %d / %d"
+          % (len(wins), same_rows, outs["fused"][1], outs["per-position"][1]))
+    assert same_rows >= 0.98
+    assert outs["fused"][1] == outs["per-position"][1]
