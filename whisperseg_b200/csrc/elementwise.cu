@@ -326,6 +326,44 @@ int conv1_gelu(const float* feats, const float* wt, const float* b, __nv_bfloat1
     return 0;
 }
 
+// ------------------------------------------------------------------------------ features -> time-major bf16 (conv1 GEMM operand)
+__global__ void __launch_bounds__(256) features_tm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int n_cols) {
+    // every feature is written as a bf16 pair hi = bf16(x), lo = bf16(x - hi): the GEMM sums both against the same weight, so the
+    // operand keeps ~16 mantissa bits (the fp32 conv1 it replaces saw the features unrounded)
+    __shared__ float tile[80][33];
+    const int b = blockIdx.y, t0 = blockIdx.x * 32, tid = threadIdx.x;
+    const float* xb = x + static_cast<size_t>(b) * kC1In * n_cols;
+    for (int i = tid; i < kC1In * 32; i += 256) {
+        const int ci = i >> 5, j = i & 31;
+        tile[ci][j] = (t0 + j < n_cols) ? __ldg(xb + static_cast<size_t>(ci) * n_cols + t0 + j) : 0.0f;
+    }
+    __syncthreads();
+    constexpr int kRow = 2 * kC1In;
+    __nv_bfloat16* ob = out + static_cast<size_t>(b) * (n_cols + 3) * kRow;
+    for (int i = tid; i < 32 * kC1In; i += 256) {
+        const int j = i / kC1In, ci = i - j * kC1In;
+        if (t0 + j < n_cols) {
+            const float v = tile[ci][j];
+            const __nv_bfloat16 hi = __float2bfloat16(v);
+            __nv_bfloat16* o = ob + static_cast<size_t>(1 + t0 + j) * kRow;
+            o[ci] = hi;
+            o[kC1In + ci] = __float2bfloat16(v - __bfloat162float(hi));
+        }
+    }
+    if (blockIdx.x == 0 && tid < kRow) {                 // the zero rows: conv padding (row 0, row n_cols + 1) and the K tail (row n_cols + 2)
+        ob[tid] = __float2bfloat16(0.0f);
+        ob[static_cast<size_t>(n_cols + 1) * kRow + tid] = __float2bfloat16(0.0f);
+        ob[static_cast<size_t>(n_cols + 2) * kRow + tid] = __float2bfloat16(0.0f);
+    }
+}
+
+int features_time_major_bf16(const float* feats, __nv_bfloat16* out, int B, int n_cols, cudaStream_t stream) {
+    if (B <= 0) return 0;
+    WSB_CHECK_CUDA(launch_kernel(features_tm_kernel, dim3(ceil_div(n_cols, 32), B), dim3(256), 0, stream, feats, out, n_cols));
+    count_launch();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------ decoder embedding
 __global__ void embed_kernel(const int* __restrict__ tokens, const int* __restrict__ step_ptr, int pos_offset,
                              const __nv_bfloat16* __restrict__ emb, const float* __restrict__ pos_emb,

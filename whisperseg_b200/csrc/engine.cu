@@ -117,6 +117,8 @@ struct Model {
     // encoder weights
     const float *conv1_wt, *conv1_b, *conv2_b, *enc_pos, *enc_ln_g, *enc_ln_b;
     const __nv_bfloat16* conv2_w;
+    const __nv_bfloat16* conv1_wg = nullptr;   // optional: conv1 as a GEMM (weights.py: enc.conv1.wg); WSB_CONV1_FP32=1 keeps the CUDA-core kernel
+    __nv_bfloat16* feat_tm = nullptr;          // [B][n_cols + 3][160] time-major bf16 features (hi | lo)
     std::vector<EncLayer> enc;
     // decoder weights
     const __nv_bfloat16 *dec_emb, *crosskv_w;
@@ -202,6 +204,7 @@ static int model_layout(Model* m, bool assign) {
     char* p = assign ? m->ws : nullptr;
     char* p0 = p;
     m->h1p = carve<__nv_bfloat16>(p, B * (c.n_cols + 1) * d);
+    m->feat_tm = carve<__nv_bfloat16>(p, B * (c.n_cols + 3) * 160 + 256);
     m->x = carve<float>(p, rows * d);
     m->xn = carve<__nv_bfloat16>(p, rows * d);
     m->qkv = carve<__nv_bfloat16>(p, rows * 3 * d);
@@ -281,6 +284,7 @@ static int model_create(const wsb_model_config* cfg, const char* const* names, c
     WSB_GET(m->conv1_wt, "enc.conv1.wt");
     WSB_GET(m->conv1_b, "enc.conv1.b");
     WSB_GET(m->conv2_w, "enc.conv2.w");
+    if (tab.count("enc.conv1.wg")) WSB_GET(m->conv1_wg, "enc.conv1.wg");
     WSB_GET(m->conv2_b, "enc.conv2.b");
     WSB_GET(m->enc_pos, "enc.pos");
     WSB_GET(m->enc_ln_g, "enc.ln.g");
@@ -409,7 +413,30 @@ static int encode(Model* m, const float* feats, int B, float* hidden_f32, cudaSt
     WSB_REQUIRE(B >= 1 && B <= c.max_batch, "batch exceeds the model's max_batch");
     const int d = c.d_model, T = m->T, rows = B * T;
     const long long h1_stride = static_cast<long long>(c.n_cols + 1) * d;
-    {
+    if (m->conv1_wg != nullptr && std::getenv("WSB_CONV1_FP32") == nullptr && d % 32 == 0) {
+        // conv1 (k = 3, pad 1) as an im2col-free tcgen05 GEMM: row t of batch b is the contiguous span of 3 x (80 hi + 80 lo) bf16
+        // features starting at time-major row t (zero row in front), K padded to 512 with zero weights; bias + GELU in the epilogue,
+        // written straight into h1p rows 1.. of every batch (row 0 = conv2's left padding)
+        ProfScope ps(PROF_CONV1, 2.0 * B * c.n_cols * 240.0 * d, s);
+        WSB_RUN(features_time_major_bf16(feats, m->feat_tm, B, c.n_cols, s));
+        WSB_CHECK_CUDA(cudaMemset2DAsync(m->h1p, static_cast<size_t>(h1_stride) * 2, 0, static_cast<size_t>(d) * 2, B, s));
+        GemmArgs g;
+        g.A = m->feat_tm;
+        g.lda = 160;
+        g.a_rows_per_batch = c.n_cols;
+        g.a_batch_stride = static_cast<long long>(c.n_cols + 3) * 160;
+        g.W = m->conv1_wg;
+        g.M = B * c.n_cols;
+        g.N = d;
+        g.K = 512;
+        g.bias = m->conv1_b;
+        g.act = GEMM_ACT_GELU;
+        g.out = m->h1p + d;
+        g.ldc = d;
+        g.out_mode = GEMM_OUT_BF16;
+        g.c_batch_pad = 1;
+        WSB_RUN(gemm_bf16(g, s));
+    } else {
         ProfScope ps(PROF_CONV1, 2.0 * B * c.n_cols * 240.0 * d, s);
         WSB_RUN(conv1_gelu(feats, m->conv1_wt, m->conv1_b, m->h1p, B, c.n_cols, d, h1_stride, s));
     }

@@ -51,6 +51,7 @@ struct GemmDev {
     long long split_stride;        // elements between partial planes of the output
     const unsigned char* row_skip; // optional [M]: rows flagged non-zero are not stored (finished decode rows)
     const int* n_tile_list;        // optional: only these n-tiles are computed (n_tiles = length of the list)
+    int c_batch_pad;               // bf16 outputs with a_rows_per_batch > 0: extra rows between batches of C (row = global row + batch * pad)
     int group_m;                   // 0: tiles run n-fastest (A read from HBM once, B re-read per m-tile out of L2);
                                    // G > 0: when B is too big for L2, super-rows of G m-tiles are walked n-outer /
                                    // m-inner, so the CTAs in flight share a few B tiles and B streams once per super-row
@@ -235,12 +236,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int as = local & 1;
             const uint32_t aphase = (local >> 1) & 1;
             long long grow0;                            // global row of this warp's first lane
+            long long crow_shift = 0;                   // C rows are shifted by this much (batches of C padded with extra rows)
             int nvalid;                                 // valid rows in the 32-row slab
             if (tiles_per_batch > 0) {
                 const int b = mt / tiles_per_batch;
                 const int brow0 = (mt - b * tiles_per_batch) * kBM + q * 32;
                 nvalid = min(32, max(0, p.a_rows_per_batch - brow0));
                 grow0 = static_cast<long long>(b) * p.a_rows_per_batch + brow0;
+                crow_shift = static_cast<long long>(b) * p.c_batch_pad;
             } else {
                 grow0 = static_cast<long long>(mt) * kBM + q * 32;
                 nvalid = static_cast<int>(min(32LL, max(0LL, static_cast<long long>(p.M) - grow0)));
@@ -411,7 +414,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 o = reinterpret_cast<__nv_bfloat16*>(p.out) +
                                     ((b * (p.N >> 6) + (c8 >> 6)) * p.rows_per_batch + t) * 64 + (c8 & 63);
                             } else {
-                                o = reinterpret_cast<__nv_bfloat16*>(p.out) + (grow0 + rr) * p.ldc + c8;
+                                o = reinterpret_cast<__nv_bfloat16*>(p.out) + (grow0 + crow_shift + rr) * p.ldc + c8;
                             }
                             if (vec) {
                                 uint4 w;
@@ -567,6 +570,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.splits = ceil_div(a.K / kBK, p.kb_per_split);          // drop empty trailing splits
     p.split_stride = a.split_stride;
     p.row_skip = a.row_skip;
+    p.c_batch_pad = a.c_batch_pad;
     // B (weights) beyond half of the 126 MB L2 (the cross-K/V projection of all decoder layers: 210 MB): walk
     // super-rows of 16 m-tiles so that B streams from HBM once per super-row instead of once per m-tile
     p.group_m = (static_cast<double>(a.N) * a.K * 2.0 > 64e6 && p.m_tiles > 1) ? 16 : 0;

@@ -50,6 +50,7 @@ struct GemmArgs {
     int splits = 1;                     // split-K factor (GEMM_OUT_F32 without bias only): partial plane s is
     int64_t split_stride = 0;           //   written at out + s * split_stride; see splitk_reduce_* below
     const unsigned char* row_skip = nullptr;   // optional [M] flags: flagged rows are not stored (GEMM_OUT_F32)
+    int c_batch_pad = 0;                // GEMM_OUT_BF16 with a_rows_per_batch > 0: C has this many extra rows between batches
     const int* n_tile_list = nullptr;   // optional device list of the n-tiles (of width block_n) to compute; the
     int n_tile_count = 0;               //   arg-max partials are then [M][n_tile_count]
 };
@@ -66,6 +67,10 @@ int layernorm_f32_to_bf16(const float* x, const float* gamma, const float* beta,
                           float* out_f32, int rows, int d, cudaStream_t stream);
 int conv1_gelu(const float* feats, const float* w /*[d][80][3]*/, const float* b, __nv_bfloat16* out, int B,
                int n_cols, int d, int64_t out_batch_stride, cudaStream_t stream);
+// f32 features [B][80][n_cols] -> bf16 time-major [B][n_cols + 3][160] (80 hi parts, then 80 lo parts = bf16(x - hi)) with a
+// zero row in front and two behind: the (k = 3, pad = 1) conv1 window of frame t is then the contiguous span of 480 elements
+// starting at row t (im2col-free GEMM operand)
+int features_time_major_bf16(const float* feats, __nv_bfloat16* out, int B, int n_cols, cudaStream_t stream);
 // split-K second phase: out = epilogue(sum_s partial[s]) -- deterministic summation order.
 //   bf16 variant : out_bf16[M][N] = act(sum + bias)
 //   resid+LN     : x[M][N] += sum + bias (fp32, in place); if gamma: xn_bf16 = LayerNorm(x) (N <= 1536)

@@ -7,6 +7,7 @@ Reads the same directory the reference hands to `WhisperForConditionalGeneration
 
 Prepared tensors handed to wsb_model_create (all on the target device):
   enc.conv1.wt  f32 [240][d]    (ci*3+k major, channel contiguous)     enc.conv1.b f32 [d]
+  enc.conv1.wg  bf16 [d][512]   (k*160+{0,80}+ci along K, zero tail: conv1 as an im2col-free GEMM over time-major hi+lo bf16 features)
   enc.conv2.w   bf16 [d][3d]    (k*d+ci along K: matches the strided im2col-free view)
   enc.pos f32 [T][d];  enc.ln.{g,b};  per layer l: enc.l.{ln1,ln2}.{g,b}, qkv.{w bf16 [3d][d], b f32 [3d]}
   (q rows pre-scaled by head_dim^-0.5 -- HF multiplies q by `scaling`, modeling_whisper.py:279-310 --
@@ -84,6 +85,12 @@ def prepare_tensors(cfg, sd, gen, device):
     w1 = g("model.encoder.conv1.weight")                              # [d][80][3]
     out["enc.conv1.wt"] = f32(w1.permute(1, 2, 0).reshape(-1, d))
     out["enc.conv1.b"] = f32(g("model.encoder.conv1.bias"))
+    # conv1 as a tcgen05 GEMM over time-major bf16 features split into hi + lo parts (160 per frame):
+    # Wg[co][k * 160 + ci] = Wg[co][k * 160 + 80 + ci] = w[co][ci][k], K padded from 480 to 512
+    wg = torch.zeros(d, 512, dtype=torch.float32)
+    wk = w1.permute(0, 2, 1)                                   # [d][3][80]
+    wg[:, :480] = torch.cat([wk, wk], dim=2).reshape(d, 480)
+    out["enc.conv1.wg"] = bf16(wg)
     w2 = g("model.encoder.conv2.weight")                              # [d][d][3]
     out["enc.conv2.w"] = bf16(w2.permute(0, 2, 1).reshape(d, 3 * d))
     out["enc.conv2.b"] = f32(g("model.encoder.conv2.bias"))
