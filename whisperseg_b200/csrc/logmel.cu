@@ -14,10 +14,12 @@
 // through distributed shared memory, then the clamp + affine is applied while the tile is
 // written out -- so HBM traffic is exactly samples-in + features-out.
 #include "common.cuh"
+#include "logmel_fft.cuh"
 #include "wsb_internal.h"
 
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace cg = cooperative_groups;
@@ -35,6 +37,15 @@ struct LogmelPlan {
     int span_floats, tile_stride;
     size_t smem_bytes;
     bool smem_tables = false;
+    bool two_pass = false;          // n_fft 512 / 1024: logmel2_kernel (two-pass register FFT, lane = frame mel stage)
+    struct TwoPassCfg {             // one per cluster size that fits in shared memory; logmel_run picks per launch
+        int cluster, frames_per_cta, tile_stride, resident_clusters;
+        size_t smem_bytes;
+    };
+    std::vector<TwoPassCfg> tp;
+    int chunk_floats = 0;           // two-pass kernel: floats per staged sample chunk (one of two buffers)
+    float* hann_half = nullptr;     // [n_fft]  0.5 * hann (two-pass kernel)
+    float2* twp = nullptr;          // [16][M/16]  exp(-2 pi i n1 k2 / M) (two-pass kernel)
     float* hann = nullptr;          // [n_fft]
     float2* tw = nullptr;           // [3 n_fft/4]  exp(-2 pi i j / n_fft)
     int* mel_start = nullptr;       // [80]
@@ -57,6 +68,9 @@ struct LogmelParams {
     int n_fft, hop, clip_len, n_frames, n_cols, log2m;
     int frames_per_cta, group_threads, n_groups, span_floats, tile_stride;
     int mel_nnz;
+    const float* hann_half;         // two-pass kernel only
+    const float2* twp;
+    int chunk_floats;
 };
 
 // padded index into a frame group's FFT buffer: the strided scatters of the early Stockham passes (stride 4,
@@ -481,6 +495,221 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-pass kernel for n_fft 512 / 1024 (every sampling rate up to 80 kHz).  Same contract and the same cluster-per-window
+// layout as logmel_kernel above; what changes is how a CTA spends its instructions (round-2 ncu of the one-frame-per-warp
+// kernel: ~2600 warp instructions per frame, 960 of them in the five shuffle stages, 600 in the untangle, 400 in the mel
+// stage):
+//   * FFT: the two register passes of logmel_fft.cuh with one shared-memory transpose between them, no shuffles
+//   * untangle: one thread per (k, M - k) pair, powers written transposed, P[k][frame]
+//   * mel + log10 with lane = frame over the 16 (M = 512) or 32 (M = 256) frames of a CTA iteration: every lane of a warp
+//     walks the same filter, the weights are warp-uniform loads and the power reads are conflict-free
+//   * samples are staged per iteration (two cp.async buffers) instead of per CTA, which leaves room for 4-CTA clusters
+//     (8-CTA clusters keep 15 x 8 = 120 of the 148 SMs busy; the plan picks the cluster size per launch from
+//     cudaOccupancyMaxActiveClusters)
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Stages the samples of window frames [frame0, frame0 + nfr) into dst (asynchronously); the first frame's first sample lands
+// at dst[0].  Interior, fully valid chunks whose first sample is 16-byte aligned in the audio buffer (always the case when
+// hop and the window length are multiples of 4 samples) are copied as 16-byte pieces; chunks that touch the reflected head /
+// tail of the clip or the zero padding outside [lo, hi), and unaligned ones, go element by element.
+template <int N_FFT>
+__device__ __forceinline__ void stage_chunk(const LogmelParams& p, float* dst, int frame0, int nfr, long long start, long long lo,
+                                            long long hi, int tid) {
+    const int span = (nfr - 1) * p.hop + N_FFT;
+    const int p0 = frame0 * p.hop - N_FFT / 2;              // padded-clip coordinate of the chunk's first sample
+    const long long a0 = start + p0;
+    const int n4 = (span + 3) >> 2;
+    if (p0 >= 0 && p0 + span <= p.clip_len && (a0 & 3) == 0 && a0 >= lo && a0 + 4LL * n4 <= hi) {
+        for (int q = tid; q < n4; q += kLogmelThreads) cp_async16(dst + 4 * q, p.audio + a0 + 4 * q);
+        return;
+    }
+    for (int j = tid; j < span; j += kLogmelThreads) {
+        int pc = p0 + j;
+        if (pc < 0) pc = -pc;
+        else if (pc >= p.clip_len) pc = 2 * (p.clip_len - 1) - pc;
+        const long long a = start + pc;
+        if (a >= lo && a < hi) cp_async4(dst + j, p.audio + a);
+        else dst[j] = 0.0f;
+    }
+}
+
+template <int LOG2M>
+__global__ void __launch_bounds__(kLogmelThreads, 1) logmel2_kernel(const LogmelParams p) {
+    using T = lfft::TwoPass<LOG2M>;
+    constexpr int M = T::M, N_FFT = 2 * M, G = T::G;
+    constexpr int NF = 16 * G;                            // frames per CTA iteration
+    constexpr int PS = NF + 1;                            // row stride of the transposed power array
+    constexpr int NPH = kLogmelThreads / NF;              // mel stage: filter phases (thread = (frame, phase))
+    constexpr int NWARPS = kLogmelThreads / 32;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = static_cast<int>(cluster.block_rank());
+    const int csize = static_cast<int>(cluster.num_blocks());
+    const int w = blockIdx.x / csize;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_samp = reinterpret_cast<float*>(smem_raw);                                   // 2 x chunk_floats
+    float* s_tile = s_samp + 2 * p.chunk_floats;                                          // 80 x tile_stride
+    float2* s_buf = reinterpret_cast<float2*>(s_tile + ((kMels * p.tile_stride + 3) & ~3));   // per warp: T::BUF
+    float* s_pt = reinterpret_cast<float*>(s_buf + NWARPS * T::BUF);                      // (M + 1) x PS
+    float2* s_tw = reinterpret_cast<float2*>(s_pt + (((M + 1) * PS + 3) & ~3));           // untangle twiddles
+    float2* s_twp = s_tw + ((T::TWN + 1) & ~1);                                           // pass-1 twiddles [k2][n1]
+    float* s_hann = reinterpret_cast<float*>(s_twp + T::TWP);                             // 0.5 x Hann
+    float* s_melw = s_hann + N_FFT;                                                       // CSR mel weights
+    __shared__ float s_red[2][NWARPS];
+    __shared__ float s_cluster_red[2];
+    __shared__ int s_mel[3][kMels];
+
+    for (int i = tid; i < T::TWN; i += kLogmelThreads) s_tw[i] = p.tw[i];
+    for (int i = tid; i < T::TWP; i += kLogmelThreads) s_twp[i] = p.twp[i];
+    for (int i = tid; i < N_FFT; i += kLogmelThreads) s_hann[i] = p.hann_half[i];
+    for (int i = tid; i < p.mel_nnz; i += kLogmelThreads) s_melw[i] = p.mel_w[i];
+    if (tid < kMels) {
+        s_mel[0][tid] = p.mel_start[tid];
+        s_mel[1][tid] = p.mel_cnt[tid];
+        s_mel[2][tid] = p.mel_off[tid];
+    }
+
+    const int f0 = rank * p.frames_per_cta;
+    const int f1 = min(p.n_frames, f0 + p.frames_per_cta);
+    const int nf = max(0, f1 - f0);
+    const long long start = p.win[3 * w + 0];
+    const long long lo = p.win[3 * w + 1];
+    const long long hi = p.win[3 * w + 2];
+
+    const int iters = (nf + NF - 1) / NF;
+    if (iters > 0) stage_chunk<N_FFT>(p, s_samp, f0, min(NF, nf), start, lo, hi, tid);
+    cp_async_commit();
+    float2* buf = s_buf + warp * T::BUF;
+    const int slot0 = warp * G;                           // this warp's first frame slot of an iteration
+    const int slot = slot0 + T::frame_of(lane);
+    float vmax = -INFINITY, vmin = INFINITY;
+    __syncthreads();                                      // tables staged
+    float2 hwin[16];                                      // this lane's window pairs, register-resident across the frames
+    T::load_window(lane, s_hann, hwin);
+
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        const float* cur = s_samp + (it & 1) * p.chunk_floats;
+        if (it + 1 < iters)
+            stage_chunk<N_FFT>(p, s_samp + ((it + 1) & 1) * p.chunk_floats, f0 + (it + 1) * NF,
+                                           min(NF, nf - (it + 1) * NF), start, lo, hi, tid);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();          // chunk `it` (first pass: the tables too) is visible; the previous mel stage is done with s_pt
+        const bool active = it * NF + slot < nf;
+        if (active) {
+            const int xo = slot * p.hop;                 // even hop (kernel-uniform): every frame is float2-aligned
+            if ((p.hop & 1) == 0) T::pass1(lane, cur + xo, true, hwin, s_twp, buf);
+            else T::pass1(lane, cur + xo, (xo & 1) == 0, hwin, s_twp, buf);
+        }
+        __syncwarp();
+        float2 u[16];
+        if (active) T::pass2_load(lane, buf, u);
+        __syncwarp();
+        if (active) T::pass2_store(lane, u, buf);
+        __syncwarp();
+        T::untangle(lane, buf, s_tw, s_pt, PS, slot0, active);
+        __syncthreads();
+        {   // mel + log10, lane = frame
+            const int f = tid & (NF - 1);
+            const int fl = it * NF + f;
+            if (fl < nf) {
+                const float* pcol = s_pt + f;
+                // filters are dealt to the NPH phases widest first, alternating direction every round, so that the phases
+                // (warps) carry about the same number of filter taps
+                const int phase = tid / NF;
+                for (int j = 0;; ++j) {
+                    const int r = j * NPH + ((j & 1) ? NPH - 1 - phase : phase);
+                    if (r >= kMels) break;
+                    const int m = kMels - 1 - r;
+                    const int cnt = s_mel[1][m];
+                    const float* wt = s_melw + s_mel[2][m];
+                    const float* pw = pcol + s_mel[0][m] * PS;
+                    float acc0 = 0.0f, acc1 = 0.0f;
+                    int i = 0;
+#pragma unroll 1
+                    for (; i + 4 <= cnt; i += 4) {
+                        const float w0 = wt[i], w1 = wt[i + 1], w2 = wt[i + 2], w3 = wt[i + 3];
+                        const float q0 = pw[i * PS], q1 = pw[(i + 1) * PS], q2 = pw[(i + 2) * PS], q3 = pw[(i + 3) * PS];
+                        acc0 = fmaf(w0, q0, acc0);
+                        acc1 = fmaf(w1, q1, acc1);
+                        acc0 = fmaf(w2, q2, acc0);
+                        acc1 = fmaf(w3, q3, acc1);
+                    }
+#pragma unroll 1
+                    for (; i < cnt; ++i) acc0 = fmaf(wt[i], pw[i * PS], acc0);
+                    // log10 through lg2.approx (absolute error ~2e-7 in log2, far inside the 1e-4 bar); the 1e-10 floor is
+                    // selected, not computed, so that silence stays exactly -10
+                    const float acc = acc0 + acc1;
+                    const float v = acc > 1e-10f ? __log2f(acc) * 0.30102999566398120f : -10.0f;
+                    s_tile[m * p.tile_stride + fl] = v;
+                    vmax = fmaxf(vmax, v);
+                    if (f0 + fl < p.n_cols) vmin = fminf(vmin, v);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- window-global max / min across the cluster ---------------------------------------------
+    vmax = warp_max(vmax);
+    vmin = warp_min(vmin);
+    if (lane == 0) {
+        s_red[0][warp] = vmax;
+        s_red[1][warp] = vmin;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float a = s_red[0][0], b = s_red[1][0];
+        for (int i = 1; i < NWARPS; ++i) {
+            a = fmaxf(a, s_red[0][i]);
+            b = fminf(b, s_red[1][i]);
+        }
+        s_cluster_red[0] = a;
+        s_cluster_red[1] = b;
+    }
+    cluster.sync();
+    float gmax = -INFINITY, gmin = INFINITY;
+    for (int r = 0; r < csize; ++r) {
+        const float* peer = cluster.map_shared_rank(s_cluster_red, r);
+        gmax = fmaxf(gmax, peer[0]);
+        gmin = fminf(gmin, peer[1]);
+    }
+    cluster.sync();                                     // peers may exit only after everyone has read
+
+    // ---- clamp + affine + store --------------------------------------------------------------------
+    const float floor_v = gmax - 8.0f;
+    float* outw = p.out + static_cast<size_t>(w) * kMels * p.n_cols;
+    const int ncol = max(0, min(f1, p.n_cols) - f0);
+    for (int m = warp; m < kMels; m += NWARPS) {
+        const float* row = s_tile + m * p.tile_stride;
+        float* orow = outw + m * p.n_cols + f0;
+        for (int c = lane; c < ncol; c += 32) orow[c] = (fmaxf(row[c], floor_v) + 4.0f) * 0.25f;
+    }
+    // clips with fewer than n_cols frames: pad with the window minimum (model.py:155-161)
+    if (p.n_frames < p.n_cols) {
+        const float padv = (p.n_frames > 0) ? (fmaxf(gmin, floor_v) + 4.0f) * 0.25f : 0.0f;
+        const int npad = p.n_cols - p.n_frames;
+        const int per = (npad + csize - 1) / csize;
+        const int q0 = p.n_frames + rank * per, q1 = min(p.n_cols, q0 + per);
+        const int nq = max(0, q1 - q0);
+        for (int m = warp; m < kMels; m += NWARPS)
+            for (int c = lane; c < nq; c += 32) outw[m * p.n_cols + q0 + c] = padv;
+    }
+}
+
 typedef void (*LogmelKernelFn)(const LogmelParams);
 static LogmelKernelFn pick_logmel_kernel(int log2m, bool smem_tables) {
     switch (log2m) {
@@ -500,6 +729,79 @@ static int ilog2(int v) {
     int l = 0;
     while ((1 << l) < v) ++l;
     return l;
+}
+
+static LogmelKernelFn pick_two_pass_kernel(int log2m) {
+    return log2m == 8 ? logmel2_kernel<8> : log2m == 9 ? logmel2_kernel<9> : nullptr;
+}
+
+// Two-pass kernel (n_fft 512 / 1024): tables and one launch configuration per cluster size that fits in shared memory.
+// WSB_LOGMEL_V1=1 keeps the one-frame-per-warp kernel; WSB_LOGMEL_CLUSTER=n pins the cluster size (diagnostics).
+static int two_pass_plan(LogmelPlan* pl, const std::vector<float>& hann, const std::vector<float2>& tw, int max_smem) {
+    LogmelKernelFn fn = pick_two_pass_kernel(pl->log2m);
+    if (fn == nullptr || std::getenv("WSB_LOGMEL_V1") != nullptr) return 0;
+    const int n_fft = pl->n_fft, M = n_fft / 2, N1 = M / 16, G = 32 / N1, NF = 16 * G, PS = NF + 1;
+    const int twn = M / 2 + 1, twp_n = 16 * N1;
+    pl->chunk_floats = ((NF - 1) * pl->hop + n_fft + 3) & ~3;
+    cudaFuncAttributes fa;
+    WSB_CHECK_CUDA(cudaFuncGetAttributes(&fa, fn));
+    const size_t avail = static_cast<size_t>(max_smem) - fa.sharedSizeBytes;
+    WSB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(avail)));
+    int dev = 0, n_sms = 148;
+    WSB_CHECK_CUDA(cudaGetDevice(&dev));
+    WSB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+    int pinned = 0;
+    if (const char* e = std::getenv("WSB_LOGMEL_CLUSTER")) pinned = std::atoi(e);
+    for (int c = kMaxCluster; c >= 1; --c) {
+        if (pinned > 0 && c != pinned) continue;
+        LogmelPlan::TwoPassCfg cfg;
+        cfg.cluster = c;
+        cfg.frames_per_cta = std::max(1, ceil_div(std::max(pl->n_frames, 1), c));
+        cfg.tile_stride = cfg.frames_per_cta | 1;
+        const size_t floats = 2 * static_cast<size_t>(pl->chunk_floats) + ((kMels * cfg.tile_stride + 3) & ~3) +
+                              static_cast<size_t>(kLogmelThreads / 32) * 2 * (32 * 17) + (((M + 1) * PS + 3) & ~3) +
+                              2 * ((twn + 1) & ~1) + 2 * twp_n + n_fft + ((pl->nnz + 3) & ~3);
+        cfg.smem_bytes = sizeof(float) * floats;
+        if (cfg.smem_bytes > avail) continue;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(static_cast<unsigned>(c) * n_sms);
+        lc.blockDim = dim3(kLogmelThreads);
+        lc.dynamicSmemBytes = cfg.smem_bytes;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = c;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+        int resident = 0;
+        if (cudaOccupancyMaxActiveClusters(&resident, fn, &lc) != cudaSuccess || resident < 1) {
+            (void)cudaGetLastError();
+            resident = std::max(1, n_sms / (c < 3 ? c : c + 1));        // clusters do not span GPCs: assume some loss
+        }
+        cfg.resident_clusters = resident;
+        if (std::getenv("WSB_LOGMEL_DEBUG"))
+            fprintf(stderr, "[wsb] log-mel two-pass: cluster %d, %d frames per CTA, %zu B shared memory, %d clusters resident\n", c,
+                    cfg.frames_per_cta, cfg.smem_bytes, resident);
+        pl->tp.push_back(cfg);
+    }
+    if (pl->tp.empty()) return 0;                          // large hop: the one-frame-per-warp kernel stays
+    std::vector<float> hh(n_fft);
+    for (int i = 0; i < n_fft; ++i) hh[i] = 0.5f * hann[i];
+    std::vector<float2> twp(twp_n);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k2 = 0; k2 < 16; ++k2)
+        for (int n1 = 0; n1 < N1; ++n1) {
+            const double a = two_pi * static_cast<double>((n1 * k2) % M) / M;
+            twp[k2 * N1 + n1] = make_float2(static_cast<float>(cos(a)), static_cast<float>(-sin(a)));
+        }
+    (void)tw;
+    WSB_CHECK_CUDA(cudaMalloc(&pl->hann_half, sizeof(float) * n_fft));
+    WSB_CHECK_CUDA(cudaMalloc(&pl->twp, sizeof(float2) * twp_n));
+    WSB_CHECK_CUDA(cudaMemcpy(pl->hann_half, hh.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
+    WSB_CHECK_CUDA(cudaMemcpy(pl->twp, twp.data(), sizeof(float2) * twp_n, cudaMemcpyHostToDevice));
+    pl->two_pass = true;
+    return 0;
 }
 
 int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float* mel_filters_host, int n_freq,
@@ -580,6 +882,10 @@ int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float
     WSB_CHECK_CUDA(cudaFuncGetAttributes(&fa, fn));
     WSB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         max_smem - static_cast<int>(fa.sharedSizeBytes)));
+    if (two_pass_plan(pl, hann, tw, max_smem)) {
+        logmel_plan_destroy(pl);
+        return 1;
+    }
     *out = pl;
     return 0;
 }
@@ -587,6 +893,8 @@ int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float
 void logmel_plan_destroy(LogmelPlan* pl) {
     if (!pl) return;
     cudaFree(pl->hann);
+    cudaFree(pl->hann_half);
+    cudaFree(pl->twp);
     cudaFree(pl->tw);
     cudaFree(pl->mel_start);
     cudaFree(pl->mel_cnt);
@@ -622,19 +930,45 @@ int logmel_run(const LogmelPlan* pl, const float* audio_dev, const long long* wi
     p.tile_stride = pl->tile_stride;
     p.mel_nnz = pl->nnz;
 
+    p.hann_half = pl->hann_half;
+    p.twp = pl->twp;
+    p.chunk_floats = pl->chunk_floats;
+    int cluster = pl->cluster;
+    size_t smem_bytes = pl->smem_bytes;
+    LogmelKernelFn fn = pick_logmel_kernel(pl->log2m, pl->smem_tables);
+    if (pl->two_pass) {
+        // cluster size for this launch: fewest (waves of resident clusters) x (frames a CTA walks)
+        // (measured on the 240-window 48 kHz and 360-window 16 kHz workloads for clusters of 4 / 5 / 6 / 8: the ordering follows
+        // waves x (frames per CTA + ~10 frames of per-CTA fixed cost), profiles/r2_logmel_two_pass.txt)
+        const LogmelPlan::TwoPassCfg* best = nullptr;
+        long long best_cost = 0;
+        for (const auto& c : pl->tp) {
+            const long long waves = ceil_div(n_win, c.resident_clusters);
+            const long long cost = waves * (c.frames_per_cta + 10);
+            if (best == nullptr || cost < best_cost) {
+                best = &c;
+                best_cost = cost;
+            }
+        }
+        cluster = best->cluster;
+        smem_bytes = best->smem_bytes;
+        p.frames_per_cta = best->frames_per_cta;
+        p.tile_stride = best->tile_stride;
+        fn = pick_two_pass_kernel(pl->log2m);
+    }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(n_win) * pl->cluster);
+    cfg.gridDim = dim3(static_cast<unsigned>(n_win) * cluster);
     cfg.blockDim = dim3(kLogmelThreads);
-    cfg.dynamicSmemBytes = pl->smem_bytes;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = pl->cluster;
+    attr[0].val.clusterDim.x = cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    WSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pick_logmel_kernel(pl->log2m, pl->smem_tables), p));
+    WSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, p));
     count_launch();
     return 0;
 }
