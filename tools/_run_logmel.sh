@@ -1,5 +1,5 @@
 timeout 300 python -m pytest tests/test_gpu_logmel.py -x -q 2>&1 | tail -4
-for c in "" 4 5 6 8; do
+for c in "" 5 6; do
   echo "== cluster '$c'"; WSB_LOGMEL_CLUSTER=$c timeout 120 python tools/logmel_one.py 2>&1 | tail -1
   WSB_LOGMEL_CLUSTER=$c timeout 120 python tools/logmel_one.py 16000 0.01 3600 2>&1 | tail -1
 done

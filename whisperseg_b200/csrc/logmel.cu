@@ -44,6 +44,9 @@ struct LogmelPlan {
     };
     std::vector<TwoPassCfg> tp;
     int chunk_floats = 0;           // two-pass kernel: floats per staged sample chunk (one of two buffers)
+    int4* mel_desc = nullptr;       // [80] {first bin, groups of 4 taps, offset into mel_w4, 0} (two-pass kernel)
+    float* mel_w4 = nullptr;        // CSR weights, every filter zero-padded to a multiple of 4 taps
+    int nnz4 = 0;
     float* hann_half = nullptr;     // [n_fft]  0.5 * hann (two-pass kernel)
     float2* twp = nullptr;          // [16][M/16]  exp(-2 pi i n1 k2 / M) (two-pass kernel)
     float* hann = nullptr;          // [n_fft]
@@ -70,6 +73,9 @@ struct LogmelParams {
     int mel_nnz;
     const float* hann_half;         // two-pass kernel only
     const float2* twp;
+    const int4* mel_desc;
+    const float* mel_w4;
+    int mel_nnz4;
     int chunk_floats;
 };
 
@@ -562,24 +568,21 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel2_kernel(const Logmel
     float* s_samp = reinterpret_cast<float*>(smem_raw);                                   // 2 x chunk_floats
     float* s_tile = s_samp + 2 * p.chunk_floats;                                          // 80 x tile_stride
     float2* s_buf = reinterpret_cast<float2*>(s_tile + ((kMels * p.tile_stride + 3) & ~3));   // per warp: T::BUF
-    float* s_pt = reinterpret_cast<float*>(s_buf + NWARPS * T::BUF);                      // (M + 1) x PS
-    float2* s_tw = reinterpret_cast<float2*>(s_pt + (((M + 1) * PS + 3) & ~3));           // untangle twiddles
+    float* s_pt = reinterpret_cast<float*>(s_buf + NWARPS * T::BUF);                      // (M + 4) x PS, rows > M stay zero
+    float2* s_tw = reinterpret_cast<float2*>(s_pt + (((M + 4) * PS + 3) & ~3));           // untangle twiddles
     float2* s_twp = s_tw + ((T::TWN + 1) & ~1);                                           // pass-1 twiddles [k2][n1]
     float* s_hann = reinterpret_cast<float*>(s_twp + T::TWP);                             // 0.5 x Hann
-    float* s_melw = s_hann + N_FFT;                                                       // CSR mel weights
+    float* s_melw = s_hann + N_FFT;                                                       // CSR mel weights, 4-tap groups
     __shared__ float s_red[2][NWARPS];
     __shared__ float s_cluster_red[2];
-    __shared__ int s_mel[3][kMels];
+    __shared__ __align__(16) int4 s_meld[kMels];                                          // {first bin, 4-tap groups, offset}
 
     for (int i = tid; i < T::TWN; i += kLogmelThreads) s_tw[i] = p.tw[i];
     for (int i = tid; i < T::TWP; i += kLogmelThreads) s_twp[i] = p.twp[i];
     for (int i = tid; i < N_FFT; i += kLogmelThreads) s_hann[i] = p.hann_half[i];
-    for (int i = tid; i < p.mel_nnz; i += kLogmelThreads) s_melw[i] = p.mel_w[i];
-    if (tid < kMels) {
-        s_mel[0][tid] = p.mel_start[tid];
-        s_mel[1][tid] = p.mel_cnt[tid];
-        s_mel[2][tid] = p.mel_off[tid];
-    }
+    for (int i = tid; i < p.mel_nnz4; i += kLogmelThreads) s_melw[i] = p.mel_w4[i];
+    for (int i = tid; i < 3 * PS; i += kLogmelThreads) s_pt[(M + 1) * PS + i] = 0.0f;     // read by the zero-weight pad taps
+    if (tid < kMels) s_meld[tid] = p.mel_desc[tid];
 
     const int f0 = rank * p.frames_per_cta;
     const int f1 = min(p.n_frames, f0 + p.frames_per_cta);
@@ -634,22 +637,18 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel2_kernel(const Logmel
                     const int r = j * NPH + ((j & 1) ? NPH - 1 - phase : phase);
                     if (r >= kMels) break;
                     const int m = kMels - 1 - r;
-                    const int cnt = s_mel[1][m];
-                    const float* wt = s_melw + s_mel[2][m];
-                    const float* pw = pcol + s_mel[0][m] * PS;
+                    const int4 dsc = s_meld[m];
+                    const float4* wt = reinterpret_cast<const float4*>(s_melw + dsc.z);
+                    const float* pw = pcol + dsc.x * PS;
                     float acc0 = 0.0f, acc1 = 0.0f;
-                    int i = 0;
 #pragma unroll 1
-                    for (; i + 4 <= cnt; i += 4) {
-                        const float w0 = wt[i], w1 = wt[i + 1], w2 = wt[i + 2], w3 = wt[i + 3];
-                        const float q0 = pw[i * PS], q1 = pw[(i + 1) * PS], q2 = pw[(i + 2) * PS], q3 = pw[(i + 3) * PS];
-                        acc0 = fmaf(w0, q0, acc0);
-                        acc1 = fmaf(w1, q1, acc1);
-                        acc0 = fmaf(w2, q2, acc0);
-                        acc1 = fmaf(w3, q3, acc1);
+                    for (int g4 = 0; g4 < dsc.y; ++g4, pw += 4 * PS) {
+                        const float4 wv = wt[g4];
+                        acc0 = fmaf(wv.x, pw[0], acc0);
+                        acc1 = fmaf(wv.y, pw[PS], acc1);
+                        acc0 = fmaf(wv.z, pw[2 * PS], acc0);
+                        acc1 = fmaf(wv.w, pw[3 * PS], acc1);
                     }
-#pragma unroll 1
-                    for (; i < cnt; ++i) acc0 = fmaf(wt[i], pw[i * PS], acc0);
                     // log10 through lg2.approx (absolute error ~2e-7 in log2, far inside the 1e-4 bar); the 1e-10 floor is
                     // selected, not computed, so that silence stays exactly -10
                     const float acc = acc0 + acc1;
@@ -737,9 +736,22 @@ static LogmelKernelFn pick_two_pass_kernel(int log2m) {
 
 // Two-pass kernel (n_fft 512 / 1024): tables and one launch configuration per cluster size that fits in shared memory.
 // WSB_LOGMEL_V1=1 keeps the one-frame-per-warp kernel; WSB_LOGMEL_CLUSTER=n pins the cluster size (diagnostics).
-static int two_pass_plan(LogmelPlan* pl, const std::vector<float>& hann, const std::vector<float2>& tw, int max_smem) {
+static int two_pass_plan(LogmelPlan* pl, const std::vector<float>& hann, const std::vector<int>& mel_start,
+                         const std::vector<int>& mel_cnt, const std::vector<int>& mel_off, const std::vector<float>& mel_w,
+                         int max_smem) {
     LogmelKernelFn fn = pick_two_pass_kernel(pl->log2m);
     if (fn == nullptr || std::getenv("WSB_LOGMEL_V1") != nullptr) return 0;
+    // CSR filter bank in groups of 4 taps (one float4 weight load per group); pad taps carry weight 0 and may point at
+    // the three zero rows behind the last bin
+    std::vector<int4> desc(kMels);
+    std::vector<float> w4;
+    for (int m = 0; m < kMels; ++m) {
+        const int groups = (mel_cnt[m] + 3) / 4;
+        desc[m] = make_int4(mel_start[m], groups, static_cast<int>(w4.size()), 0);
+        for (int i = 0; i < 4 * groups; ++i) w4.push_back(i < mel_cnt[m] ? mel_w[mel_off[m] + i] : 0.0f);
+    }
+    if (w4.empty()) w4.resize(4, 0.0f);
+    pl->nnz4 = static_cast<int>(w4.size());
     const int n_fft = pl->n_fft, M = n_fft / 2, N1 = M / 16, G = 32 / N1, NF = 16 * G, PS = NF + 1;
     const int twn = M / 2 + 1, twp_n = 16 * N1;
     pl->chunk_floats = ((NF - 1) * pl->hop + n_fft + 3) & ~3;
@@ -759,8 +771,8 @@ static int two_pass_plan(LogmelPlan* pl, const std::vector<float>& hann, const s
         cfg.frames_per_cta = std::max(1, ceil_div(std::max(pl->n_frames, 1), c));
         cfg.tile_stride = cfg.frames_per_cta | 1;
         const size_t floats = 2 * static_cast<size_t>(pl->chunk_floats) + ((kMels * cfg.tile_stride + 3) & ~3) +
-                              static_cast<size_t>(kLogmelThreads / 32) * 2 * (32 * 17) + (((M + 1) * PS + 3) & ~3) +
-                              2 * ((twn + 1) & ~1) + 2 * twp_n + n_fft + ((pl->nnz + 3) & ~3);
+                              static_cast<size_t>(kLogmelThreads / 32) * 2 * (32 * 17) + (((M + 4) * PS + 3) & ~3) +
+                              2 * ((twn + 1) & ~1) + 2 * twp_n + n_fft + pl->nnz4;
         cfg.smem_bytes = sizeof(float) * floats;
         if (cfg.smem_bytes > avail) continue;
         cudaLaunchConfig_t lc = {};
@@ -795,7 +807,10 @@ static int two_pass_plan(LogmelPlan* pl, const std::vector<float>& hann, const s
             const double a = two_pi * static_cast<double>((n1 * k2) % M) / M;
             twp[k2 * N1 + n1] = make_float2(static_cast<float>(cos(a)), static_cast<float>(-sin(a)));
         }
-    (void)tw;
+    WSB_CHECK_CUDA(cudaMalloc(&pl->mel_desc, sizeof(int4) * kMels));
+    WSB_CHECK_CUDA(cudaMalloc(&pl->mel_w4, sizeof(float) * w4.size()));
+    WSB_CHECK_CUDA(cudaMemcpy(pl->mel_desc, desc.data(), sizeof(int4) * kMels, cudaMemcpyHostToDevice));
+    WSB_CHECK_CUDA(cudaMemcpy(pl->mel_w4, w4.data(), sizeof(float) * w4.size(), cudaMemcpyHostToDevice));
     WSB_CHECK_CUDA(cudaMalloc(&pl->hann_half, sizeof(float) * n_fft));
     WSB_CHECK_CUDA(cudaMalloc(&pl->twp, sizeof(float2) * twp_n));
     WSB_CHECK_CUDA(cudaMemcpy(pl->hann_half, hh.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
@@ -882,7 +897,7 @@ int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float
     WSB_CHECK_CUDA(cudaFuncGetAttributes(&fa, fn));
     WSB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         max_smem - static_cast<int>(fa.sharedSizeBytes)));
-    if (two_pass_plan(pl, hann, tw, max_smem)) {
+    if (two_pass_plan(pl, hann, st, cnt, off, wts, max_smem)) {
         logmel_plan_destroy(pl);
         return 1;
     }
@@ -895,6 +910,8 @@ void logmel_plan_destroy(LogmelPlan* pl) {
     cudaFree(pl->hann);
     cudaFree(pl->hann_half);
     cudaFree(pl->twp);
+    cudaFree(pl->mel_desc);
+    cudaFree(pl->mel_w4);
     cudaFree(pl->tw);
     cudaFree(pl->mel_start);
     cudaFree(pl->mel_cnt);
@@ -932,6 +949,9 @@ int logmel_run(const LogmelPlan* pl, const float* audio_dev, const long long* wi
 
     p.hann_half = pl->hann_half;
     p.twp = pl->twp;
+    p.mel_desc = pl->mel_desc;
+    p.mel_w4 = pl->mel_w4;
+    p.mel_nnz4 = pl->nnz4;
     p.chunk_floats = pl->chunk_floats;
     int cluster = pl->cluster;
     size_t smem_bytes = pl->smem_bytes;
