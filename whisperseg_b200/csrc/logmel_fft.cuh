@@ -158,17 +158,19 @@ struct TwoPass {
         float* col = pt + slot0 + f;
         const int kk = lane & (N1 - 1);
 #pragma unroll
-        for (int i = 0; i <= M / 2 / N1; ++i) {
+        for (int i = 0; i < M / 2 / N1; ++i) {             // pairs (k, M - k), k = 0 .. M/2 - 1 (k = 0 pairs with itself: P[0], P[M])
             const int k = kk + i * N1;
-            if (k <= M / 2) {
-                const float2 zk = z[k], zm = z[(M - k) & (M - 1)];
-                const float2 e = make_float2(zk.x + zm.x, zk.y - zm.y);
-                const float2 o = make_float2(zk.y + zm.y, zm.x - zk.x);
-                const float2 t = cmulf(o, tw[k]);
-                const float ax = e.x + t.x, ay = e.y + t.y, bx = e.x - t.x, by = e.y - t.y;
-                col[k * ps] = ax * ax + ay * ay;
-                col[(M - k) * ps] = bx * bx + by * by;
-            }
+            const float2 zk = z[k], zm = z[(M - k) & (M - 1)];
+            const float2 e = make_float2(zk.x + zm.x, zk.y - zm.y);
+            const float2 o = make_float2(zk.y + zm.y, zm.x - zk.x);
+            const float2 t = cmulf(o, tw[k]);
+            const float ax = e.x + t.x, ay = e.y + t.y, bx = e.x - t.x, by = e.y - t.y;
+            col[k * ps] = ax * ax + ay * ay;
+            col[(M - k) * ps] = bx * bx + by * by;
+        }
+        if (kk == N1 - 1) {                                 // the self-paired middle bin: X[M/2] = 2 conj(Z[M/2])
+            const float2 zc = z[M / 2];
+            col[(M / 2) * ps] = 4.0f * (zc.x * zc.x + zc.y * zc.y);
         }
     }
 };
