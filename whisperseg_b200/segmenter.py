@@ -13,7 +13,10 @@ Design differences (B200-first):
   * the front-end runs on the GPU for all windows of a call in one launch (the reference loops
     over windows on the CPU, model.py:146-165); features never leave HBM;
   * windows are independent, so `batch_size` only bounds memory: the engine decodes up to
-    `max_batch` windows together whatever `batch_size` says (results do not depend on batching);
+    `max_batch` windows together whatever `batch_size` says.  A window's tokens do not depend on its neighbours in
+    exact arithmetic; in bf16 the decode linear layers switch implementation with the number of live rows (<= 64: fused
+    LayerNorm + linear kernels, above: tensor-core split-K), so a near-tie between two tokens (top-1/top-2 margin below
+    the bf16 noise floor, tests/test_noise_floor.py) can resolve differently in a different batch;
   * `num_beams=1` decodes greedily (BASELINE.json north_star); `num_beams` 2..4 -- the reference default
     is 4 -- runs HF-equivalent beam search on the device (csrc/beam.cu), `length_penalty` honoured;
     `top_k` / `top_p` only matter for sampling and the reference always passes top_k=1.
@@ -223,7 +226,8 @@ class SegmenterBase:
         copy of the concatenated samples, one log-mel launch (per-window [lo, hi) bounds keep clips from
         leaking into each other), encoder/decoder batches filled across clip boundaries, then the token
         streams are regrouped per clip and post-processed exactly like segment().  Returns a list of
-        predictions, one per clip, identical to per-clip segment() calls."""
+        predictions, one per clip: the same windows, features and post-processing as per-clip segment() calls (tokens equal
+        up to the near-tie caveat in the module docstring)."""
         if min_frequency is None:
             min_frequency = self.default_segmentation_config.get("min_frequency", 0)
         if spec_time_step is None:
