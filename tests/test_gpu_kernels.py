@@ -80,7 +80,8 @@ def test_layernorm(lib, rows, d):
     assert (o16.float() - ref).abs().max().item() < 4e-2
 
 
-@pytest.mark.parametrize("B,T,H", [(1, 500, 6), (3, 500, 20), (2, 128, 8), (2, 300, 6)])
+# (the last three give every persistent CTA several (head, window) units: next-unit K / Q / V prefetch, 4, 1 and 3 tiles per unit)
+@pytest.mark.parametrize("B,T,H", [(1, 500, 6), (3, 500, 20), (2, 128, 8), (2, 300, 6), (24, 500, 20), (50, 128, 8), (70, 300, 6)])
 def test_encoder_attention(lib, B, T, H):
     import torch
     from whisperseg_b200 import _lib

@@ -3,8 +3,11 @@
 // Replaces HF WhisperAttention.forward for the encoder (modeling_whisper.py:310-357): softmax(q k^T) v
 // with q already scaled (the 1/sqrt(64) factor is folded into the q projection weights at load time).
 //
-// One CTA per (head, window), looping over the 128-query tiles.  Q, K and V are TMA-loaded straight out of the
-// packed [B*T, 3d] QKV activation (128-byte swizzle; keys beyond T are zero-filled by TMA and masked).
+// Persistent CTAs (one per SM) walk the (head, window) units; per unit a CTA loops over the 128-query tiles.  Q, K and V are
+// TMA-loaded straight out of the packed [B*T, 3d] QKV activation (128-byte swizzle; keys beyond T are zero-filled by TMA and
+// masked).  Only one CTA fits per SM (208 KB of shared memory, all 512 TMEM columns), so a unit's K/V load cannot hide behind
+// another CTA: instead the NEXT unit's K and first Q tile are requested as soon as the last S = Q K^T of the current unit has
+// completed (the K buffer is dead from then on) and its V as soon as the last P V has completed.
 //   S = Q K^T      : 2 x (M=128, N=256, K=64) tcgen05.mma into all 512 TMEM columns (fp32)
 //   softmax        : thread r owns TMEM lane r = query row r: pass 1 row max, pass 2 exp2 + row sum,
 //                    P written as bf16 into a double-buffered, manually 128B-swizzled smem tile
@@ -17,8 +20,8 @@
 
 namespace wsb {
 
-#ifndef WSB_ATT_POLY_MASK
-#define WSB_ATT_POLY_MASK 2          // pairs whose index has these bits set use the polynomial exp2 (2 = every second pair; 64 = none)
+#ifndef WSB_ATT_POLY_SEL
+#define WSB_ATT_POLY_SEL 0x8888      // bit j set: column pair j of a thread's 16 pairs per chunk takes the polynomial exp2 (0 = all on MUFU)
 #endif
 constexpr int kAttThreads = 512;    // four warps per TMEM lane quarter: each owns a quarter of the key columns
 constexpr int kAttQ = 128;          // query rows per tile
@@ -31,11 +34,12 @@ __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
     return (static_cast<unsigned long long>(__float_as_uint(hi)) << 32) | __float_as_uint(lo);
 }
 
-// One CTA per (head, window): K and V are loaded once and shared by all query tiles; Q tiles are
-// double-buffered; TMEM (512 columns) is allocated once.
+// K and V of a unit are loaded once and shared by its query tiles; the Q tile is reloaded as soon as its S has completed;
+// TMEM (512 columns) and the mbarriers are set up once per CTA, so every barrier parity below counts over the CTA's
+// lifetime: `it` = units done by this CTA, `tq` = query tiles done by this CTA.
 __global__ void __launch_bounds__(kAttThreads, 1)
 encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                         __nv_bfloat16* __restrict__ out, int T, int d) {
+                         __nv_bfloat16* __restrict__ out, int T, int d, int n_heads, int n_units) {
     extern __shared__ unsigned char att_smem_raw[];
     unsigned char* smem = att_smem_raw + ((1024u - (smem_u32(att_smem_raw) & 1023u)) & 1023u);
     unsigned char* sQ = smem;                                   // 16 KB (reloaded as soon as S = QK^T has completed)
@@ -54,9 +58,11 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int quarter = warp & 3, colgrp = warp >> 2;   // TMEM lanes 32*quarter.., key-column group (0..3)
-    __shared__ float s_xchg[4][kAttQ];
-    const int h = blockIdx.x, b = blockIdx.y;
+    __shared__ float s_xchg[4][kAttQ];                        // row maxima of the four key-column groups
+    __shared__ float s_xsum[4][kAttQ];                        // row sums (own array: no barrier between its write and s_xchg's reads)
     const int n_qt = (T + kAttQ - 1) / kAttQ;
+    int unit = blockIdx.x;                                      // grid <= n_units
+    int h = unit % n_heads, b = unit / n_heads;
 
     if (tid == 0) {
         tma_prefetch_desc(&tm_q);
@@ -102,10 +108,16 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     const int row = tid & (kAttQ - 1);                     // query row within the tile == TMEM lane
 
 #pragma unroll 1
+    for (int it = 0; unit < n_units; ++it, unit += gridDim.x) {
+    h = unit % n_heads;
+    b = unit / n_heads;
+    const int next_unit = unit + gridDim.x;
+#pragma unroll 1
     for (int qt = 0; qt < n_qt; ++qt) {
+        const int tq = it * n_qt + qt;                          // query tiles this CTA has finished before this one
         if (tid == 0) {
-            if (qt == 0) mbar_wait(bar_kv, 0);
-            mbar_wait(bar_q, qt & 1);
+            if (qt == 0) mbar_wait(bar_kv, it & 1);
+            mbar_wait(bar_q, tq & 1);
             tc_fence_after();
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256, 0, 0);
             const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
@@ -119,12 +131,21 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             umma_commit(bar_s);
         }
         ATT_STAMP(0);                                       // loop top -> S MMAs issued (incl. K/V / Q load waits)
-        mbar_wait(bar_s, qt & 1);
+        mbar_wait(bar_s, tq & 1);
         tc_fence_after();
         ATT_STAMP(1);                                       // S = Q K^T complete
-        if (tid == 0 && qt + 1 < n_qt) {                   // S is in TMEM: the Q buffer is free, prefetch the next tile
-            mbar_arrive_expect_tx(bar_q, kAttQ * kHd * 2);
-            tma_load_3d(sQ, &tm_q, bar_q, h * kHd, (qt + 1) * kAttQ, b);
+        if (tid == 0) {
+            if (qt + 1 < n_qt) {                            // S is in TMEM: the Q buffer is free, prefetch the next tile
+                mbar_arrive_expect_tx(bar_q, kAttQ * kHd * 2);
+                tma_load_3d(sQ, &tm_q, bar_q, h * kHd, (qt + 1) * kAttQ, b);
+            } else if (next_unit < n_units) {               // last S of this unit: K is dead too -> the next unit's K and Q
+                const int nh = next_unit % n_heads, nb = next_unit / n_heads;
+                mbar_arrive_expect_tx(bar_kv, kAttKeys * kHd * 2);
+                tma_load_3d(sK, &tm_kv, bar_kv, d + nh * kHd, 0, nb);
+                tma_load_3d(sK + 256 * kHd * 2, &tm_kv, bar_kv, d + nh * kHd, 256, nb);
+                mbar_arrive_expect_tx(bar_q, kAttQ * kHd * 2);
+                tma_load_3d(sQ, &tm_q, bar_q, nh * kHd, 0, nb);
+            }
         }
 
         // pass 1: row max over the T valid keys (each warp of the pair scans its 256-column half)
@@ -158,9 +179,11 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         tmem_ld_32x32(lane_base + colgrp * 32, rnext);
         const float nm = -mscaled;
         const unsigned long long scale2 = pack_f32x2(kLog2e, kLog2e), shift2 = pack_f32x2(nm, nm);
-        // every second pair of columns takes its exponential as a degree-3 polynomial (relative error 8e-4, below the bf16
-        // rounding of P) so that the MUFU pipe -- 16 ex2 per clock and SM, the floor of this pass -- carries half the load
-        constexpr int kPolyMask = WSB_ATT_POLY_MASK;
+        // one column pair in four (WSB_ATT_POLY_SEL) takes its exponential as a degree-3 polynomial on the FMA / integer pipes
+        // (relative error 8e-4, below the bf16 rounding of P): a polynomial pair costs ~14 issue slots, a MUFU pair 2 issue
+        // slots but 16 cycles of the 16-lane MUFU pipe, and the pass is issue-bound -- measured 0.747 / 0.735 / 0.729 / 0.728 ms
+        // per launch with 8 / 6 / 5 / 4 of the 16 pairs on the polynomial
+        constexpr unsigned kPolySel = WSB_ATT_POLY_SEL;
         const unsigned long long kMagic2 = pack_f32x2(12582912.0f, 12582912.0f), kNegMagic2 = pack_f32x2(-12582912.0f, -12582912.0f);
         const unsigned long long kNegOne2 = pack_f32x2(-1.0f, -1.0f), kOne2 = pack_f32x2(1.0f, 1.0f);
         const unsigned long long kC3 = pack_f32x2(0.05550411f, 0.05550411f), kC2 = pack_f32x2(0.24022651f, 0.24022651f);
@@ -168,7 +191,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
 #pragma unroll
         for (int c = 0; c < kAttKeys / kAttChunk; ++c) {
             const int buf = c & 1;
-            const int use = qt * (kAttKeys / kAttChunk / 2) + (c >> 1);  // how many times this buffer was used before
+            const int use = tq * (kAttKeys / kAttChunk / 2) + (c >> 1);  // how many times this buffer was used before
             // this warp's 32 of the chunk's 128 keys: sub-tile (64 keys) colgrp>>1, 32-key half colgrp&1
             unsigned char* pbuf = sP + buf * kAttQ * kAttChunk * 2 + (colgrp >> 1) * kAttQ * kHd * 2 + row * 128;
             {
@@ -186,7 +209,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
                     const unsigned long long s2 = (static_cast<unsigned long long>(r[i + 1]) << 32) | r[i];
                     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x2) : "l"(s2), "l"(scale2), "l"(shift2));
                     float e0, e1;
-                    if ((i & kPolyMask) == kPolyMask) {
+                    if ((kPolySel >> (i >> 1)) & 1u) {
                         // this pair on the FMA / integer pipes: 2^x = 2^n * p(f), n = round(x), f = x - n in [-0.5, 0.5]
                         const float a0 = fmaxf(__uint_as_float(static_cast<uint32_t>(x2)), -125.0f);
                         const float a1 = fmaxf(__uint_as_float(static_cast<uint32_t>(x2 >> 32)), -125.0f);
@@ -236,7 +259,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             if ((tid & 31) == 0) mbar_arrive(&bar_ready[buf]);
             if (tid == 0) {
                 mbar_wait(&bar_ready[buf], use & 1);
-                if (qt == 0 && c == 0) mbar_wait(bar_v, 0);
+                if (qt == 0 && c == 0) mbar_wait(bar_v, it & 1);
                 tc_fence_after();
                 constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);     // B (= V) is MN-major
                 const uint64_t dv = umma_desc_mn_sw128(smem_u32(sV + c * kAttChunk * kHd * 2));
@@ -252,25 +275,30 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         }
         const float rsum = __uint_as_float(static_cast<uint32_t>(rsum2)) + __uint_as_float(static_cast<uint32_t>(rsum2 >> 32));
         ATT_STAMP(3);                                       // pass 2 (exp, P, PV issue)
-        mbar_wait(bar_o, qt & 1);
+        mbar_wait(bar_o, tq & 1);
         tc_fence_after();
         ATT_STAMP(4);                                       // last PV MMAs complete
+        if (tid == 0 && qt + 1 == n_qt && next_unit < n_units) {   // V is dead: the next unit's V
+            const int nh = next_unit % n_heads, nb = next_unit / n_heads;
+            mbar_arrive_expect_tx(bar_v, kAttKeys * kHd * 2);
+            tma_load_3d(sV, &tm_kv, bar_v, 2 * d + nh * kHd, 0, nb);
+            tma_load_3d(sV + 256 * kHd * 2, &tm_kv, bar_v, 2 * d + nh * kHd, 256, nb);
+        }
 
-        // epilogue: O / rowsum (row sums of the two column halves are combined through shared memory)
-        __syncthreads();                                       // s_xchg was last read right after pass 1
-        s_xchg[colgrp][row] = rsum;
+        // epilogue: O / rowsum (the row sums of the four key-column groups are combined through shared memory); every warp
+        // takes 16 of the 64 output dims of its 32 rows
+        s_xsum[colgrp][row] = rsum;
         __syncthreads();
         const int q_row = qt * kAttQ + row;
-        const float inv = 1.0f / ((s_xchg[0][row] + s_xchg[1][row]) + (s_xchg[2][row] + s_xchg[3][row]));
-        if (colgrp < 2) {
-            const int hlf = colgrp;                            // 32 of the 64 output dims (warp groups 0 and 1)
-            uint32_t r[32];
-            tmem_ld_32x32(lane_base + hlf * 32, r);
+        const float inv = 1.0f / ((s_xsum[0][row] + s_xsum[1][row]) + (s_xsum[2][row] + s_xsum[3][row]));
+        {
+            uint32_t r[16];
+            tmem_ld_32x16(lane_base + colgrp * 16, r);
             tmem_ld_wait();
             if (q_row < T) {
-                __nv_bfloat16* o = out + (static_cast<size_t>(b) * T + q_row) * d + h * kHd + hlf * 32;
+                __nv_bfloat16* o = out + (static_cast<size_t>(b) * T + q_row) * d + h * kHd + colgrp * 16;
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
+                for (int i = 0; i < 16; i += 8) {
                     uint4 pk;
                     pk.x = pack_bf16x2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
                     pk.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
@@ -285,9 +313,10 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         __syncthreads();
         ATT_STAMP(5);                                       // epilogue
     }
+    }
 #ifdef WSB_ATT_TRACE
-    if (tid == 0 && blockIdx.x == 3 && blockIdx.y == 7)
-        printf("attention trace (ns, thread 0, 4 tiles): wait-loads+issue S %llu | S mma %llu | pass1 %llu | pass2 %llu | PV tail %llu | epilogue %llu\n",
+    if (tid == 0 && blockIdx.x == 3)
+        printf("attention trace (ns, thread 0, all units of CTA 3): wait-loads+issue S %llu | S mma %llu | pass1 %llu | pass2 %llu | PV tail %llu | epilogue %llu\n",
                tr[0], tr[1], tr[2], tr[3], tr[4], tr[5]);
 #endif
     if (warp == 1) tmem_dealloc<512>(tmem);
@@ -312,8 +341,12 @@ int encoder_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T
     if (rc) return rc;
     rc = make_tmap_bf16(&tm_kv, qkv, 3, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    dim3 grid(n_heads, B);
-    encoder_attention_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(tm_q, tm_kv, out, T, d);
+    const int n_units = n_heads * B;
+    int num_sms = 148;
+    WSB_CHECK_CUDA(cudaGetDevice(&dev));
+    WSB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = std::min(n_units, std::max(8, num_sms - g_sm_reserve));
+    encoder_attention_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(tm_q, tm_kv, out, T, d, n_heads, n_units);
     WSB_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
