@@ -8,6 +8,7 @@
 // masked).  Only one CTA fits per SM (208 KB of shared memory, all 512 TMEM columns), so a unit's K/V load cannot hide behind
 // another CTA: instead the NEXT unit's K and first Q tile are requested as soon as the last S = Q K^T of the current unit has
 // completed (the K buffer is dead from then on) and its V as soon as the last P V has completed.
+//   roles          : 16 softmax warps (512 threads) + one issuing warp whose lane 0 launches every TMA load and every MMA
 //   S = Q K^T      : 2 x (M=128, N=256, K=64) tcgen05.mma into all 512 TMEM columns (fp32)
 //   softmax        : thread r owns TMEM lane r = query row r: pass 1 row max, pass 2 exp2 + row sum,
 //                    P written as bf16 into a double-buffered, manually 128B-swizzled smem tile
@@ -23,12 +24,16 @@ namespace wsb {
 #ifndef WSB_ATT_POLY_SEL
 #define WSB_ATT_POLY_SEL 0x8888      // bit j set: column pair j of a thread's 16 pairs per chunk takes the polynomial exp2 (0 = all on MUFU)
 #endif
-constexpr int kAttThreads = 512;    // four warps per TMEM lane quarter: each owns a quarter of the key columns
+constexpr int kAttThreads = 512;    // softmax threads: four warps per TMEM lane quarter, each owns a quarter of the key columns
+constexpr int kAttAll = kAttThreads + 32;   // + one warp whose lane 0 issues every TMA load and every MMA
 constexpr int kAttQ = 128;          // query rows per tile
 constexpr int kAttKeys = 512;       // padded key count
 constexpr int kHd = 64;
 constexpr int kAttChunk = 128;      // keys per P tile / PV MMA group
 constexpr int kAttSmem = (kAttQ * kHd + 2 * kAttKeys * kHd + 2 * kAttQ * kAttChunk) * 2 + 1024 + 128;
+
+// barrier among the 512 softmax threads (the issuing warp never joins it)
+__device__ __forceinline__ void softmax_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kAttThreads) : "memory"); }
 
 __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
     return (static_cast<unsigned long long>(__float_as_uint(hi)) << 32) | __float_as_uint(lo);
@@ -37,7 +42,7 @@ __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
 // K and V of a unit are loaded once and shared by its query tiles; the Q tile is reloaded as soon as its S has completed;
 // TMEM (512 columns) and the mbarriers are set up once per CTA, so every barrier parity below counts over the CTA's
 // lifetime: `it` = units done by this CTA, `tq` = query tiles done by this CTA.
-__global__ void __launch_bounds__(kAttThreads, 1)
+__global__ void __launch_bounds__(kAttAll, 1)
 encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                          __nv_bfloat16* __restrict__ out, int T, int d, int n_heads, int n_units) {
     extern __shared__ unsigned char att_smem_raw[];
@@ -54,7 +59,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     uint64_t* bar_p = bars + 4;                                 // [2] P buffer consumed by the tensor core
     uint64_t* bar_o = bars + 6;
     uint64_t* bar_ready = bars + 7;                             // [2] every warp has written its part of the P buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* bar_epi = bars + 9;                               // every warp has read its part of O out of TMEM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int quarter = warp & 3, colgrp = warp >> 2;   // TMEM lanes 32*quarter.., key-column group (0..3)
@@ -76,6 +82,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         mbar_init(bar_o, 1);
         mbar_init(&bar_ready[0], kAttThreads / 32);
         mbar_init(&bar_ready[1], kAttThreads / 32);
+        mbar_init(bar_epi, kAttThreads / 32);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -83,17 +90,6 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar_kv, kAttKeys * kHd * 2);
-        tma_load_3d(sK, &tm_kv, bar_kv, d + h * kHd, 0, b);
-        tma_load_3d(sK + 256 * kHd * 2, &tm_kv, bar_kv, d + h * kHd, 256, b);
-        mbar_arrive_expect_tx(bar_q, kAttQ * kHd * 2);
-        tma_load_3d(sQ, &tm_q, bar_q, h * kHd, 0, b);
-        mbar_arrive_expect_tx(bar_v, kAttKeys * kHd * 2);
-        tma_load_3d(sV, &tm_kv, bar_v, 2 * d + h * kHd, 0, b);
-        tma_load_3d(sV + 256 * kHd * 2, &tm_kv, bar_v, 2 * d + h * kHd, 256, b);
-    }
 
 #ifdef WSB_ATT_TRACE
     unsigned long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -107,46 +103,102 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     constexpr float kLog2e = 1.4426950408889634f;
     const int row = tid & (kAttQ - 1);                     // query row within the tile == TMEM lane
 
+    if (warp == kAttThreads / 32) {
+        // ---- the issuing warp: every TMA load and every MMA of the CTA comes from its lane 0, so that no softmax thread carries
+        // the ~100 serial instructions of an MMA group on the critical path of its tile ---------------------------------------
+        if ((tid & 31) == 0) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256, 0, 0);
+            constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);         // B (= V) is MN-major
+            mbar_arrive_expect_tx(bar_kv, kAttKeys * kHd * 2);
+            tma_load_3d(sK, &tm_kv, bar_kv, d + h * kHd, 0, b);
+            tma_load_3d(sK + 256 * kHd * 2, &tm_kv, bar_kv, d + h * kHd, 256, b);
+            mbar_arrive_expect_tx(bar_q, kAttQ * kHd * 2);
+            tma_load_3d(sQ, &tm_q, bar_q, h * kHd, 0, b);
+            mbar_arrive_expect_tx(bar_v, kAttKeys * kHd * 2);
+            tma_load_3d(sV, &tm_kv, bar_v, 2 * d + h * kHd, 0, b);
+            tma_load_3d(sV + 256 * kHd * 2, &tm_kv, bar_v, 2 * d + h * kHd, 256, b);
+            const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
+            const uint64_t dk0 = umma_desc_k_sw128(smem_u32(sK)), dk1 = umma_desc_k_sw128(smem_u32(sK + 256 * kHd * 2));
+#pragma unroll 1
+            for (int it = 0; unit < n_units; ++it, unit += gridDim.x) {
+                h = unit % n_heads;
+                b = unit / n_heads;
+                const int next_unit = unit + gridDim.x;
+#pragma unroll 1
+                for (int qt = 0; qt < n_qt; ++qt) {
+                    const int tq = it * n_qt + qt;
+                    // S = Q K^T.  Upper key half (TMEM columns 256..511): for qt > 0 it was issued behind the previous
+                    // tile's last P V (those columns were dead by then); lower half: once the previous O has been read out.
+                    if (qt == 0) {
+                        mbar_wait(bar_kv, it & 1);
+                        mbar_wait(bar_q, tq & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < kHd / 16; ++k) umma_bf16_ss(tmem + 256, dq + 2 * k, dk1 + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                    }
+                    if (tq > 0) mbar_wait(bar_epi, (tq - 1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < kHd / 16; ++k) umma_bf16_ss(tmem, dq + 2 * k, dk0 + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                    umma_commit(bar_s);
+                    mbar_wait(bar_s, tq & 1);                   // S is in TMEM: the Q buffer is free (and after the last tile K too)
+                    if (qt + 1 < n_qt) {
+                        mbar_arrive_expect_tx(bar_q, kAttQ * kHd * 2);
+                        tma_load_3d(sQ, &tm_q, bar_q, h * kHd, (qt + 1) * kAttQ, b);
+                    } else if (next_unit < n_units) {
+                        const int nh = next_unit % n_heads, nb = next_unit / n_heads;
+                        mbar_arrive_expect_tx(bar_kv, kAttKeys * kHd * 2);
+                        tma_load_3d(sK, &tm_kv, bar_kv, d + nh * kHd, 0, nb);
+                        tma_load_3d(sK + 256 * kHd * 2, &tm_kv, bar_kv, d + nh * kHd, 256, nb);
+                        mbar_arrive_expect_tx(bar_q, kAttQ * kHd * 2);
+                        tma_load_3d(sQ, &tm_q, bar_q, nh * kHd, 0, nb);
+                    }
+#pragma unroll 1
+                    for (int c = 0; c < kAttKeys / kAttChunk; ++c) {
+                        const int buf = c & 1;
+                        const int use = tq * (kAttKeys / kAttChunk / 2) + (c >> 1);
+                        mbar_wait(&bar_ready[buf], use & 1);
+                        if (qt == 0 && c == 0) mbar_wait(bar_v, it & 1);
+                        tc_fence_after();
+                        const uint64_t dv = umma_desc_mn_sw128(smem_u32(sV + c * kAttChunk * kHd * 2));
+#pragma unroll
+                        for (int k = 0; k < kAttChunk / 16; ++k) {     // 16 keys per MMA: P advances 32 B (next sub-tile after
+                                                                       // 64 keys), V advances 16 rows = 2048 B
+                            const uint64_t dp = umma_desc_k_sw128(smem_u32(sP + buf * kAttQ * kAttChunk * 2 + (k >> 2) * kAttQ * kHd * 2));
+                            umma_bf16_ss(tmem, dp + 2 * (k & 3), dv + ((16 * kHd * 2) >> 4) * k, idesc_o, (c > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&bar_p[buf]);
+                    }
+                    umma_commit(bar_o);
+                    if (qt + 1 < n_qt) {
+                        // every warp has read its columns of the last chunk (bar_ready): columns 256..511 are dead
+                        mbar_wait(bar_q, (tq + 1) & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < kHd / 16; ++k) umma_bf16_ss(tmem + 256, dq + 2 * k, dk1 + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                    } else if (next_unit < n_units) {           // V is dead once the last P V has completed: the next unit's V
+                        mbar_wait(bar_o, tq & 1);
+                        const int nh = next_unit % n_heads, nb = next_unit / n_heads;
+                        mbar_arrive_expect_tx(bar_v, kAttKeys * kHd * 2);
+                        tma_load_3d(sV, &tm_kv, bar_v, 2 * d + nh * kHd, 0, nb);
+                        tma_load_3d(sV + 256 * kHd * 2, &tm_kv, bar_v, 2 * d + nh * kHd, 256, nb);
+                    }
+                }
+            }
+        }
+        __syncwarp();                                           // lanes 1..31 wait here for lane 0: the warp reaches the final barrier converged
+    } else {
 #pragma unroll 1
     for (int it = 0; unit < n_units; ++it, unit += gridDim.x) {
     h = unit % n_heads;
     b = unit / n_heads;
-    const int next_unit = unit + gridDim.x;
 #pragma unroll 1
     for (int qt = 0; qt < n_qt; ++qt) {
         const int tq = it * n_qt + qt;                          // query tiles this CTA has finished before this one
-        if (tid == 0) {
-            if (qt == 0) mbar_wait(bar_kv, it & 1);
-            mbar_wait(bar_q, tq & 1);
-            tc_fence_after();
-            constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256, 0, 0);
-            const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + half * 256 * kHd * 2));
-#pragma unroll
-                for (int k = 0; k < kHd / 16; ++k)
-                    umma_bf16_ss(tmem + half * 256, dq + 2 * k, dk + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-            }
-            umma_commit(bar_s);
-        }
-        ATT_STAMP(0);                                       // loop top -> S MMAs issued (incl. K/V / Q load waits)
+        ATT_STAMP(0);
         mbar_wait(bar_s, tq & 1);
         tc_fence_after();
         ATT_STAMP(1);                                       // S = Q K^T complete
-        if (tid == 0) {
-            if (qt + 1 < n_qt) {                            // S is in TMEM: the Q buffer is free, prefetch the next tile
-                mbar_arrive_expect_tx(bar_q, kAttQ * kHd * 2);
-                tma_load_3d(sQ, &tm_q, bar_q, h * kHd, (qt + 1) * kAttQ, b);
-            } else if (next_unit < n_units) {               // last S of this unit: K is dead too -> the next unit's K and Q
-                const int nh = next_unit % n_heads, nb = next_unit / n_heads;
-                mbar_arrive_expect_tx(bar_kv, kAttKeys * kHd * 2);
-                tma_load_3d(sK, &tm_kv, bar_kv, d + nh * kHd, 0, nb);
-                tma_load_3d(sK + 256 * kHd * 2, &tm_kv, bar_kv, d + nh * kHd, 256, nb);
-                mbar_arrive_expect_tx(bar_q, kAttQ * kHd * 2);
-                tma_load_3d(sQ, &tm_q, bar_q, nh * kHd, 0, nb);
-            }
-        }
 
         // pass 1: row max over the T valid keys (each warp of the pair scans its 256-column half)
         float rmax = -INFINITY;
@@ -166,14 +218,14 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             }
         }
         s_xchg[colgrp][row] = rmax;
-        __syncthreads();
+        softmax_sync();
         rmax = fmaxf(fmaxf(s_xchg[0][row], s_xchg[1][row]), fmaxf(s_xchg[2][row], s_xchg[3][row]));
         const float mscaled = rmax * kLog2e;
         ATT_STAMP(2);                                       // pass 1 (row max)
 
         // pass 2: P chunks + PV MMAs.  The TMEM columns of chunk c + 1 are requested before chunk c is exponentiated, the
         // scale and the row sum run as packed f32x2 instructions (FFMA2 / FADD2), and the warps hand their part of the P
-        // buffer over with an mbarrier arrive instead of a CTA-wide barrier (only the MMA-issuing thread waits for the slowest).
+        // buffer over with an mbarrier arrive instead of a CTA-wide barrier (only the issuing warp waits for the slowest).
         unsigned long long rsum2 = 0ull;                       // (sum of even columns, sum of odd columns)
         uint32_t rnext[32];
         tmem_ld_32x32(lane_base + colgrp * 32, rnext);
@@ -256,39 +308,18 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             fence_proxy_async_smem();                          // generic-proxy smem writes -> visible to the MMA
             tc_fence_before();
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&bar_ready[buf]);
-            if (tid == 0) {
-                mbar_wait(&bar_ready[buf], use & 1);
-                if (qt == 0 && c == 0) mbar_wait(bar_v, it & 1);
-                tc_fence_after();
-                constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);     // B (= V) is MN-major
-                const uint64_t dv = umma_desc_mn_sw128(smem_u32(sV + c * kAttChunk * kHd * 2));
-#pragma unroll
-                for (int k = 0; k < kAttChunk / 16; ++k) {     // 16 keys per MMA: P advances 32 B (next sub-tile after
-                                                               // 64 keys), V advances 16 rows = 2048 B
-                    const uint64_t dp = umma_desc_k_sw128(smem_u32(sP + buf * kAttQ * kAttChunk * 2 + (k >> 2) * kAttQ * kHd * 2));
-                    umma_bf16_ss(tmem, dp + 2 * (k & 3), dv + ((16 * kHd * 2) >> 4) * k, idesc_o, (c > 0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(&bar_p[buf]);
-                if (c == kAttKeys / kAttChunk - 1) umma_commit(bar_o);
-            }
+            if ((tid & 31) == 0) mbar_arrive(&bar_ready[buf]);          // the issuing warp launches this chunk's P V when all 16 have arrived
         }
         const float rsum = __uint_as_float(static_cast<uint32_t>(rsum2)) + __uint_as_float(static_cast<uint32_t>(rsum2 >> 32));
         ATT_STAMP(3);                                       // pass 2 (exp, P, PV issue)
         mbar_wait(bar_o, tq & 1);
         tc_fence_after();
         ATT_STAMP(4);                                       // last PV MMAs complete
-        if (tid == 0 && qt + 1 == n_qt && next_unit < n_units) {   // V is dead: the next unit's V
-            const int nh = next_unit % n_heads, nb = next_unit / n_heads;
-            mbar_arrive_expect_tx(bar_v, kAttKeys * kHd * 2);
-            tma_load_3d(sV, &tm_kv, bar_v, 2 * d + nh * kHd, 0, nb);
-            tma_load_3d(sV + 256 * kHd * 2, &tm_kv, bar_v, 2 * d + nh * kHd, 256, nb);
-        }
 
         // epilogue: O / rowsum (the row sums of the four key-column groups are combined through shared memory); every warp
         // takes 16 of the 64 output dims of its 32 rows
         s_xsum[colgrp][row] = rsum;
-        __syncthreads();
+        softmax_sync();
         const int q_row = qt * kAttQ + row;
         const float inv = 1.0f / ((s_xsum[0][row] + s_xsum[1][row]) + (s_xsum[2][row] + s_xsum[3][row]));
         {
@@ -308,12 +339,16 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
                 }
             }
         }
-        // the next tile's S MMA overwrites the TMEM columns O was just read from
+        // the lower half of the next tile's S overwrites the TMEM columns O was just read from: tell the issuing warp
         tc_fence_before();
-        __syncthreads();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(bar_epi);
         ATT_STAMP(5);                                       // epilogue
     }
     }
+    }
+    tc_fence_before();
+    __syncthreads();                                            // every MMA has completed (bar_o) and every TMEM read is done
 #ifdef WSB_ATT_TRACE
     if (tid == 0 && blockIdx.x == 3)
         printf("attention trace (ns, thread 0, all units of CTA 3): wait-loads+issue S %llu | S mma %llu | pass1 %llu | pass2 %llu | PV tail %llu | epilogue %llu\n",
@@ -346,7 +381,7 @@ int encoder_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T
     WSB_CHECK_CUDA(cudaGetDevice(&dev));
     WSB_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = std::min(n_units, std::max(8, num_sms - g_sm_reserve));
-    encoder_attention_kernel<<<grid, kAttThreads, kAttSmem, stream>>>(tm_q, tm_kv, out, T, d, n_heads, n_units);
+    encoder_attention_kernel<<<grid, kAttAll, kAttSmem, stream>>>(tm_q, tm_kv, out, T, d, n_heads, n_units);
     WSB_CHECK_CUDA(cudaGetLastError());
     count_launch();
     return 0;
