@@ -43,7 +43,8 @@ struct LogmelPlan {
         size_t smem_bytes;
     };
     std::vector<TwoPassCfg> tp;
-    int chunk_floats = 0;           // two-pass kernel: floats per staged sample chunk (one of two buffers)
+    int chunk_floats = 0;           // two-pass kernel: floats per staged sample chunk
+    int chunk_bufs = 2;             // chunk buffers: 2 (the next chunk lands while this one is transformed), 1 for large hops
     int4* mel_desc = nullptr;       // [80] {first bin, groups of 4 taps, offset into mel_w4, 0} (two-pass kernel)
     float* mel_w4 = nullptr;        // CSR weights, every filter zero-padded to a multiple of 4 taps
     int nnz4 = 0;
@@ -77,6 +78,7 @@ struct LogmelParams {
     const float* mel_w4;
     int mel_nnz4;
     int chunk_floats;
+    int chunk_bufs;
 };
 
 // padded index into a frame group's FFT buffer: the strided scatters of the early Stockham passes (stride 4,
@@ -550,7 +552,7 @@ __device__ __forceinline__ void stage_chunk(const LogmelParams& p, float* dst, i
     }
 }
 
-template <int LOG2M>
+template <int LOG2M, int BUFS>
 __global__ void __launch_bounds__(kLogmelThreads, 1) logmel2_kernel(const LogmelParams p) {
     using T = lfft::TwoPass<LOG2M>;
     constexpr int M = T::M, N_FFT = 2 * M, G = T::G;
@@ -565,8 +567,8 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel2_kernel(const Logmel
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_samp = reinterpret_cast<float*>(smem_raw);                                   // 2 x chunk_floats
-    float* s_tile = s_samp + 2 * p.chunk_floats;                                          // 80 x tile_stride
+    float* s_samp = reinterpret_cast<float*>(smem_raw);                                   // chunk_bufs x chunk_floats
+    float* s_tile = s_samp + BUFS * p.chunk_floats;                                          // 80 x tile_stride
     float2* s_buf = reinterpret_cast<float2*>(s_tile + ((kMels * p.tile_stride + 3) & ~3));   // per warp: T::BUF
     float* s_pt = reinterpret_cast<float*>(s_buf + NWARPS * T::BUF);                      // (M + 4) x PS, rows > M stay zero
     float2* s_tw = reinterpret_cast<float2*>(s_pt + (((M + 4) * PS + 3) & ~3));           // untangle twiddles
@@ -604,12 +606,20 @@ __global__ void __launch_bounds__(kLogmelThreads, 1) logmel2_kernel(const Logmel
 
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
-        const float* cur = s_samp + (it & 1) * p.chunk_floats;
-        if (it + 1 < iters)
-            stage_chunk<N_FFT>(p, s_samp + ((it + 1) & 1) * p.chunk_floats, f0 + (it + 1) * NF,
-                                           min(NF, nf - (it + 1) * NF), start, lo, hi, tid);
-        cp_async_commit();
-        cp_async_wait<1>();
+        const float* cur = s_samp;
+        if constexpr (BUFS == 2) {                       // the next chunk lands in the other buffer while this one is transformed
+            cur += (it & 1) * p.chunk_floats;
+            if (it + 1 < iters)
+                stage_chunk<N_FFT>(p, s_samp + ((it + 1) & 1) * p.chunk_floats, f0 + (it + 1) * NF, min(NF, nf - (it + 1) * NF),
+                                   start, lo, hi, tid);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {                                         // large hop: one buffer, staged here (every pass-1 read of the previous
+            if (it > 0)                                  // chunk happened before the barrier that ended its untangle)
+                stage_chunk<N_FFT>(p, s_samp, f0 + it * NF, min(NF, nf - it * NF), start, lo, hi, tid);
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
         __syncthreads();          // chunk `it` (first pass: the tables too) is visible; the previous mel stage is done with s_pt
         const bool active = it * NF + slot < nf;
         if (active) {
@@ -730,8 +740,10 @@ static int ilog2(int v) {
     return l;
 }
 
-static LogmelKernelFn pick_two_pass_kernel(int log2m) {
-    return log2m == 8 ? logmel2_kernel<8> : log2m == 9 ? logmel2_kernel<9> : nullptr;
+static LogmelKernelFn pick_two_pass_kernel(int log2m, int bufs) {
+    if (log2m == 8) return bufs == 2 ? logmel2_kernel<8, 2> : logmel2_kernel<8, 1>;
+    if (log2m == 9) return bufs == 2 ? logmel2_kernel<9, 2> : logmel2_kernel<9, 1>;
+    return nullptr;
 }
 
 // Two-pass kernel (n_fft 512 / 1024): tables and one launch configuration per cluster size that fits in shared memory.
@@ -739,7 +751,7 @@ static LogmelKernelFn pick_two_pass_kernel(int log2m) {
 static int two_pass_plan(LogmelPlan* pl, const std::vector<float>& hann, const std::vector<int>& mel_start,
                          const std::vector<int>& mel_cnt, const std::vector<int>& mel_off, const std::vector<float>& mel_w,
                          int max_smem) {
-    LogmelKernelFn fn = pick_two_pass_kernel(pl->log2m);
+    LogmelKernelFn fn = pick_two_pass_kernel(pl->log2m, 2);
     if (fn == nullptr || std::getenv("WSB_LOGMEL_V1") != nullptr) return 0;
     // CSR filter bank in groups of 4 taps (one float4 weight load per group); pad taps carry weight 0 and may point at
     // the three zero rows behind the last bin
@@ -759,18 +771,23 @@ static int two_pass_plan(LogmelPlan* pl, const std::vector<float>& hann, const s
     WSB_CHECK_CUDA(cudaFuncGetAttributes(&fa, fn));
     const size_t avail = static_cast<size_t>(max_smem) - fa.sharedSizeBytes;
     WSB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(avail)));
+    WSB_CHECK_CUDA(cudaFuncSetAttribute(pick_two_pass_kernel(pl->log2m, 1), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(avail)));
     int dev = 0, n_sms = 148;
     WSB_CHECK_CUDA(cudaGetDevice(&dev));
     WSB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
     int pinned = 0;
     if (const char* e = std::getenv("WSB_LOGMEL_CLUSTER")) pinned = std::atoi(e);
+    // two chunk buffers if any cluster size fits with them, else one (hops of several hundred samples)
+    for (int bufs = 2; bufs >= 1 && pl->tp.empty(); --bufs) {
+    pl->chunk_bufs = bufs;
     for (int c = kMaxCluster; c >= 1; --c) {
         if (pinned > 0 && c != pinned) continue;
         LogmelPlan::TwoPassCfg cfg;
         cfg.cluster = c;
         cfg.frames_per_cta = std::max(1, ceil_div(std::max(pl->n_frames, 1), c));
         cfg.tile_stride = cfg.frames_per_cta | 1;
-        const size_t floats = 2 * static_cast<size_t>(pl->chunk_floats) + ((kMels * cfg.tile_stride + 3) & ~3) +
+        const size_t floats = static_cast<size_t>(pl->chunk_bufs) * pl->chunk_floats + ((kMels * cfg.tile_stride + 3) & ~3) +
                               static_cast<size_t>(kLogmelThreads / 32) * 2 * (32 * 17) + (((M + 4) * PS + 3) & ~3) +
                               2 * ((twn + 1) & ~1) + 2 * twp_n + n_fft + pl->nnz4;
         cfg.smem_bytes = sizeof(float) * floats;
@@ -787,17 +804,18 @@ static int two_pass_plan(LogmelPlan* pl, const std::vector<float>& hann, const s
         lc.attrs = attr;
         lc.numAttrs = 1;
         int resident = 0;
-        if (cudaOccupancyMaxActiveClusters(&resident, fn, &lc) != cudaSuccess || resident < 1) {
+        if (cudaOccupancyMaxActiveClusters(&resident, pick_two_pass_kernel(pl->log2m, bufs), &lc) != cudaSuccess || resident < 1) {
             (void)cudaGetLastError();
             resident = std::max(1, n_sms / (c < 3 ? c : c + 1));        // clusters do not span GPCs: assume some loss
         }
         cfg.resident_clusters = resident;
         if (std::getenv("WSB_LOGMEL_DEBUG"))
-            fprintf(stderr, "[wsb] log-mel two-pass: cluster %d, %d frames per CTA, %zu B shared memory, %d clusters resident\n", c,
-                    cfg.frames_per_cta, cfg.smem_bytes, resident);
+            fprintf(stderr, "[wsb] log-mel two-pass: cluster %d, %d frames per CTA, %d chunk buffer(s), %zu B shared memory, %d clusters resident\n",
+                    c, cfg.frames_per_cta, pl->chunk_bufs, cfg.smem_bytes, resident);
         pl->tp.push_back(cfg);
     }
-    if (pl->tp.empty()) return 0;                          // large hop: the one-frame-per-warp kernel stays
+    }
+    if (pl->tp.empty()) return 0;                          // very large hop: the one-frame-per-warp kernel stays
     std::vector<float> hh(n_fft);
     for (int i = 0; i < n_fft; ++i) hh[i] = 0.5f * hann[i];
     std::vector<float2> twp(twp_n);
@@ -885,21 +903,26 @@ int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float
     const size_t static_bytes = 2048;                   // s_red, s_cluster_red, s_mel + margin
     pl->smem_tables = base_bytes + table_bytes + static_bytes <= static_cast<size_t>(max_smem);
     pl->smem_bytes = base_bytes + (pl->smem_tables ? table_bytes : 0);
-    if (pl->smem_bytes + static_bytes > static_cast<size_t>(max_smem)) {
-        set_last_error("log-mel plan needs " + std::to_string(pl->smem_bytes) + " B shared memory per CTA (limit " +
-                       std::to_string(max_smem) + "): hop/n_fft combination too large for an 8-CTA cluster");
-        logmel_plan_destroy(pl);
-        return 3;
-    }
+    // the one-frame-per-warp kernel stages a CTA's whole sample span: hops of a few hundred samples do not fit; the two-pass
+    // kernel (n_fft 512 / 1024) stages per iteration and reaches further
+    const bool v1_fits = pl->smem_bytes + static_bytes <= static_cast<size_t>(max_smem);
     LogmelKernelFn fn = pick_logmel_kernel(pl->log2m, pl->smem_tables);
     WSB_REQUIRE(fn != nullptr, "unsupported n_fft");
-    cudaFuncAttributes fa;
-    WSB_CHECK_CUDA(cudaFuncGetAttributes(&fa, fn));
-    WSB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        max_smem - static_cast<int>(fa.sharedSizeBytes)));
+    if (v1_fits) {
+        cudaFuncAttributes fa;
+        WSB_CHECK_CUDA(cudaFuncGetAttributes(&fa, fn));
+        WSB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            max_smem - static_cast<int>(fa.sharedSizeBytes)));
+    }
     if (two_pass_plan(pl, hann, st, cnt, off, wts, max_smem)) {
         logmel_plan_destroy(pl);
         return 1;
+    }
+    if (!v1_fits && !pl->two_pass) {
+        set_last_error("log-mel plan needs " + std::to_string(pl->smem_bytes) + " B shared memory per CTA (limit " +
+                       std::to_string(max_smem) + "): hop/n_fft combination too large");
+        logmel_plan_destroy(pl);
+        return 3;
     }
     *out = pl;
     return 0;
@@ -953,6 +976,7 @@ int logmel_run(const LogmelPlan* pl, const float* audio_dev, const long long* wi
     p.mel_w4 = pl->mel_w4;
     p.mel_nnz4 = pl->nnz4;
     p.chunk_floats = pl->chunk_floats;
+    p.chunk_bufs = pl->chunk_bufs;
     int cluster = pl->cluster;
     size_t smem_bytes = pl->smem_bytes;
     LogmelKernelFn fn = pick_logmel_kernel(pl->log2m, pl->smem_tables);
@@ -974,7 +998,7 @@ int logmel_run(const LogmelPlan* pl, const float* audio_dev, const long long* wi
         smem_bytes = best->smem_bytes;
         p.frames_per_cta = best->frames_per_cta;
         p.tile_stride = best->tile_stride;
-        fn = pick_two_pass_kernel(pl->log2m);
+        fn = pick_two_pass_kernel(pl->log2m, pl->chunk_bufs);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(n_win) * cluster);
