@@ -35,6 +35,7 @@ struct LogmelPlan {
     int n_fft, hop, clip_len, n_frames, n_cols, log2m;
     int cluster, frames_per_cta, group_threads, n_groups;
     int span_floats, tile_stride;
+    int sub_frames = 0;             // one-frame-per-warp kernel: frames staged at a time (= frames_per_cta unless the span is too large)
     size_t smem_bytes;
     bool smem_tables = false;
     bool two_pass = false;          // n_fft 512 / 1024: logmel2_kernel (two-pass register FFT, lane = frame mel stage)
@@ -70,7 +71,7 @@ struct LogmelParams {
     const int* mel_off;
     const float* mel_w;
     int n_fft, hop, clip_len, n_frames, n_cols, log2m;
-    int frames_per_cta, group_threads, n_groups, span_floats, tile_stride;
+    int frames_per_cta, group_threads, n_groups, span_floats, tile_stride, sub_frames;
     int mel_nnz;
     const float* hann_half;         // two-pass kernel only
     const float2* twp;
@@ -204,10 +205,31 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
     const long long lo = p.win[3 * w + 1];
     const long long hi = p.win[3 * w + 2];
 
-    // ---- stage this CTA's sample span ---------------------------------------------------------
-    if (nf > 0) {
-        const int span = (nf - 1) * p.hop + N_FFT;
-        const int p0 = f0 * p.hop - M;                    // padded-clip coordinate of s_samples[0]
+    // ---- per-frame FFT + mel + log ---------------------------------------------------------------
+    const int g = tid / G;
+    const int gt = tid - g * G;
+    float2* buf = reinterpret_cast<float2*>(s_fft + g * C::GROUP_FLOATS);
+    float* power = reinterpret_cast<float*>(buf + C::MPAD);
+    float vmax = -INFINITY, vmin = INFINITY;
+    // twiddles of the cross-lane DIF stages (register FFT path): exp(-2 pi i (lane mod h) / (2h)), h = 16, 8, 4, 2, 1
+    float2 lane_tw[5];
+#pragma unroll
+    for (int st = 0; st < 5; ++st) {
+        const int h = 16 >> st;
+        float sn, cs;
+        sincospif(static_cast<float>(gt & (h - 1)) / static_cast<float>(h), &sn, &cs);
+        lane_tw[st] = make_float2(cs, -sn);
+    }
+    constexpr int Q = M / 4;
+
+#pragma unroll 1
+    for (int sf = 0; sf < nf; sf += p.sub_frames) {       // rounds of sub_frames frames (one round unless the hop is large)
+    const int nfs = min(p.sub_frames, nf - sf);
+    __syncthreads();                                      // the previous round is done with s_samples
+    // ---- stage the sample span of this round's frames (all of the CTA's frames unless the span is too large) -------------
+    if (nfs > 0) {
+        const int span = (nfs - 1) * p.hop + N_FFT;
+        const int p0 = (f0 + sf) * p.hop - M;             // padded-clip coordinate of s_samples[0]
         const int jlo = max(0, -p0);                      // first j with clip index >= 0
         const int jhi = min(span, p.clip_len - p0);       // first j with clip index >= clip_len
         // reflected head / tail (only the first / last CTA of a window has any)
@@ -244,35 +266,19 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
     }
     __syncthreads();
 
-    // ---- per-frame FFT + mel + log ---------------------------------------------------------------
-    const int g = tid / G;
-    const int gt = tid - g * G;
-    float2* buf = reinterpret_cast<float2*>(s_fft + g * C::GROUP_FLOATS);
-    float* power = reinterpret_cast<float*>(buf + C::MPAD);
-    float vmax = -INFINITY, vmin = INFINITY;
-    // twiddles of the cross-lane DIF stages (register FFT path): exp(-2 pi i (lane mod h) / (2h)), h = 16, 8, 4, 2, 1
-    float2 lane_tw[5];
-#pragma unroll
-    for (int st = 0; st < 5; ++st) {
-        const int h = 16 >> st;
-        float sn, cs;
-        sincospif(static_cast<float>(gt & (h - 1)) / static_cast<float>(h), &sn, &cs);
-        lane_tw[st] = make_float2(cs, -sn);
-    }
-    const int iters = (nf + C::NGROUPS - 1) / C::NGROUPS;
-    constexpr int Q = M / 4;
-
+    const int iters = (nfs + C::NGROUPS - 1) / C::NGROUPS;
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
-        const int fl = it * C::NGROUPS + g;              // frame index local to this CTA
-        const bool active = fl < nf;
+        const int fls = it * C::NGROUPS + g;             // frame index local to this round
+        const int fl = sf + fls;                         // frame index local to this CTA
+        const bool active = fls < nfs;
         if constexpr (LOG2M == 8 || LOG2M == 9) {
             constexpr int R = M / 32, LOGR = LOG2M - 5;
             // transposed, padded spectrum: Z[R k1 + k2] lives at zt[k2 * 33 + k1]
             float2* zt = buf;
             if (active) {
-                const float* x = s_samples + fl * p.hop;
-                const bool x_aligned = ((fl * p.hop) & 1) == 0;       // warp-uniform
+                const float* x = s_samples + fls * p.hop;
+                const bool x_aligned = ((fls * p.hop) & 1) == 0;       // warp-uniform
                 float2 v[R];
 #pragma unroll
                 for (int n2 = 0; n2 < R; ++n2) {
@@ -334,8 +340,8 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
         } else {
             // window + pack: z[j] = x[2j] w[2j] + i x[2j+1] w[2j+1]
             if (active) {
-                const float* x = s_samples + fl * p.hop;
-                const bool x_aligned = ((fl * p.hop) & 1) == 0;       // warp-uniform
+                const float* x = s_samples + fls * p.hop;
+                const bool x_aligned = ((fls * p.hop) & 1) == 0;       // warp-uniform
     #pragma unroll
                 for (int i = 0; i < M / G; ++i) {
                     const int j = gt + i * G;
@@ -451,6 +457,7 @@ __global__ void __launch_bounds__(kLogmelThreads) logmel_kernel(const LogmelPara
             }
         }
         group_sync<G>(g);
+    }
     }
 
     // ---- window-global max / min across the cluster ---------------------------------------------
@@ -857,7 +864,8 @@ int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float
     WSB_CHECK_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     pl->cluster = kMaxCluster;
     pl->frames_per_cta = std::max(1, ceil_div(std::max(pl->n_frames, 1), pl->cluster));
-    pl->span_floats = ((pl->frames_per_cta - 1) * hop + n_fft + 3) & ~3;
+    pl->sub_frames = pl->frames_per_cta;
+    pl->span_floats = ((pl->sub_frames - 1) * hop + n_fft + 3) & ~3;
     pl->tile_stride = pl->frames_per_cta | 1;
     std::vector<float> hann(n_fft);
     const int n_tw = 3 * n_fft / 4;
@@ -897,10 +905,17 @@ int logmel_plan_create(int n_fft, int hop, int clip_len, int n_cols, const float
     // shared-memory budget: samples + tile + per-group FFT buffers (+ tables when they fit)
     pl->group_threads = fft_group_threads(pl->log2m);
     pl->n_groups = kLogmelThreads / pl->group_threads;
-    const size_t base_bytes = sizeof(float) * (static_cast<size_t>(pl->span_floats) + ((kMels * pl->tile_stride + 3) & ~3) +
-                                               static_cast<size_t>(pl->n_groups) * (2 * (M + M / 16) + M + 4));
-    const size_t table_bytes = sizeof(float) * (2 * static_cast<size_t>(n_tw) + n_fft + ((wts.size() + 3) & ~size_t(3)));
     const size_t static_bytes = 2048;                   // s_red, s_cluster_red, s_mel + margin
+    const size_t fixed_bytes = sizeof(float) * (((kMels * pl->tile_stride + 3) & ~3) +
+                                                static_cast<size_t>(pl->n_groups) * (2 * (M + M / 16) + M + 4));
+    // large hops: the CTA's frames are staged in rounds of sub_frames frames (whole iterations of n_groups frames) until the
+    // span fits -- e.g. 192 kHz / 0.0025 s (hop 480, n_fft 4096) runs 2 rounds
+    while (sizeof(float) * pl->span_floats + fixed_bytes + static_bytes > static_cast<size_t>(max_smem) && pl->sub_frames > pl->n_groups) {
+        pl->sub_frames = std::max(pl->n_groups, ceil_div(ceil_div(pl->sub_frames, 2), pl->n_groups) * pl->n_groups);
+        pl->span_floats = ((pl->sub_frames - 1) * hop + n_fft + 3) & ~3;
+    }
+    const size_t base_bytes = sizeof(float) * pl->span_floats + fixed_bytes;
+    const size_t table_bytes = sizeof(float) * (2 * static_cast<size_t>(n_tw) + n_fft + ((wts.size() + 3) & ~size_t(3)));
     pl->smem_tables = base_bytes + table_bytes + static_bytes <= static_cast<size_t>(max_smem);
     pl->smem_bytes = base_bytes + (pl->smem_tables ? table_bytes : 0);
     // the one-frame-per-warp kernel stages a CTA's whole sample span: hops of a few hundred samples do not fit; the two-pass
@@ -967,6 +982,7 @@ int logmel_run(const LogmelPlan* pl, const float* audio_dev, const long long* wi
     p.group_threads = pl->group_threads;
     p.n_groups = pl->n_groups;
     p.span_floats = pl->span_floats;
+    p.sub_frames = pl->sub_frames;
     p.tile_stride = pl->tile_stride;
     p.mel_nnz = pl->nnz;
 
