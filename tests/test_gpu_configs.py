@@ -92,6 +92,24 @@ def test_cfg2_whisper_large_two_windows():
     assert conf >= 0.999 and raw >= 0.85
 
 
+@pytest.mark.parametrize("arch,emax_bound,emean_bound", [("small", 0.08, 0.01), ("medium", 0.08, 0.01)])
+def test_other_whisper_sizes(arch, emax_bound, emean_bound):
+    """The published WhisperSeg checkpoints are base and large; the kernels take any Whisper size (head dim 64).  small
+    (768 / 12 layers / 12 heads) and medium (1024 / 24 / 16) on two windows: encoder error, teacher-forced tokens."""
+    import torch
+    from oracle import frontend_np as FO
+    from tools import synth
+    seg, state = _segmenter(arch, 4)
+    audio = synth.synth_audio(5.0, 32000, seed=4)
+    ref_feats = FO.sliced_audio_features(audio, 32000, 0, 0.0025, 1, dtype=np.float32)
+    x = torch.from_numpy(np.asarray([f[2] for f in ref_feats]))
+    raw, conf, n, emax, emean = _teacher_forced(seg, state, x, 40)
+    print("%s: encoder max-abs %.4f mean-abs %.5f; teacher-forced raw %.4f confident %.4f over %d positions"
+          % (arch, emax, emean, raw, conf, n))
+    assert emax <= emax_bound and emean <= emean_bound
+    assert conf >= 0.999 and raw >= 0.85
+
+
 def test_cfg3_zebra_finch_three_trials(tiny_checkpoint):
     from oracle import frontend_np as FO
     from oracle import postprocess_ref as PR

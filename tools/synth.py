@@ -28,6 +28,7 @@ ARCHS = {
     "tiny":  (384, 4, 6, 1536),
     "base":  (512, 6, 8, 2048),
     "small": (768, 12, 12, 3072),
+    "medium": (1024, 24, 16, 4096),
     "large": (1280, 32, 20, 5120),
 }
 VOCAB_SIZE = 51865
@@ -310,7 +311,7 @@ def sinusoids(length, channels, max_timescale=10000):
 # per-architecture EOS boost: deeper networks need a larger one for rows to terminate (tuned on the GPU
 # with tools/tune_large.py: large/3.0 -> median 16, mean ~110 generated tokens, ~5 % of rows never stop)
 ARCH_EOS_RAMP = {"large": 0.1}
-ARCH_EOS_SCALE = {"tiny": 1.3, "base": 1.3, "small": 1.3, "large": 3.0}
+ARCH_EOS_SCALE = {"tiny": 1.3, "base": 1.3, "small": 1.3, "medium": 1.3, "large": 3.0}
 
 
 def make_state(arch="large", seed=0, n_digits=2, eos_scale=None, qk_cross=3.0, qk_self=2.0, emb_std=0.05,
