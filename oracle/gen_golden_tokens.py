@@ -26,7 +26,10 @@ CASES = {
     "large_confident": ("large", dict(confident=True), 600.0, 48000, 0.0025, 2, 240, 64),
     "large_stress32": ("large", dict(), 80.0, 48000, 0.0025, 2, 32, 160),
     "base_confident": ("base", dict(confident=True), 60.0, 16000, 0.01, 1, 6, 64),
-    "tiny_confident": ("tiny", dict(confident=True), 640.0, 16000, 0.01, 11, 64, 64),
+    # tiny: script boost 15 and audio seed 12 -- the default boost (14, seed 11) leaves 3 of the 1600 positions with an oracle
+    # margin below 0.02, coin flips for any bf16 implementation and 0.19 % of a sample on which one flip is 0.06 %; here the
+    # smallest margin is 0.128 (8 positions below 0.2) and the rows still leave the script where the audio says so
+    "tiny_confident": ("tiny", dict(confident=True, script_boost=15.0), 640.0, 16000, 0.01, 12, 64, 64),
 }
 
 
