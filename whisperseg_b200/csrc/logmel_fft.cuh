@@ -16,7 +16,7 @@
 // The Hann window handed in is pre-multiplied by 0.5 (exact), which absorbs the two 1/2 factors of E and O.
 //
 // Everything here is __host__ __device__ so that the index math runs on the CPU too
-// (tests/test_logmel_fft_host.py compiles tests/host/logmel_fft_host.cu and compares with a float64 DFT).
+// (tests/test_logmel_fft_host.py compiles tests/host/logmel_fft_host.cpp and compares with a float64 DFT).
 #pragma once
 #include <cuda_runtime.h>
 
